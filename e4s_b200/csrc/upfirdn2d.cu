@@ -1,0 +1,189 @@
+// upfirdn2d for sm_100a: zero-stuff (up), pad/crop, true 2-D convolution with a small FIR, decimate (down).
+//
+// Replaces upfirdn2d_kernel<> of the reference (src/models/stylegan2/op/upfirdn2d_kernel.cu:52-137),
+// which stages tiles through `volatile` shared memory with scalar loads and 16 MACs per pixel from
+// shared-memory taps.  This op is HBM-bound (8 B of traffic per output element), so the kernel is
+// organised around memory, not math:
+//   * hot configuration (up = down = 1, 4x4 FIR: the Blur after every up-sampling conv and its
+//     gradient): one CTA streams a 128x32 (or 32x128) output tile; the input tile (+3 halo) is
+//     staged once through shared memory with fully coalesced loads, FIR taps live in registers,
+//     every thread produces a 4x4 micro-tile from two conflict-free 128-bit shared loads per input
+//     row and writes 128-bit streaming stores;
+//   * everything else (up = 2 RGB-skip up-sampling, down = 2, odd FIR sizes): a gather kernel with
+//     the read-only path; these carry < 4 % of the op's bytes in the model.
+#include "common.cuh"
+
+namespace {
+
+struct UpfirdnParams {
+    int in_h, in_w, out_h, out_w;
+    int kh, kw;
+    int up_x, up_y, down_x, down_y;
+    int pad_x0, pad_y0;
+};
+
+// ----------------------------------------------------------------------------- generic gather
+__global__ void __launch_bounds__(256) upfirdn2d_gather_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                               const float* __restrict__ fir, UpfirdnParams p,
+                                                               int64_t total) {
+    __shared__ float sk[64];
+    if (threadIdx.x < p.kh * p.kw) sk[threadIdx.x] = fir[threadIdx.x];
+    __syncthreads();
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        int ox = (int)(idx % p.out_w);
+        int64_t t = idx / p.out_w;
+        int oy = (int)(t % p.out_h);
+        int64_t plane = t / p.out_h;
+        const float* xp = x + plane * (int64_t)p.in_h * p.in_w;
+        // position of tap (ky,kx) of the FLIPPED kernel on the zero-stuffed, padded grid
+        int my0 = oy * p.down_y - p.pad_y0;
+        int mx0 = ox * p.down_x - p.pad_x0;
+        float acc = 0.f;
+        for (int ky = 0; ky < p.kh; ++ky) {
+            int my = my0 + ky;
+            if (my < 0 || my % p.up_y != 0) continue;
+            int iy = my / p.up_y;
+            if (iy >= p.in_h) continue;
+            for (int kx = 0; kx < p.kw; ++kx) {
+                int mx = mx0 + kx;
+                if (mx < 0 || mx % p.up_x != 0) continue;
+                int ix = mx / p.up_x;
+                if (ix >= p.in_w) continue;
+                acc += __ldg(xp + (int64_t)iy * p.in_w + ix) * sk[(p.kh - 1 - ky) * p.kw + (p.kw - 1 - kx)];
+            }
+        }
+        y[idx] = acc;
+    }
+}
+
+// ------------------------------------------------------------------- hot path: up=down=1, 4x4 FIR
+// TXN x-threads per tile row, each owning 4 consecutive output columns; 256/TXN y-threads each owning
+// 4 consecutive output rows.
+template <int TXN>
+__global__ void __launch_bounds__(256) upfirdn2d_fir4_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                             const float* __restrict__ fir, UpfirdnParams p,
+                                                             int tiles_x, int tiles_y) {
+    constexpr int TYN = 256 / TXN;
+    constexpr int TW = 4 * TXN, TH = 4 * TYN;
+    constexpr int SW = TW + 4;      // staged columns (TW + 3 needed, rounded to a multiple of 4)
+    constexpr int SH = TH + 3;
+    __shared__ __align__(16) float tile[SH * SW];
+
+    int bid = blockIdx.x;
+    int tile_x = bid % tiles_x;
+    bid /= tiles_x;
+    int tile_y = bid % tiles_y;
+    int64_t plane = bid / tiles_y;
+
+    const int oy0 = tile_y * TH, ox0 = tile_x * TW;
+    const int iy0 = oy0 - p.pad_y0, ix0 = ox0 - p.pad_x0;
+    const float* xp = x + plane * (int64_t)p.in_h * p.in_w;
+
+    // FIR taps in registers, flipped (true convolution, reference kernel.cu:77).
+    float kf[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) kf[a][b] = __ldg(fir + (3 - a) * 4 + (3 - b));
+
+    // Stage the input tile: consecutive threads -> consecutive floats of a row (coalesced); all loads
+    // of a thread are issued before the first shared store so ~18 requests per thread are in flight.
+    constexpr int NELEM = SH * SW;
+    constexpr int NITER = (NELEM + 255) / 256;
+    float stage[NITER];
+#pragma unroll
+    for (int it = 0; it < NITER; ++it) {
+        int e = threadIdx.x + it * 256;
+        int r = e / SW, c = e - r * SW;
+        int iy = iy0 + r, ix = ix0 + c;
+        float v = 0.f;
+        if (e < NELEM && iy >= 0 && iy < p.in_h && ix >= 0 && ix < p.in_w) v = ld_stream_f1(xp + (int64_t)iy * p.in_w + ix);
+        stage[it] = v;
+    }
+#pragma unroll
+    for (int it = 0; it < NITER; ++it) {
+        int e = threadIdx.x + it * 256;
+        if (e < NELEM) tile[e] = stage[it];
+    }
+    __syncthreads();
+
+    const int tx = threadIdx.x % TXN, ty = threadIdx.x / TXN;
+    float acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+        const float4* rowp = reinterpret_cast<const float4*>(&tile[(4 * ty + j) * SW + 4 * tx]);
+        float4 lo = rowp[0], hi = rowp[1];
+        float v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+        for (int orow = 0; orow < 4; ++orow) {
+            int ky = j - orow;
+            if (ky < 0 || ky > 3) continue;
+#pragma unroll
+            for (int oc = 0; oc < 4; ++oc)
+#pragma unroll
+                for (int kx = 0; kx < 4; ++kx) acc[orow][oc] = fmaf(v[oc + kx], kf[ky][kx], acc[orow][oc]);
+        }
+    }
+
+    float* yp = y + plane * (int64_t)p.out_h * p.out_w;
+    const int ox = ox0 + 4 * tx;
+    const bool vec_ok = ((p.out_w & 3) == 0) && (ox + 3 < p.out_w);
+#pragma unroll
+    for (int orow = 0; orow < 4; ++orow) {
+        int oy = oy0 + 4 * ty + orow;
+        if (oy >= p.out_h) continue;
+        float* dst = yp + (int64_t)oy * p.out_w + ox;
+        if (vec_ok) {
+            st_stream_f4(dst, make_float4(acc[orow][0], acc[orow][1], acc[orow][2], acc[orow][3]));
+        } else {
+#pragma unroll
+            for (int oc = 0; oc < 4; ++oc)
+                if (ox + oc < p.out_w) dst[oc] = acc[orow][oc];
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int e4s_upfirdn2d_f32(const float* x, float* y, const float* fir, int planes, int in_h, int in_w,
+                                 int out_h, int out_w, int kh, int kw, int up_x, int up_y, int down_x, int down_y,
+                                 int pad_x0, int pad_x1, int pad_y0, int pad_y1, void* stream) {
+    E4S_REQUIRE(x && y && fir, E4S_ERR_ARG);
+    E4S_REQUIRE(planes > 0 && in_h > 0 && in_w > 0 && kh > 0 && kw > 0, E4S_ERR_ARG);
+    E4S_REQUIRE(up_x > 0 && up_y > 0 && down_x > 0 && down_y > 0, E4S_ERR_ARG);
+    E4S_REQUIRE(kh <= 8 && kw <= 8, E4S_ERR_SHAPE);
+    // out size rule of the reference, upfirdn2d.py:100-101 / upfirdn2d_kernel.cu:167-168
+    int eh = (in_h * up_y + pad_y0 + pad_y1 - kh) / down_y + 1;
+    int ew = (in_w * up_x + pad_x0 + pad_x1 - kw) / down_x + 1;
+    E4S_REQUIRE(eh == out_h && ew == out_w && out_h > 0 && out_w > 0, E4S_ERR_SHAPE);
+    UpfirdnParams p{in_h, in_w, out_h, out_w, kh, kw, up_x, up_y, down_x, down_y, pad_x0, pad_y0};
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool hot = (up_x == 1 && up_y == 1 && down_x == 1 && down_y == 1 && kh == 4 && kw == 4 &&
+                      e4s_aligned16(y));
+    if (hot) {
+        if (out_w > 64) {
+            int tx = (int)e4s_ceil_div(out_w, 128), ty = (int)e4s_ceil_div(out_h, 32);
+            int64_t nblk = (int64_t)tx * ty * planes;
+            E4S_REQUIRE(nblk < (1ll << 31), E4S_ERR_SHAPE);
+            upfirdn2d_fir4_kernel<32><<<(unsigned)nblk, 256, 0, st>>>(x, y, fir, p, tx, ty);
+        } else {
+            int tx = (int)e4s_ceil_div(out_w, 32), ty = (int)e4s_ceil_div(out_h, 128);
+            int64_t nblk = (int64_t)tx * ty * planes;
+            E4S_REQUIRE(nblk < (1ll << 31), E4S_ERR_SHAPE);
+            upfirdn2d_fir4_kernel<8><<<(unsigned)nblk, 256, 0, st>>>(x, y, fir, p, tx, ty);
+        }
+    } else {
+        int64_t total = (int64_t)planes * out_h * out_w;
+        int64_t want = e4s_ceil_div(total, 256);
+        int64_t cap = (int64_t)E4S_NUM_SMS * 32;  // grid-stride: a few waves of 8 CTAs/SM
+        unsigned nblk = (unsigned)(want < cap ? want : cap);
+        upfirdn2d_gather_kernel<<<nblk, 256, 0, st>>>(x, y, fir, p, total);
+    }
+    return e4s_launch_status();
+}

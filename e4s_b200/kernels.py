@@ -1,0 +1,265 @@
+"""Tensor-level wrappers over the C ABI (no autograd here; see stylegan2/op and stylegan2/model).
+
+Conventions: "planar" tensors are ordinary contiguous NCHW; "pixel-major" tensors are contiguous
+[B, H, W, C] (returned to users as ``.permute(0, 3, 1, 2)`` views, i.e. NCHW tensors with
+channels_last strides).  Every function checks device/dtype/contiguity and raises RuntimeError.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import check, ptr, stream_ptr
+
+Tensor = torch.Tensor
+
+
+class LaunchStats:
+    """Counts kernel launches made through the C ABI and, when `timing` is on, brackets every launch with
+    CUDA events on the launching stream (bench.py reads per-kernel device time from here)."""
+    launches = 0
+    timing = False
+    records = []          # (name, work, start_event, end_event); work = algorithmic FLOPs or bytes of the launch
+
+    @classmethod
+    def reset(cls, timing=False):
+        cls.launches, cls.timing, cls.records = 0, timing, []
+
+    @classmethod
+    def summary(cls):
+        """name -> (launches, total_ms, total_work).  Call after torch.cuda.synchronize()."""
+        out = {}
+        for name, work, e0, e1 in cls.records:
+            n, ms, w = out.get(name, (0, 0.0, 0.0))
+            out[name] = (n + 1, ms + e0.elapsed_time(e1), w + work)
+        return out
+
+
+def _call(name, fn, *args, work=0.0):
+    LaunchStats.launches += 1
+    if LaunchStats.timing:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        LaunchStats.records.append((name, work, e0, e1))
+    else:
+        rc = fn(*args)
+    check(rc, name)
+
+
+def _f32c(t: Tensor, what: str) -> Tensor:
+    _lib.require_cuda(t, what)
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def to_pixel_major(x: Tensor) -> Tensor:
+    """Logical NCHW tensor -> contiguous [B, H, W, C] storage (free if x is already channels_last)."""
+    _lib.require_cuda(x)
+    xp = x.permute(0, 2, 3, 1)
+    if xp.is_contiguous() and x.dtype == torch.float32:
+        return xp
+    x = _f32c(x, "input")
+    b, c, h, w = x.shape
+    y = torch.empty((b, h, w, c), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        _call("e4s_planar_to_pixel_f32", _lib.load().e4s_planar_to_pixel_f32, ptr(x), ptr(y), b, c, h, w, stream_ptr())
+    return y
+
+
+def to_planar(x_pm: Tensor) -> Tensor:
+    """Contiguous [B, H, W, C] -> contiguous NCHW."""
+    b, h, w, c = x_pm.shape
+    y = torch.empty((b, c, h, w), device=x_pm.device, dtype=torch.float32)
+    with torch.cuda.device(x_pm.device):
+        _call("e4s_pixel_to_planar_f32", _lib.load().e4s_pixel_to_planar_f32, ptr(x_pm), ptr(y), b, c, h, w, stream_ptr())
+    return y
+
+
+def upfirdn2d_raw(x: Tensor, fir: Tensor, up_x: int, up_y: int, down_x: int, down_y: int, pad_x0: int, pad_x1: int,
+                  pad_y0: int, pad_y1: int) -> Tensor:
+    """x: planar [N, C, H, W] fp32 CUDA.  Mirrors the pybind op upfirdn2d.cpp:12-19 (NCHW instead of
+    the reference's [major, H, W, 1] view)."""
+    x = _f32c(x, "input")
+    fir = _f32c(fir, "kernel")
+    _lib.ensure_device(x)
+    n, c, h, w = x.shape
+    kh, kw = fir.shape
+    out_h = (h * up_y + pad_y0 + pad_y1 - kh) // down_y + 1
+    out_w = (w * up_x + pad_x0 + pad_x1 - kw) // down_x + 1
+    if out_h <= 0 or out_w <= 0:
+        raise RuntimeError(f"upfirdn2d: empty output ({out_h}x{out_w})")
+    y = torch.empty((n, c, out_h, out_w), device=x.device, dtype=torch.float32)
+    if n * c == 0:
+        return y
+    with torch.cuda.device(x.device):
+        _call("e4s_upfirdn2d_f32", _lib.load().e4s_upfirdn2d_f32, ptr(x), ptr(y), ptr(fir), n * c, h, w, out_h, out_w, kh, kw, up_x, up_y,
+                                            down_x, down_y, pad_x0, pad_x1, pad_y0, pad_y1, stream_ptr(),
+              work=4.0 * n * c * (h * w + out_h * out_w))
+    return y
+
+
+def bias_act_fwd(x: Tensor, bias: Optional[Tensor], alpha: float, scale: float) -> Tensor:
+    """scale*lrelu(x + bias[channel]); channel axis is dim 1 of the LOGICAL tensor.  Works on both planar
+    and channels_last storage without a copy."""
+    _lib.require_cuda(x, "input")
+    if bias is not None:
+        _lib.require_cuda(bias, "bias")
+        bias = bias.float().contiguous()
+    if x.dtype != torch.float32:
+        x = x.float()
+    _lib.ensure_device(x)
+    size_b = x.shape[1] if x.ndim > 1 else 1
+    if x.ndim == 4 and not x.is_contiguous() and x.permute(0, 2, 3, 1).is_contiguous():
+        step_b = 1                                    # pixel-major storage: channel is the fastest axis
+        y = torch.empty_like(x)                       # preserves channels_last strides
+    else:
+        x = x.contiguous()
+        step_b = 1
+        for d in x.shape[2:]:
+            step_b *= d
+        y = torch.empty_like(x)
+    n = x.numel()
+    if n:
+        with torch.cuda.device(x.device):
+            _call("e4s_bias_act_fwd_f32", _lib.load().e4s_bias_act_fwd_f32, ptr(x), ptr(bias), ptr(y), n, step_b, size_b, alpha, scale, stream_ptr())
+    return y
+
+
+def _same_storage_order(a: Tensor, like: Tensor) -> Tensor:
+    if a.dtype != torch.float32:
+        a = a.float()
+    if a.stride() == like.stride() and a.shape == like.shape:
+        return a
+    out = torch.empty_like(like)
+    out.copy_(a)
+    return out
+
+
+def bias_act_bwd(grad: Tensor, out: Tensor, alpha: float, scale: float) -> Tensor:
+    """gx = scale * (out > 0 ? g : alpha*g); `out` is the forward output (fused_act.py:27-29)."""
+    grad = _same_storage_order(grad, out)
+    gx = torch.empty_like(out)
+    n = out.numel()
+    if n:
+        with torch.cuda.device(out.device):
+            _call("e4s_bias_act_bwd_f32", _lib.load().e4s_bias_act_bwd_f32, ptr(grad), ptr(out), ptr(gx), n, alpha, scale, stream_ptr())
+    return gx
+
+
+def bias_grad(gx: Tensor) -> Tensor:
+    """Sum over every axis but the channel axis (dim 1)."""
+    c = gx.shape[1]
+    gb = torch.empty((c,), device=gx.device, dtype=torch.float32)
+    if gx.ndim == 4 and not gx.is_contiguous() and gx.permute(0, 2, 3, 1).is_contiguous():
+        outer, step = gx.numel() // c, 1
+    else:
+        gx = gx.contiguous()
+        step = 1
+        for d in gx.shape[2:]:
+            step *= d
+        outer = gx.shape[0]
+    with torch.cuda.device(gx.device):
+        _call("e4s_bias_grad_f32", _lib.load().e4s_bias_grad_f32, ptr(gx), ptr(gb), outer, c, step, stream_ptr())
+    return gb
+
+
+# ------------------------------------------------------------------------------ mask ops
+def onehot_to_label(onehot: Tensor):
+    """[B, ncls, H, W] float one-hot -> ([B, H, W] uint8, device int flag: 1 if not one-hot)."""
+    onehot = _f32c(onehot, "mask")
+    _lib.ensure_device(onehot)
+    b, ncls, h, w = onehot.shape
+    label = torch.empty((b, h, w), device=onehot.device, dtype=torch.uint8)
+    flag = torch.zeros((1,), device=onehot.device, dtype=torch.int32)
+    with torch.cuda.device(onehot.device):
+        _call("e4s_onehot_to_label_u8", _lib.load().e4s_onehot_to_label_u8, ptr(onehot), ptr(label), ptr(flag), b, ncls, h, w, stream_ptr())
+    return label, flag
+
+
+def label_to_onehot(label: Tensor, ncls: int) -> Tensor:
+    """labelMap2OneHot (src/utils/torch_utils.py:166-172).  label: [B,1,H,W] or [B,H,W] integer tensor."""
+    _lib.require_cuda(label, "label")
+    if label.ndim == 4:
+        label = label[:, 0]
+    lab = label.to(torch.uint8).contiguous()
+    b, h, w = lab.shape
+    out = torch.empty((b, ncls, h, w), device=lab.device, dtype=torch.float32)
+    with torch.cuda.device(lab.device):
+        _call("e4s_label_to_onehot_f32", _lib.load().e4s_label_to_onehot_f32, ptr(lab), ptr(out), b, ncls, h, w, stream_ptr())
+    return out
+
+
+def label_resize_nearest(label: Tensor, out_h: int, out_w: int) -> Tensor:
+    label = label.contiguous()
+    b, h, w = label.shape
+    if (h, w) == (out_h, out_w):
+        return label
+    out = torch.empty((b, out_h, out_w), device=label.device, dtype=torch.uint8)
+    with torch.cuda.device(label.device):
+        _call("e4s_label_resize_nearest_u8", _lib.load().e4s_label_resize_nearest_u8, ptr(label), ptr(out), b, h, w, out_h, out_w, stream_ptr())
+    return out
+
+
+def label_remap(label: Tensor, lut: Tensor) -> Tensor:
+    label = label.contiguous()
+    lut = lut.to(device=label.device, dtype=torch.uint8).contiguous()
+    assert lut.numel() == 256
+    out = torch.empty_like(label)
+    with torch.cuda.device(label.device):
+        _call("e4s_label_remap_u8", _lib.load().e4s_label_remap_u8, ptr(label), ptr(out), ptr(lut), label.numel(), stream_ptr())
+    return out
+
+
+def region_mean(feats_pm: Tensor, label: Tensor, ncls: int):
+    """feats_pm: [B, H, W, C] contiguous; label: [B, H, W] uint8 -> ([B, ncls, C], area [B, ncls] int32)."""
+    b, h, w, c = feats_pm.shape
+    out = torch.empty((b, ncls, c), device=feats_pm.device, dtype=torch.float32)
+    area = torch.empty((b, ncls), device=feats_pm.device, dtype=torch.int32)
+    with torch.cuda.device(feats_pm.device):
+        _call("e4s_region_mean_f32", _lib.load().e4s_region_mean_f32, ptr(feats_pm), ptr(label), ptr(out), ptr(area), b, ncls, h, w, c, stream_ptr())
+    return out, area
+
+
+# ------------------------------------------------------------------------------ conv ops
+def demod(s: Tensor, wsq: Tensor, eps: float = 1e-8) -> Tensor:
+    """s: [..., Cin]; wsq: [Cout, Cin] -> [..., Cout] = rsqrt(s^2 @ wsq^T + eps)."""
+    s2 = s.reshape(-1, s.shape[-1]).contiguous()
+    rows, cin = s2.shape
+    cout = wsq.shape[0]
+    out = torch.empty((rows, cout), device=s.device, dtype=torch.float32)
+    with torch.cuda.device(s.device):
+        _call("e4s_demod_f32", _lib.load().e4s_demod_f32, ptr(s2), ptr(wsq), ptr(out), rows, cin, cout, eps, stream_ptr())
+    return out.reshape(*s.shape[:-1], cout)
+
+
+def modconv3x3_fwd(x_pm: Tensor, wt: Tensor, s: Tensor, dm: Optional[Tensor], label: Optional[Tensor],
+                   noise: Optional[Tensor], noise_w: Optional[Tensor], bias: Optional[Tensor], up: bool, act: bool) -> Tensor:
+    """x_pm [B,H,W,Cin]; wt [nphase,9,Cin,Cout]; s [B,ncls,Cin]; dm [B,ncls,Cout]|None; label [B,Ho,Wo] u8|None;
+    noise [B|1, Ho, Wo]|None -> y_pm [B,Ho,Wo,Cout]."""
+    b, h, w, cin = x_pm.shape
+    cout = wt.shape[-1]
+    ncls = s.shape[1]
+    m = 2 if up else 1
+    y = torch.empty((b, h * m, w * m, cout), device=x_pm.device, dtype=torch.float32)
+    nb = noise.shape[0] if noise is not None else 1
+    with torch.cuda.device(x_pm.device):
+        _call("e4s_modconv3x3_fwd_f32", _lib.load().e4s_modconv3x3_fwd_f32, ptr(x_pm), ptr(wt), ptr(s), ptr(dm), ptr(label), ptr(noise), ptr(noise_w),
+                                                 ptr(bias), ptr(y), b, h, w, cin, cout, ncls, int(up), nb, int(act),
+                                                 stream_ptr(), work=2.0 * 9 * cin * cout * b * h * w)
+    return y
+
+
+def torgb_fwd(x_pm: Tensor, wrgb: Tensor, s: Tensor, label: Optional[Tensor], bias: Optional[Tensor],
+              skip: Optional[Tensor], fir: Optional[Tensor]) -> Tensor:
+    """x_pm [B,H,W,Cin]; wrgb [3,Cin]; s [B,ncls,Cin]; skip planar [B,3,H/2,W/2]|None -> planar [B,3,H,W]."""
+    b, h, w, cin = x_pm.shape
+    out = torch.empty((b, 3, h, w), device=x_pm.device, dtype=torch.float32)
+    with torch.cuda.device(x_pm.device):
+        _call("e4s_torgb_fwd_f32", _lib.load().e4s_torgb_fwd_f32, ptr(x_pm), ptr(wrgb), ptr(s), ptr(label), ptr(bias), ptr(skip), ptr(fir), ptr(out),
+                                            b, h, w, cin, s.shape[1], stream_ptr(), work=4.0 * b * h * w * (cin + 3))
+    return out

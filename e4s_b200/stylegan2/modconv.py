@@ -1,0 +1,177 @@
+"""Host side of the region-selected modulated convolutions (label pyramid, weight preparation, autograd).
+
+Reference behaviour being replaced: StyledConv / ToRGB run ``ModulatedConv2d`` once per region and
+mask-sum the results (src/models/stylegan2/model.py:395-398, 434-437).  Here a float one-hot mask
+becomes a uint8 label map once per forward (``LabelPyramid``), each layer selects the style of every
+output pixel's own region inside the kernel, and the modulated weights are never materialised
+(shared-weight form, model.py:245-274).
+"""
+from __future__ import annotations
+
+import math
+import os
+import warnings
+from typing import Dict, Optional, Tuple
+
+import torch
+from torch.autograd import Function
+
+from .. import kernels as K
+
+Tensor = torch.Tensor
+
+
+# =============================================================================== label pyramid
+class LabelPyramid:
+    """uint8 class map of a one-hot region mask plus its nearest-resized copies.
+
+    ``at(h, w)`` equals ``argmax_c F.interpolate(mask, (h, w), mode='nearest')`` (model.py:391, :430):
+    every level is resampled from the ORIGINAL mask, like the reference does, never from another level.
+    """
+
+    _validated: Dict[Tuple, bool] = {}
+
+    def __init__(self, label: Tensor, ncls: int):
+        assert label.dtype == torch.uint8 and label.ndim == 3
+        self.base = label.contiguous()
+        self.ncls = int(ncls)
+        self._levels: Dict[Tuple[int, int], Tensor] = {tuple(label.shape[1:]): self.base}
+
+    @classmethod
+    def from_mask(cls, mask) -> "LabelPyramid":
+        if isinstance(mask, LabelPyramid):
+            return mask
+        if mask.ndim != 4:
+            raise RuntimeError(f"mask must be [B, ncls, H, W], got {tuple(mask.shape)}")
+        if not mask.is_cuda:
+            raise RuntimeError("mask must be a CUDA tensor")
+        label, flag = K.onehot_to_label(mask)
+        key = (mask.data_ptr(), mask._version, tuple(mask.shape), str(mask.device))
+        if os.environ.get("E4S_B200_CHECK_MASK", "1") != "0" and key not in cls._validated:
+            if int(flag.item()) != 0:   # one host sync per distinct mask tensor
+                raise RuntimeError(
+                    "e4s_b200: the region mask is not one-hot (exactly one 1.0 per pixel). The region-selected "
+                    "kernels implement the reference's mask-sum (model.py:395-398) for one-hot masks only.")
+            if len(cls._validated) > 64:
+                cls._validated.clear()
+            cls._validated[key] = True
+        return cls(label, mask.shape[1])
+
+    def at(self, h: int, w: int) -> Tensor:
+        key = (int(h), int(w))
+        if key not in self._levels:
+            self._levels[key] = K.label_resize_nearest(self.base, key[0], key[1])
+        return self._levels[key]
+
+
+# =========================================================================== weight preparation
+def fold_upsample_kernels(weight: Tensor, blur: Tensor) -> Tensor:
+    """Fold conv_transpose2d(stride 2, 3x3) + upfirdn2d(blur 4x4, pad (1,1)) (model.py:287-300) into four
+    3x3 kernels, one per output parity (py, px), acting on the INPUT grid with zero padding 1:
+
+        out[2m+py, 2n+px] = sum_{dy,dx} Weff[py,px][:, :, dy, dx] * x[m+dy-1, n+dx-1]
+        Weff[py,px][dy,dx] = sum_{ky,kx} W[ky,kx] * blur_flipped[2(dy-1)+ky+1-py, 2(dx-1)+kx+1-px]
+
+    (indices outside 0..3 contribute nothing).  weight: [Cout, Cin, 3, 3]; returns [4, Cout, Cin, 3, 3].
+    """
+    assert weight.shape[-1] == 3 and tuple(blur.shape) == (4, 4)
+    bf = torch.flip(blur.to(torch.float64), [0, 1])
+    w64 = weight.to(torch.float64)
+    out = torch.zeros((4,) + tuple(weight.shape), dtype=torch.float64, device=weight.device)
+    for py in range(2):
+        for px in range(2):
+            for dy in range(3):
+                for dx in range(3):
+                    for ky in range(3):
+                        a = 2 * (dy - 1) + ky + 1 - py
+                        if a < 0 or a > 3:
+                            continue
+                        for kx in range(3):
+                            c = 2 * (dx - 1) + kx + 1 - px
+                            if c < 0 or c > 3:
+                                continue
+                            out[py * 2 + px, :, :, dy, dx] += w64[:, :, ky, kx] * bf[a, c]
+    return out.to(torch.float32)
+
+
+class PreparedConv:
+    """Kernel-ready views of one ModulatedConv2d's frozen parameters, rebuilt when the parameter changes."""
+
+    def __init__(self):
+        self.key = None
+        self.wt = None      # [nphase, 9, Cin, Cout] (3x3) - scaled by 1/sqrt(fan_in)
+        self.wsq = None     # [Cout, Cin] sum_k (scale*W)^2
+        self.wrgb = None    # [Cout, Cin] for 1x1 convs
+
+    def get(self, weight: Tensor, upsample: bool, blur: Optional[Tensor]):
+        key = (weight.data_ptr(), weight._version, str(weight.device),
+               None if blur is None else (blur.data_ptr(), blur._version))
+        if key == self.key:
+            return self
+        with torch.no_grad():
+            w = weight.detach().float()[0]                      # [Cout, Cin, k, k]
+            cout, cin, k, _ = w.shape
+            ws = w * (1.0 / math.sqrt(cin * k * k))             # model.py:223-224
+            self.wsq = ws.pow(2).sum((2, 3)).contiguous()
+            if k == 1:
+                self.wrgb = ws[:, :, 0, 0].contiguous()
+                self.wt = None
+            else:
+                if upsample:
+                    wk = fold_upsample_kernels(ws, blur.detach().float())     # [4, Cout, Cin, 3, 3]
+                else:
+                    wk = ws.unsqueeze(0)
+                # -> [nphase, tap, Cin, Cout]
+                self.wt = wk.permute(0, 3, 4, 2, 1).reshape(wk.shape[0], 9, cin, cout).contiguous()
+                self.wrgb = None
+        self.key = key
+        return self
+
+
+_warned_weight_grad = False
+
+
+def warn_frozen(weight: Tensor):
+    global _warned_weight_grad
+    if weight.requires_grad and torch.is_grad_enabled() and not _warned_weight_grad:
+        warnings.warn("e4s_b200: synthesis-network weights are treated as frozen (as Net3 does for inference and "
+                      "inversion, networks.py:69-71); no gradient is produced for them.")
+        _warned_weight_grad = True
+
+
+# ================================================================================== autograd
+class StyledConvFn(Function):
+    """y = act(demod * conv(x*s) + noise_w*noise + bias) on pixel-major tensors; differentiable wrt x, s, noise."""
+
+    @staticmethod
+    def forward(ctx, x_pm, s, noise, noise_w, bias, label, prep, up, demodulate, act):
+        dm = K.demod(s, prep.wsq) if demodulate else None
+        y = K.modconv3x3_fwd(x_pm, prep.wt, s.contiguous(), dm, label, noise, noise_w, bias, up, act)
+        ctx.set_materialize_grads(False)
+        if any(ctx.needs_input_grad[:3]):
+            from . import modconv_bwd
+            modconv_bwd.save_for_styled_backward(ctx, x_pm, s, dm, noise, noise_w, bias, label, prep, up, demodulate, act, y)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        from . import modconv_bwd
+        return modconv_bwd.styled_backward(ctx, gy)
+
+
+class ToRGBFn(Function):
+    """rgb = conv1x1(x*s) + bias + upsample(skip); differentiable wrt x, s, skip."""
+
+    @staticmethod
+    def forward(ctx, x_pm, s, skip, bias, label, prep, fir):
+        out = K.torgb_fwd(x_pm, prep.wrgb, s.contiguous(), label, bias, skip, fir)
+        ctx.set_materialize_grads(False)
+        if any(ctx.needs_input_grad[:3]):
+            from . import modconv_bwd
+            modconv_bwd.save_for_torgb_backward(ctx, x_pm, s, skip, label, prep, fir)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        from . import modconv_bwd
+        return modconv_bwd.torgb_backward(ctx, g)

@@ -1,0 +1,397 @@
+"""Mask-guided StyleGAN2 synthesis network on the e4s_b200 kernels.
+
+Host-side mirror of the generator half of src/models/stylegan2/model.py: same class names, constructor
+arguments, parameter / buffer names and shapes (checkpoint drop-in) and the same
+``forward`` signatures, so ``Net3`` (src/models/networks.py) and the reference scripts run on it
+unchanged.  What differs is the execution:
+
+* every StyledConv / ToRGB is ONE kernel launch for all regions (the reference loops over regions,
+  model.py:395-398 / :434-437), with noise, bias and activation fused into the conv epilogue;
+* activations travel between layers in pixel-major storage (NCHW tensors with channels_last strides);
+* region masks travel as a uint8 label pyramid built once per forward.
+
+Outputs equal the reference's for one-hot masks (tests/test_parity_gpu.py).  The discriminator half of the
+reference file (model.py:670-799) is training-only and out of scope.
+"""
+from __future__ import annotations
+
+import math
+import random
+
+import torch
+from torch import nn
+from torch.nn import functional as F
+
+from .op import FusedLeakyReLU, fused_leaky_relu, upfirdn2d, conv2d_gradfix
+from . import modconv as MC
+from .. import kernels as K
+
+
+class PixelNorm(nn.Module):
+    def forward(self, input):
+        return input * torch.rsqrt(input.pow(2).mean(dim=1, keepdim=True) + 1e-8)
+
+
+def make_kernel(k):
+    """1-D taps -> normalised 2-D FIR (reference make_kernel, model.py:23-31)."""
+    k = torch.as_tensor(k, dtype=torch.float32)
+    if k.ndim == 1:
+        k = torch.outer(k, k)
+    return k / k.sum()
+
+
+class Upsample(nn.Module):
+    def __init__(self, kernel, factor=2):
+        super().__init__()
+        self.factor = factor
+        self.register_buffer("kernel", make_kernel(kernel) * (factor ** 2))
+        p = self.kernel.shape[0] - factor
+        self.pad = ((p + 1) // 2 + factor - 1, p // 2)
+
+    def forward(self, input):
+        return upfirdn2d(input, self.kernel, up=self.factor, down=1, pad=self.pad)
+
+
+class Downsample(nn.Module):
+    def __init__(self, kernel, factor=2):
+        super().__init__()
+        self.factor = factor
+        self.register_buffer("kernel", make_kernel(kernel))
+        p = self.kernel.shape[0] - factor
+        self.pad = ((p + 1) // 2, p // 2)
+
+    def forward(self, input):
+        return upfirdn2d(input, self.kernel, up=1, down=self.factor, pad=self.pad)
+
+
+class Blur(nn.Module):
+    def __init__(self, kernel, pad, upsample_factor=1):
+        super().__init__()
+        kernel = make_kernel(kernel)
+        if upsample_factor > 1:
+            kernel = kernel * (upsample_factor ** 2)
+        self.register_buffer("kernel", kernel)
+        self.pad = pad
+
+    def forward(self, input):
+        return upfirdn2d(input, self.kernel, pad=self.pad)
+
+
+class EqualConv2d(nn.Module):
+    """Plain conv with equalised learning rate (model.py:97-132); used outside the synthesis hot path."""
+
+    def __init__(self, in_channel, out_channel, kernel_size, stride=1, padding=0, bias=True):
+        super().__init__()
+        self.weight = nn.Parameter(torch.randn(out_channel, in_channel, kernel_size, kernel_size))
+        self.scale = 1 / math.sqrt(in_channel * kernel_size ** 2)
+        self.stride = stride
+        self.padding = padding
+        self.bias = nn.Parameter(torch.zeros(out_channel)) if bias else None
+
+    def forward(self, input):
+        return conv2d_gradfix.conv2d(input, self.weight * self.scale, bias=self.bias, stride=self.stride,
+                                     padding=self.padding)
+
+    def __repr__(self):
+        return (f"{self.__class__.__name__}({self.weight.shape[1]}, {self.weight.shape[0]},"
+                f" {self.weight.shape[2]}, stride={self.stride}, padding={self.padding})")
+
+
+class EqualLinear(nn.Module):
+    def __init__(self, in_dim, out_dim, bias=True, bias_init=0, lr_mul=1, activation=None):
+        super().__init__()
+        self.weight = nn.Parameter(torch.randn(out_dim, in_dim).div_(lr_mul))
+        self.bias = nn.Parameter(torch.zeros(out_dim).fill_(bias_init)) if bias else None
+        self.activation = activation
+        self.scale = (1 / math.sqrt(in_dim)) * lr_mul
+        self.lr_mul = lr_mul
+
+    def forward(self, input):
+        w = self.weight * self.scale
+        if self.activation:
+            return fused_leaky_relu(F.linear(input, w), self.bias * self.lr_mul)
+        return F.linear(input, w, bias=None if self.bias is None else self.bias * self.lr_mul)
+
+    def __repr__(self):
+        return f"{self.__class__.__name__}({self.weight.shape[1]}, {self.weight.shape[0]})"
+
+
+class ScaledLeakyReLU(nn.Module):
+    def __init__(self, negative_slope=0.2):
+        super().__init__()
+        self.negative_slope = negative_slope
+
+    def forward(self, input):
+        return F.leaky_relu(input, negative_slope=self.negative_slope) * math.sqrt(2)
+
+
+def _as_nchw_view(y_pm):
+    return y_pm.permute(0, 3, 1, 2)
+
+
+class ModulatedConv2d(nn.Module):
+    """Modulated (and optionally demodulated / up-sampling) convolution, reference model.py:184-320.
+
+    ``forward(input, style)`` takes ONE style per sample ([B, style_dim]) like the reference.  The
+    region-selected entry point used by StyledConv / ToRGB is ``forward_regions``.
+    """
+
+    def __init__(self, in_channel, out_channel, kernel_size, style_dim, demodulate=True, upsample=False,
+                 downsample=False, blur_kernel=[1, 3, 3, 1], fused=True):
+        super().__init__()
+        if downsample:
+            raise NotImplementedError("downsample=True is only used by the discriminator (out of scope)")
+        if kernel_size not in (1, 3):
+            raise NotImplementedError("e4s_b200 kernels cover the 3x3 and 1x1 modulated convs of the generator")
+        self.eps = 1e-8
+        self.kernel_size = kernel_size
+        self.in_channel = in_channel
+        self.out_channel = out_channel
+        self.upsample = upsample
+        self.downsample = downsample
+        if upsample:
+            factor = 2
+            p = (len(blur_kernel) - factor) - (kernel_size - 1)
+            self.blur = Blur(blur_kernel, pad=((p + 1) // 2 + factor - 1, p // 2 + 1), upsample_factor=factor)
+        self.scale = 1 / math.sqrt(in_channel * kernel_size ** 2)
+        self.padding = kernel_size // 2
+        self.weight = nn.Parameter(torch.randn(1, out_channel, in_channel, kernel_size, kernel_size))
+        self.modulation = EqualLinear(style_dim, in_channel, bias_init=1)
+        self.demodulate = demodulate
+        self.fused = fused
+        self._prep = MC.PreparedConv()
+
+    def __repr__(self):
+        return (f"{self.__class__.__name__}({self.in_channel}, {self.out_channel}, {self.kernel_size}, "
+                f"upsample={self.upsample}, downsample={self.downsample})")
+
+    def prepared(self):
+        MC.warn_frozen(self.weight)
+        return self._prep.get(self.weight, self.upsample, self.blur.kernel if self.upsample else None)
+
+    def forward_regions(self, x_pm, styles, label, noise=None, noise_w=None, bias=None, act=False):
+        """x_pm [B,H,W,Cin] pixel-major; styles [B, R, style_dim]; label [B,Ho,Wo] uint8 or None (R == 1)."""
+        s = self.modulation(styles)                                    # [B, R, Cin]   (model.py:276)
+        return MC.StyledConvFn.apply(x_pm, s, noise, noise_w, bias, label, self.prepared(), self.upsample,
+                                     self.demodulate, act)
+
+    def forward(self, input, style):
+        x_pm = K.to_pixel_major(input)
+        if self.kernel_size == 1:
+            if self.out_channel != 3 or self.demodulate:
+                raise NotImplementedError("the 1x1 modulated conv is provided in its ToRGB form (3 outputs, no demod)")
+            s = self.modulation(style).unsqueeze(1)
+            return MC.ToRGBFn.apply(x_pm, s, None, None, None, self.prepared(), None)
+        return _as_nchw_view(self.forward_regions(x_pm, style.unsqueeze(1), None))
+
+
+class NoiseInjection(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.weight = nn.Parameter(torch.zeros(1))
+
+    def forward(self, image, noise=None):
+        if noise is None:
+            b, _, h, w = image.shape
+            noise = image.new_empty(b, 1, h, w).normal_()
+        return image + self.weight * noise
+
+
+class ConstantInput(nn.Module):
+    def __init__(self, channel, size=4):
+        super().__init__()
+        self.input = nn.Parameter(torch.randn(1, channel, size, size))
+
+    def forward(self, input):
+        return self.input.repeat(input.shape[0], 1, 1, 1)
+
+
+def _fusable_noise(noise, b, h, w):
+    return (noise.ndim == 4 and noise.shape[1] == 1 and noise.shape[0] in (1, b)
+            and tuple(noise.shape[2:]) == (h, w))
+
+
+class StyledConv(nn.Module):
+    def __init__(self, in_channel, out_channel, kernel_size, style_dim, upsample=False, blur_kernel=[1, 3, 3, 1],
+                 demodulate=True, mask_op=False):
+        super().__init__()
+        self.conv = ModulatedConv2d(in_channel, out_channel, kernel_size, style_dim, upsample=upsample,
+                                    blur_kernel=blur_kernel, demodulate=demodulate)
+        self.noise = NoiseInjection()
+        self.activate = FusedLeakyReLU(out_channel)
+        self.mask_op = mask_op
+
+    def forward(self, input, style, mask, noise=None):
+        """input [B,Cin,H,W]; style [B,ncls,512] if mask_op else [B,512]; mask one-hot [B,ncls,Hm,Wm] (or a
+        LabelPyramid); noise [B|1,1,Ho,Wo] or None (fresh N(0,1), reference model.py:333)."""
+        x_pm = K.to_pixel_major(input)
+        b, h, w, _ = x_pm.shape
+        ho, wo = (2 * h, 2 * w) if self.conv.upsample else (h, w)
+        if self.mask_op:
+            label = MC.LabelPyramid.from_mask(mask).at(ho, wo)
+            styles = style
+        else:
+            label, styles = None, style.unsqueeze(1)
+        if noise is None:
+            noise = x_pm.new_empty(b, 1, ho, wo).normal_()
+        standard_act = (self.activate.negative_slope == 0.2 and abs(self.activate.scale - 2 ** 0.5) < 1e-12)
+        if _fusable_noise(noise, b, ho, wo) and standard_act:
+            y = self.conv.forward_regions(x_pm, styles, label, noise=noise.contiguous().float(),
+                                          noise_w=self.noise.weight, bias=self.activate.bias, act=True)
+            return _as_nchw_view(y)
+        # unusual noise shapes (e.g. per-channel noise): conv kernel, then the op-level pieces
+        y = _as_nchw_view(self.conv.forward_regions(x_pm, styles, label))
+        return self.activate(self.noise(y, noise=noise))
+
+
+class ToRGB(nn.Module):
+    def __init__(self, in_channel, style_dim, upsample=True, blur_kernel=[1, 3, 3, 1], mask_op=False):
+        super().__init__()
+        if upsample:
+            self.upsample = Upsample(blur_kernel)
+        self.conv = ModulatedConv2d(in_channel, 3, 1, style_dim, demodulate=False)
+        self.bias = nn.Parameter(torch.zeros(1, 3, 1, 1))
+        self.mask_op = mask_op
+
+    def forward(self, input, style, mask, skip=None):
+        x_pm = K.to_pixel_major(input)
+        b, h, w, _ = x_pm.shape
+        if self.mask_op:
+            label = MC.LabelPyramid.from_mask(mask).at(h, w)
+            styles = style
+        else:
+            label, styles = None, style.unsqueeze(1)
+        s = self.conv.modulation(styles)
+        prep = self.conv.prepared()
+        fuse_skip = (skip is not None and tuple(skip.shape[2:]) == (h // 2, w // 2) and h % 2 == 0 and w % 2 == 0
+                     and tuple(self.upsample.kernel.shape) == (4, 4) and self.upsample.pad == (2, 1))
+        if skip is None or fuse_skip:
+            sk = None if skip is None else skip.contiguous().float()
+            fir = None if skip is None else self.upsample.kernel
+            return MC.ToRGBFn.apply(x_pm, s, sk, self.bias.reshape(3), label, prep, fir)
+        out = MC.ToRGBFn.apply(x_pm, s, None, self.bias.reshape(3), label, prep, None)
+        return out + self.upsample(skip)
+
+
+class Generator(nn.Module):
+    """Mask-guided synthesis network (reference Generator, model.py:451-667).
+
+    ``forward`` keeps the reference signature and returns ``(image, latent | None, intermediate_feats)``.
+    Layer i < remaining_layer_idx takes per-region latents ``latent[:, :, i]``; later layers take the
+    global latent ``latent[:, 0, i]`` (model.py:639-657).
+    """
+
+    def __init__(self, size, style_dim, n_mlp, channel_multiplier=2, blur_kernel=[1, 3, 3, 1], lr_mlp=0.01,
+                 split_layer_idx=7, remaining_layer_idx=18):
+        super().__init__()
+        self.split_layer_idx = split_layer_idx
+        self.remaining_layer_idx = remaining_layer_idx
+        self.size = size
+        self.style_dim = style_dim
+
+        mapping = [PixelNorm()]
+        mapping += [EqualLinear(style_dim, style_dim, lr_mul=lr_mlp, activation="fused_lrelu") for _ in range(n_mlp)]
+        self.style = nn.Sequential(*mapping)
+
+        cm = channel_multiplier
+        self.channels = {4: 512, 8: 512, 16: 512, 32: 512, 64: 256 * cm, 128: 128 * cm, 256: 64 * cm, 512: 32 * cm,
+                         1024: 16 * cm}
+        self.log_size = int(math.log(size, 2))
+        self.num_layers = (self.log_size - 2) * 2 + 1
+        self.n_latent = self.log_size * 2 - 2
+        K_ = remaining_layer_idx
+        last_masked_res = 2 + K_ // 2                         # log2 of the last resolution with masked convs
+
+        self.input = ConstantInput(self.channels[4])
+        self.conv1 = StyledConv(self.channels[4], self.channels[4], 3, style_dim, blur_kernel=blur_kernel, mask_op=True)
+        self.to_rgb1 = ToRGB(self.channels[4], style_dim, upsample=False, mask_op=True)
+
+        self.convs = nn.ModuleList()
+        self.upsamples = nn.ModuleList()
+        self.to_rgbs = nn.ModuleList()
+        self.noises = nn.Module()
+        for layer_idx in range(self.num_layers):
+            res = 2 ** ((layer_idx + 5) // 2)
+            self.noises.register_buffer(f"noise_{layer_idx}", torch.randn(1, 1, res, res))
+
+        cin = self.channels[4]
+        for i in range(3, self.log_size + 1):
+            cout = self.channels[2 ** i]
+            masked = i <= last_masked_res
+            self.convs.append(StyledConv(cin, cout, 3, style_dim, upsample=True, blur_kernel=blur_kernel, mask_op=masked))
+            self.convs.append(StyledConv(cout, cout, 3, style_dim, blur_kernel=blur_kernel, mask_op=masked))
+            self.to_rgbs.append(ToRGB(cout, style_dim, mask_op=(K_ == 17 or i < last_masked_res)))
+            cin = cout
+
+    def make_noise(self):
+        device = self.input.input.device
+        noises = [torch.randn(1, 1, 4, 4, device=device)]
+        for i in range(3, self.log_size + 1):
+            noises += [torch.randn(1, 1, 2 ** i, 2 ** i, device=device) for _ in range(2)]
+        return noises
+
+    def mean_latent(self, n_latent):
+        z = torch.randn(n_latent, self.style_dim, device=self.input.input.device)
+        return self.style(z).mean(0, keepdim=True)
+
+    def get_latent(self, input):
+        return self.style(input)
+
+    def _assemble_latent(self, styles, inject_index):
+        if len(styles) < 2:
+            if styles[0].ndim < 4:
+                return styles[0].unsqueeze(1).repeat(1, self.n_latent, 1)
+            return styles[0]
+        if inject_index is None:
+            inject_index = random.randint(1, self.n_latent - 1)
+        first = styles[0].unsqueeze(1).repeat(1, inject_index, 1)
+        second = styles[1].unsqueeze(1).repeat(1, self.n_latent - inject_index, 1)
+        return torch.cat([first, second], 1)
+
+    def forward(self, styles, structure_feats, mask, return_latents=False, inject_index=None, truncation=1,
+                truncation_latent=None, input_is_latent=False, noise=None, randomize_noise=True,
+                use_structure_code=False):
+        if not input_is_latent:
+            styles = [self.style(s) for s in styles]
+        if noise is None:
+            if randomize_noise:
+                noise = [None] * self.num_layers
+            else:
+                noise = [getattr(self.noises, f"noise_{i}") for i in range(self.num_layers)]
+        if truncation < 1:
+            styles = [truncation_latent + truncation * (s - truncation_latent) for s in styles]
+        latent = self._assemble_latent(styles, inject_index)
+        if latent.ndim != 4:
+            raise RuntimeError("the mask-guided generator expects a per-region latent [B, ncls, n_latent, style_dim]")
+
+        K_ = self.remaining_layer_idx
+        regions = MC.LabelPyramid.from_mask(mask)            # one argmax + validation per forward
+        out = self.input(latent)
+        out = self.conv1(out, latent[:, :, 0], regions, noise=noise[0])
+        skip = self.to_rgb1(out, latent[:, :, 1], regions)
+        intermediate_feats = None
+
+        i = 1
+        for r, to_rgb in enumerate(self.to_rgbs):
+            up_conv, conv = self.convs[2 * r], self.convs[2 * r + 1]
+            n_up, n_conv = noise[1 + 2 * r], noise[2 + 2 * r]
+            if i < K_:
+                out = up_conv(out, latent[:, :, i] if up_conv.mask_op else latent[:, 0, i], regions, noise=n_up)
+                if i + 2 == self.split_layer_idx:
+                    if use_structure_code:
+                        out = structure_feats
+                    intermediate_feats = out
+                out = conv(out, latent[:, :, i + 1] if conv.mask_op else latent[:, 0, i + 1], regions, noise=n_conv)
+                if K_ == 17 or i + 2 != K_:
+                    rgb_style = latent[:, :, i + 2] if to_rgb.mask_op else latent[:, 0, i + 2]
+                else:
+                    rgb_style = latent[:, 0, i + 2]
+                skip = to_rgb(out, rgb_style, regions, skip)
+            else:
+                out = up_conv(out, latent[:, 0, i], regions, noise=n_up)
+                out = conv(out, latent[:, 0, i + 1], regions, noise=n_conv)
+                skip = to_rgb(out, latent[:, 0, i + 2], regions, skip)
+            i += 2
+
+        image = skip
+        return image, (latent if return_latents else None), intermediate_feats

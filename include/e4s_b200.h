@@ -1,0 +1,131 @@
+/* e4s_b200 - C ABI of the B200-native E4S synthesis hot path.
+ *
+ * Drop-in boundary.  The reference binds its two native ops through
+ * pybind11 modules JIT-built at import (src/models/stylegan2/op/upfirdn2d.py:8-14,
+ * fused_act.py:9-15) and runs everything else through ATen/cuDNN.  This library replaces
+ * that native layer: plain `extern "C"` functions over raw DEVICE pointers, int shapes and
+ * a cudaStream_t (passed as void*).  Rules common to every entry point:
+ *
+ *   - returns 0 on success, a negative E4S_ERR_* code for a bad argument, or the positive
+ *     cudaError_t of a failed launch; never throws, never allocates, never synchronises;
+ *   - the caller owns every buffer and guarantees the layouts stated per function;
+ *   - re-entrant; enqueues on `stream` of the CURRENT device and returns immediately;
+ *   - all floating-point tensors are fp32, labels are uint8.
+ *
+ * Layout vocabulary: "planar" = [N, C, H, W] contiguous (the reference's NCHW);
+ * "pixel-major" = [N, H, W, C] contiguous (torch channels_last storage of the same
+ * logical NCHW tensor) - the layout the convolution kernels stream.
+ */
+#ifndef E4S_B200_H_
+#define E4S_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define E4S_OK 0
+#define E4S_ERR_ARG (-1)      /* null pointer / non-positive size */
+#define E4S_ERR_SHAPE (-2)    /* unsupported shape (e.g. FIR larger than 8x8) */
+#define E4S_ERR_ALIGN (-3)    /* pointer not aligned as the kernel requires */
+#define E4S_ERR_NOT_ONEHOT (-4)
+#define E4S_ERR_ARCH (-5)     /* device is not sm_100 */
+
+/* Library version: major*10000 + minor*100 + patch. */
+int e4s_version(void);
+/* Static string naming the architecture the kernels were compiled for ("sm_100a"). */
+const char* e4s_build_arch(void);
+/* 0 if the current device can run this library (compute capability 10.x). */
+int e4s_device_ok(void);
+
+/* ---- upfirdn2d ---------------------------------------------------------------------
+ * Replaces upfirdn2d_op / upfirdn2d_kernel, src/models/stylegan2/op/upfirdn2d_kernel.cu:52-272
+ * (pybind surface upfirdn2d.cpp:12-23; Python semantics upfirdn2d.py:85-147).
+ * x: planar [planes, in_h, in_w]; y: planar [planes, out_h, out_w];
+ * fir: [kh, kw] row-major DEVICE pointer (kh, kw <= 8).  The op zero-stuffs by `up`, pads
+ * (negative pad crops), applies a TRUE convolution (kernel flipped) and keeps every
+ * `down`-th sample: out = (in*up + pad0 + pad1 - k)/down + 1, checked against out_h/out_w. */
+int e4s_upfirdn2d_f32(const float* x, float* y, const float* fir, int planes, int in_h, int in_w,
+                      int out_h, int out_w, int kh, int kw, int up_x, int up_y, int down_x, int down_y,
+                      int pad_x0, int pad_x1, int pad_y0, int pad_y1, void* stream);
+
+/* ---- fused bias + leaky ReLU -------------------------------------------------------
+ * Replaces fused_bias_act_op / fused_bias_act_kernel, fused_bias_act_kernel.cu:18-99
+ * (pybind fused_bias_act.cpp:11-21; Python fused_act.py:50-85), act=3 (lrelu).
+ * Forward: y[i] = scale * lrelu(x[i] + bias[(i / step_b) % size_b], alpha); bias may be NULL.
+ * Backward (grad=1): gx[i] = scale * (ref[i] > 0 ? g[i] : alpha * g[i]), ref = forward output. */
+int e4s_bias_act_fwd_f32(const float* x, const float* bias, float* y, int64_t n, int step_b, int size_b,
+                         float alpha, float scale, void* stream);
+int e4s_bias_act_bwd_f32(const float* g, const float* ref, float* gx, int64_t n, float alpha, float scale,
+                         void* stream);
+/* Per-channel sum of gx over everything but the channel axis (grad of bias, fused_act.py:31-36).
+ * gx viewed as [outer, size_b, step_b]; gb[size_b] is overwritten. */
+int e4s_bias_grad_f32(const float* gx, float* gb, int64_t outer, int size_b, int step_b, void* stream);
+
+/* ---- mask / index ops (bit-exact) ---------------------------------------------------
+ * onehot [B, ncls, H, W] float -> label [B, H, W] uint8 (argmax).  *flag (device int, caller
+ * zeroes it) is set to 1 if any pixel is not exactly one-hot (one 1.0, rest 0.0).
+ * Replaces the float mask arithmetic of model.py:391-398 by an index map. */
+int e4s_onehot_to_label_u8(const float* onehot, uint8_t* label, int* flag, int batch, int ncls, int h, int w,
+                           void* stream);
+/* label -> one-hot float, labelMap2OneHot, src/utils/torch_utils.py:166-172. */
+int e4s_label_to_onehot_f32(const uint8_t* label, float* onehot, int batch, int ncls, int h, int w, void* stream);
+/* Nearest resize of a label map with ATen's legacy 'nearest' index rule
+ * (src = min(floor(dst * in/out), in-1), float32), as F.interpolate(mask, mode='nearest') does at
+ * model.py:391,430 and psp_encoders.py:265. */
+int e4s_label_resize_nearest_u8(const uint8_t* src, uint8_t* dst, int batch, int in_h, int in_w, int out_h,
+                                int out_w, void* stream);
+/* Class remap through a 256-entry LUT (device pointer); the CelebAMask-HQ 19->12 conversion of
+ * src/datasets/dataset.py:153-209 is one such table. */
+int e4s_label_remap_u8(const uint8_t* src, uint8_t* dst, const uint8_t* lut256, int64_t n, void* stream);
+/* Region mean pooling, FSEncoder_PSP.get_per_comp_styleCode, psp_encoders.py:264-283.
+ * feats: pixel-major [B, H, W, C]; label: [B, H, W] uint8 (already at feature resolution);
+ * out: [B, ncls, C] (zero for empty regions); area: [B, ncls] int32 scratch/outputs. */
+int e4s_region_mean_f32(const float* feats, const uint8_t* label, float* out, int* area, int batch, int ncls,
+                        int h, int w, int c, void* stream);
+
+/* ---- modulated convolution ----------------------------------------------------------
+ * Demodulation coefficients, model.py:279-281 in the shared-weight form of model.py:245-274:
+ * demod[r, o] = rsqrt(sum_i s[r,i]^2 * wsq[o,i] + eps), wsq[o,i] = sum_k (scale*W[o,i,k])^2.
+ * s: [rows, cin], wsq: [cout, cin], demod: [rows, cout]. */
+int e4s_demod_f32(const float* s, const float* wsq, float* demod, int rows, int cin, int cout, float eps,
+                  void* stream);
+
+/* Region-selected modulated 3x3 convolution with fused noise + bias + leaky-ReLU epilogue:
+ * one call = one StyledConv.forward (model.py:382-406) for every region at once.
+ *
+ *   y[b,p,o] = act( demod[b,c(p),o] * sum_{i,k} wt[ph(p)][k][i][o] * s[b,c(p),i] * x[b,p+k,i]
+ *                   + noise_w * noise[b,p] + bias[o] )
+ *
+ * x: pixel-major [B, H, W, Cin].  y: pixel-major [B, Ho, Wo, Cout] with Ho = H*(up?2:1).
+ * s: [B, ncls, Cin] post-EqualLinear styles (model.py:276); demod: [B, ncls, Cout] or NULL (no
+ * demodulation).  label: [B, Ho, Wo] uint8 class of every OUTPUT pixel, or NULL when ncls == 1
+ * (unmasked layer).  wt: prepared weights [nphase, 9, Cin, Cout], already multiplied by
+ * 1/sqrt(9*Cin); nphase = 1 for the plain conv, 4 for the up-sampling layer where the stride-2
+ * transposed conv and the [1,3,3,1] blur (model.py:287-300) are folded into one 3x3 kernel per
+ * output parity.  noise: [noise_b, Ho, Wo] with noise_b in {1, B}, or NULL;
+ * noise_w: DEVICE pointer to the scalar NoiseInjection.weight; bias: [Cout] or NULL.
+ * act != 0 applies sqrt(2)*lrelu(.,0.2) (FusedLeakyReLU, fused_act.py:72-85). */
+int e4s_modconv3x3_fwd_f32(const float* x, const float* wt, const float* s, const float* demod,
+                           const uint8_t* label, const float* noise, const float* noise_w, const float* bias,
+                           float* y, int batch, int h, int w, int cin, int cout, int ncls, int up, int noise_b,
+                           int act, void* stream);
+
+/* Region-selected 1x1 modulated conv to RGB + bias + up-sampled skip: one ToRGB.forward
+ * (model.py:422-448).  x: pixel-major [B, H, W, Cin]; wrgb: [3, Cin] (already scaled by
+ * 1/sqrt(Cin)); s: [B, ncls, Cin]; label: [B, H, W] or NULL (ncls==1); bias: [3];
+ * skip: planar [B, 3, H/2, W/2] or NULL; fir4x4: the Upsample FIR (model.py:34-53), DEVICE pointer,
+ * may be NULL when skip is NULL; out: planar [B, 3, H, W]. */
+int e4s_torgb_fwd_f32(const float* x, const float* wrgb, const float* s, const uint8_t* label,
+                      const float* bias, const float* skip, const float* fir4x4, float* out, int batch, int h,
+                      int w, int cin, int ncls, void* stream);
+
+/* Layout shuffles between planar and pixel-major (boundary of the module-level API). */
+int e4s_planar_to_pixel_f32(const float* x, float* y, int batch, int c, int h, int w, void* stream);
+int e4s_pixel_to_planar_f32(const float* x, float* y, int batch, int c, int h, int w, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* E4S_B200_H_ */

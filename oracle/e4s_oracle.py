@@ -454,3 +454,50 @@ def synthetic_inputs(batch: int, num_cls: int, size: int, mask_size: int, seed: 
         noise.append(torch.randn(batch, 1, 2 ** i, 2 ** i, generator=g))
         noise.append(torch.randn(batch, 1, 2 ** i, 2 ** i, generator=g))
     return codes, mask, label, noise
+
+
+# ------------------------------------------------------------- replayable golden-case inputs
+MODCONV_CASES = {"plain": (24, 16, 3, True, False, 9), "up": (16, 24, 3, True, True, 6), "rgb": (24, 3, 1, False, False, 8)}
+STYLEDCONV_CASES = {"plain": (16, 24, False, 8), "up": (24, 16, True, 8)}
+
+
+def case_generator(tag: str) -> torch.Generator:
+    return torch.Generator().manual_seed(_key_seed("golden-case/" + tag))
+
+
+def modconv_case(tag: str):
+    """(x [2,cin,hw,hw], latent [2,512]) of golden case modconv/<tag>; shared by make_golden.py and the tests."""
+    cin, _cout, _k, _demod, _up, hw = MODCONV_CASES[tag]
+    g = case_generator("modconv/" + tag)
+    return torch.randn(2, cin, hw, hw, generator=g), torch.randn(2, 512, generator=g)
+
+
+def styledconv_case(tag: str):
+    cin, _cout, up, hw = STYLEDCONV_CASES[tag]
+    g = case_generator("styledconv/" + tag)
+    hout = 2 * hw if up else hw
+    codes, mask, _label, _ = synthetic_inputs(2, 5, 16, 32, seed=3)
+    return torch.randn(2, cin, hw, hw, generator=g), torch.randn(2, 1, hout, hout, generator=g), codes, mask
+
+
+def torgb_case():
+    g = case_generator("torgb")
+    codes, mask, _label, _ = synthetic_inputs(2, 5, 16, 32, seed=3)
+    return torch.randn(2, 24, 16, 16, generator=g), torch.randn(2, 3, 8, 8, generator=g), codes, mask
+
+
+def net3_case():
+    """(style vectors [2,12,1280], latent_avg [18,512], image [1,3,320,320], mask [1,12,256,256])."""
+    g = case_generator("net3")
+    sv = torch.randn(2, 12, 1280, generator=g)
+    latent_avg = 0.5 * torch.randn(18, 512, generator=g)
+    img = torch.randn(1, 3, 320, 320, generator=g)
+    _, mask, _, _ = synthetic_inputs(1, 12, 64, 256, seed=21)
+    return sv, latent_avg, img, mask
+
+
+def region_mean_case():
+    g = case_generator("region_mean")
+    feats = torch.randn(2, 70, 16, 16, generator=g)
+    lab = torch.randint(0, 3, (2, 1, 32, 32), generator=g)     # classes 3, 4 stay empty
+    return feats, label_to_onehot(lab, 5)

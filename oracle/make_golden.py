@@ -135,34 +135,26 @@ def main():
 
     # ------------------------------------------------ ModulatedConv2d variants
     print("ModulatedConv2d / StyledConv / ToRGB")
-    for tag, cin, cout, k, demod, up, hw in [("plain", 24, 16, 3, True, False, 9),
-                                             ("up", 16, 24, 3, True, True, 6),
-                                             ("rgb", 24, 3, 1, False, False, 8)]:
+    for tag, (cin, cout, k, demod, up, hw) in O.MODCONV_CASES.items():
         m = M.ModulatedConv2d(cin, cout, k, 512, demodulate=demod, upsample=up)
-        st = load_synth(m, salt=hash(tag) & 0xFFFF if False else len(tag))
-        x = torch.randn(2, cin, hw, hw, generator=g)
-        w = torch.randn(2, 512, generator=g)
+        st = load_synth(m, salt=len(tag))
+        x, w = O.modconv_case(tag)
         r = m(x, w)
         o = O.modulated_conv2d(x, w, st["weight"], st["modulation.weight"], st["modulation.bias"], demod, up)
         check("modconv/" + tag, r, o)
         gold[f"modconv/{tag}/y"] = r.numpy()
 
-    ncls = 5
-    codes, mask, label, _ = O.synthetic_inputs(2, ncls, 16, 32, seed=3)
-    for tag, cin, cout, up, hw in [("plain", 16, 24, False, 8), ("up", 24, 16, True, 8)]:
+    for tag, (cin, cout, up, hw) in O.STYLEDCONV_CASES.items():
         m = M.StyledConv(cin, cout, 3, 512, upsample=up, mask_op=True)
         st = load_synth(m, salt=7 + len(tag))
-        x = torch.randn(2, cin, hw, hw, generator=g)
-        hout = hw * 2 if up else hw
-        nz = torch.randn(2, 1, hout, hout, generator=g)
+        x, nz, codes, mask = O.styledconv_case(tag)
         r = m(x, codes[:, :, 0], mask, noise=nz)
         o = O.styled_conv(x, codes[:, :, 0], mask, nz, st, "", up, True)
         check("styledconv_masked/" + tag, r, o)
         gold[f"styledconv/{tag}/y"] = r.numpy()
     m = M.ToRGB(24, 512, upsample=True, mask_op=True)
     st = load_synth(m, salt=11)
-    x = torch.randn(2, 24, 16, 16, generator=g)
-    skip = torch.randn(2, 3, 8, 8, generator=g)
+    x, skip, codes, mask = O.torgb_case()
     r = m(x, codes[:, :, 1], mask, skip)
     check("torgb_masked", r, O.to_rgb(x, codes[:, :, 1], mask, skip, st, "", True))
     gold["torgb/y"] = r.numpy()
@@ -203,22 +195,17 @@ def main():
                                  train_G=False, start_from_latent_avg=True, learn_in_w=False)
     net = N.Net3(opts).eval()
     st = load_synth(net, salt=5)
-    net.latent_avg = 0.5 * torch.randn(18, 512, generator=torch.Generator().manual_seed(77))
-    sv = torch.randn(2, 12, 1280, generator=g)
+    sv, latent_avg, img, mask = O.net3_case()
+    net.latent_avg = latent_avg
     r = net.cal_style_codes(sv)
     check("cal_style_codes", r, O.cal_style_codes(st, sv, net.latent_avg, 13))
     gold["net3/style_codes_sub"] = r[:, :, :, ::8].numpy()
-    _, mask, label, _ = O.synthetic_inputs(1, 12, 64, 256, seed=21)
-    img = torch.randn(1, 3, 320, 320, generator=g)
     vec, struct = net.get_style_vectors(img, mask)
     ov, ostruct = O.get_style_vectors(st, img, mask)
     check("get_style_vectors", vec, ov)
     assert struct.shape == ostruct.shape and float(struct.abs().max()) == 0.0
     gold["net3/style_vectors"] = vec.numpy()
-    # region mean alone on an empty-region case (class 3 absent)
-    feats = torch.randn(2, 7, 16, 16, generator=g)
-    lab = torch.randint(0, 3, (2, 1, 32, 32), generator=g)
-    m5 = O.label_to_onehot(lab, 5)
+    feats, m5 = O.region_mean_case()
     r = net.encoder.get_per_comp_styleCode(feats, m5)
     check("region_mean", r, O.region_mean(feats, m5))
     gold["region_mean/y"] = r.numpy()

@@ -1,0 +1,77 @@
+"""Host-side logic that needs no GPU: weight folding, state-dict contract, batched LocalMLPs."""
+import math
+import types
+
+import torch
+import torch.nn.functional as F
+
+from oracle import e4s_oracle as O
+from conftest import assert_close
+
+
+def test_fold_upsample_kernels_matches_convT_plus_blur():
+    """4 parity kernels == conv_transpose2d(stride 2) followed by the [1,3,3,1] blur (model.py:287-300)."""
+    from e4s_b200.stylegan2.modconv import fold_upsample_kernels
+    g = torch.Generator().manual_seed(0)
+    cin, cout, h = 5, 7, 6
+    w = torch.randn(cout, cin, 3, 3, generator=g)
+    x = torch.randn(2, cin, h, h + 1, generator=g)
+    for blur in (O.make_fir((1, 3, 3, 1), 4.0), torch.rand(4, 4, generator=g)):   # symmetric and arbitrary FIR
+        ref = O.upfirdn2d(F.conv_transpose2d(x, w.transpose(0, 1), stride=2), blur, pad=(1, 1))
+        folded = fold_upsample_kernels(w, blur)
+        out = torch.zeros_like(ref)
+        for py in range(2):
+            for px in range(2):
+                out[:, :, py::2, px::2] = F.conv2d(x, folded[py * 2 + px], padding=1)
+        assert_close(out, ref, 1e-5)
+
+
+def test_region_selection_equals_mask_sum():
+    """Selecting each pixel's own-region conv == the reference's sum_c mask_c * conv_c for one-hot masks."""
+    st = O.synthetic_state({"conv.weight": (1, 8, 6, 3, 3), "conv.modulation.weight": (6, 512),
+                            "conv.modulation.bias": (6,), "noise.weight": (1,), "activate.bias": (8,)})
+    codes, mask, label, _ = O.synthetic_inputs(2, 4, 16, 16, seed=4)
+    x = torch.randn(2, 6, 8, 8)
+    nz = torch.randn(2, 1, 16, 16)
+    ref = O.styled_conv(x, codes[:, :, 0], mask, nz, st, "", True, True)
+    seg = O.nearest_resize(mask, 16).argmax(1)
+    per_cls = torch.stack([O.styled_conv(x, codes[:, c, 0], None, nz, st, "", True, False) for c in range(4)], 1)
+    sel = torch.gather(per_cls, 1, seg[:, None, None].expand(-1, 1, 8, -1, -1))[:, 0]
+    assert torch.equal(sel, ref) or float((sel - ref).abs().max()) < 1e-6
+
+
+def test_state_dict_contract():
+    from e4s_b200.networks import Net3
+    opts = types.SimpleNamespace(fsencoder_type="psp", remaining_layer_idx=13, num_seg_cls=12, out_size=64,
+                                 train_G=False, start_from_latent_avg=True, learn_in_w=False)
+    net = Net3(opts)
+    sd = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+    want = {}
+    want.update(O.generator_param_shapes(64, prefix="G."))
+    want.update(O.mlp_param_shapes(12))
+    want.update(O.encoder_param_shapes())
+    for k, shape in want.items():
+        assert sd.get(k) == tuple(shape), (k, sd.get(k), shape)
+    extra = [k for k in sd if k not in want and not k.startswith("G.style.")]
+    assert not extra, extra
+    assert all(not p.requires_grad for p in net.G.parameters())
+
+
+def test_batched_local_mlps_match_oracle():
+    from e4s_b200.networks import Net3
+    opts = types.SimpleNamespace(fsencoder_type="psp", remaining_layer_idx=13, num_seg_cls=12, out_size=32,
+                                 train_G=False, start_from_latent_avg=True, learn_in_w=False)
+    net = Net3(opts).eval()
+    st = O.synthetic_state({k: tuple(v.shape) for k, v in net.state_dict().items()}, salt=5)
+    net.load_state_dict(st)
+    net.latent_avg = 0.5 * torch.randn(18, 512, generator=torch.Generator().manual_seed(77))
+    for p in net.MLPs.parameters():
+        p.requires_grad = False
+    sv = torch.randn(3, 12, 1280, generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        ours = net.cal_style_codes(sv)
+    assert_close(ours, O.cal_style_codes(st, sv, net.latent_avg, 13), 1e-5)
+    # gradient wrt the texture vectors flows through the batched path (inversion optimises them)
+    sv.requires_grad_(True)
+    net.cal_style_codes(sv).square().sum().backward()
+    assert sv.grad is not None and float(sv.grad.abs().sum()) > 0

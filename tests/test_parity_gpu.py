@@ -1,0 +1,292 @@
+"""GPU parity: the sm_100a kernels (through the C ABI) against the committed reference vectors and the CPU oracle.
+
+Bar: max|ours - ref| / max|ref| <= 1e-3 for floating point (north_star), bit-exact for mask / index ops.
+"""
+import math
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import e4s_oracle as O
+from conftest import REL_TOL, assert_close
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def cu(t):
+    return t.to(DEV)
+
+
+# ------------------------------------------------------------------------------------ upfirdn2d
+def test_upfirdn2d_golden(golden):
+    from e4s_b200.stylegan2.op import upfirdn2d
+    for tag in ("blur_up", "skip_up", "blur_dn", "down2", "ragged", "crop"):
+        up, down, p0, p1, gain = golden[f"upfirdn2d/{tag}/cfg"]
+        fir = O.make_fir((1, 3, 3, 1), float(round(gain)))
+        x = torch.from_numpy(golden[f"upfirdn2d/{tag}/x"])
+        y = upfirdn2d(cu(x), cu(fir), up=int(up), down=int(down), pad=(int(p0), int(p1)))
+        assert_close(y, golden[f"upfirdn2d/{tag}/y"], 1e-5, tag)
+    x = torch.from_numpy(golden["upfirdn2d/asym/x"])
+    y = upfirdn2d(cu(x), cu(torch.from_numpy(golden["upfirdn2d/asym/fir"])), up=2, down=1, pad=(2, 1))
+    assert_close(y, golden["upfirdn2d/asym/y"], 1e-5, "asym (kernel flip)")
+
+
+@pytest.mark.parametrize("shape,up,down,pad", [
+    ((2, 3, 33, 33), 1, 1, (1, 1)),      # hot path, odd input (2H+1 -> 2H), narrow tile variant
+    ((1, 2, 257, 257), 1, 1, (1, 1)),    # hot path, wide tile variant, partial tiles
+    ((1, 2, 130, 70), 1, 1, (2, 2)),     # its gradient configuration, non-square
+    ((2, 3, 40, 24), 2, 1, (2, 1)),
+    ((1, 1, 31, 17), 1, 2, (1, 1)),
+    ((1, 2, 5, 5), 1, 1, (1, 1)),        # tiny
+])
+def test_upfirdn2d_vs_oracle(shape, up, down, pad):
+    from e4s_b200.stylegan2.op import upfirdn2d
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(*shape, generator=g)
+    fir = torch.rand(4, 4, generator=g) - 0.3            # arbitrary, non-separable, asymmetric
+    y = upfirdn2d(cu(x), cu(fir), up=up, down=down, pad=pad)
+    assert_close(y, O.upfirdn2d(x, fir, up, down, pad), 1e-5)
+
+
+def test_upfirdn2d_gradients():
+    from e4s_b200.stylegan2.op import upfirdn2d
+    g = torch.Generator().manual_seed(5)
+    for up, down, pad in [(1, 1, (1, 1)), (2, 1, (2, 1)), (1, 2, (1, 1))]:
+        x = torch.randn(2, 3, 12, 10, generator=g)
+        fir = torch.rand(4, 4, generator=g)
+        xr = x.clone().requires_grad_(True)
+        yr = O.upfirdn2d(xr, fir, up, down, pad)
+        go = torch.randn(yr.shape, generator=g)
+        yr.backward(go)
+        xg = cu(x).requires_grad_(True)
+        gog = cu(go).requires_grad_(True)
+        y = upfirdn2d(xg, cu(fir), up=up, down=down, pad=pad)
+        (gx,) = torch.autograd.grad(y, xg, gog, create_graph=True)
+        assert_close(gx, xr.grad, 1e-5, f"grad up{up} down{down}")
+        # second order (upfirdn2d.py:61-82): d<gx, v>/d(grad_output) is the forward op applied to v
+        v = torch.randn(x.shape, generator=g)
+        (gg,) = torch.autograd.grad((gx * cu(v)).sum(), gog)
+        assert_close(gg, O.upfirdn2d(v, fir, up, down, pad), 1e-5, f"double-backward up{up} down{down}")
+
+
+def test_upfirdn2d_full_size_properties():
+    """At BASELINE config-1 size the oracle is too slow; check size-independent properties instead:
+    linearity, DC gain (sum of taps) away from the border, and agreement of the tiled hot kernel with the
+    gather kernel (forced by an equivalent 5x5 zero-padded FIR)."""
+    from e4s_b200.stylegan2.op import upfirdn2d
+    fir = cu(O.make_fir((1, 3, 3, 1), 4.0))
+    x = torch.randn(4, 32, 1025, 1025, device=DEV)
+    z = torch.randn(4, 32, 1025, 1025, device=DEV)
+    y = upfirdn2d(x, fir, pad=(1, 1))
+    assert y.shape == (4, 32, 1024, 1024)
+    lin = upfirdn2d(2.0 * x - 3.0 * z, fir, pad=(1, 1))
+    assert_close(lin, 2.0 * y - 3.0 * upfirdn2d(z, fir, pad=(1, 1)), 1e-5, "linearity")
+    ones = upfirdn2d(torch.ones(1, 1, 1025, 1025, device=DEV), fir, pad=(1, 1))
+    assert torch.allclose(ones[:, :, 2:-2, 2:-2], torch.full_like(ones[:, :, 2:-2, 2:-2], 4.0), atol=1e-5)
+    fir5 = torch.zeros(5, 5, device=DEV)
+    fir5[1:, 1:] = fir                                    # same filter, but kh=kw=5 -> gather kernel
+    sub = x[:1, :4]
+    assert_close(upfirdn2d(sub, fir, pad=(1, 1)), upfirdn2d(sub, fir5, pad=(1, 2)), 1e-5, "tiled vs gather")
+
+
+# ------------------------------------------------------------------------------ fused_leaky_relu
+def test_fused_leaky_relu_golden(golden):
+    from e4s_b200.stylegan2.op import fused_leaky_relu
+    x = cu(torch.from_numpy(golden["flrelu/x"])).requires_grad_(True)
+    b = cu(torch.from_numpy(golden["flrelu/b"])).requires_grad_(True)
+    y = fused_leaky_relu(x, b)
+    assert_close(y, golden["flrelu/y"], 1e-6)
+    y.backward(cu(torch.from_numpy(golden["flrelu/go"])))
+    assert_close(x.grad, golden["flrelu/gx"], 1e-6)
+    assert_close(b.grad, golden["flrelu/gb"], 1e-5)
+
+
+def test_fused_leaky_relu_layouts_and_shapes():
+    from e4s_b200.stylegan2.op import fused_leaky_relu, FusedLeakyReLU
+    g = torch.Generator().manual_seed(2)
+    for shape in [(3, 8), (2, 8, 5, 7), (1, 12, 16, 16), (2, 5, 3, 3)]:
+        x = torch.randn(*shape, generator=g)
+        b = torch.randn(shape[1], generator=g)
+        ref = O.fused_leaky_relu(x, b)
+        assert_close(fused_leaky_relu(cu(x), cu(b)), ref, 1e-6, f"planar {shape}")
+        if len(shape) == 4:
+            xcl = cu(x).contiguous(memory_format=torch.channels_last)
+            assert_close(fused_leaky_relu(xcl, cu(b)), ref, 1e-6, f"channels_last {shape}")
+    m = FusedLeakyReLU(8).to(DEV)
+    assert list(dict(m.named_parameters())) == ["bias"]
+    with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+        fused_leaky_relu(torch.zeros(2, 3), torch.zeros(3))
+
+
+# ------------------------------------------------------------------------------------- mask ops
+def test_mask_ops_bit_exact(golden):
+    from e4s_b200 import kernels as K
+    from e4s_b200.masks import labelMap2OneHot, celeba19_to_12
+    from e4s_b200.stylegan2.modconv import LabelPyramid
+    g = torch.Generator().manual_seed(3)
+    lab = torch.randint(0, 12, (2, 1, 37, 53), generator=g)
+    oh = labelMap2OneHot(cu(lab), 12)
+    assert torch.equal(oh.cpu(), O.label_to_onehot(lab, 12))
+    label, flag = K.onehot_to_label(oh)
+    assert int(flag.item()) == 0 and torch.equal(label.cpu().long(), lab[:, 0])
+    bad = oh.clone()
+    bad[0, :, 0, 0] = 0.5
+    assert int(K.onehot_to_label(bad)[1].item()) == 1
+    with pytest.raises(RuntimeError, match="not one-hot"):
+        LabelPyramid.from_mask(bad)
+    # nearest resize, down and up, power-of-two and ragged ratios
+    oh512 = labelMap2OneHot(cu(torch.randint(0, 12, (1, 1, 96, 96), generator=g)), 12)
+    pyr = LabelPyramid.from_mask(oh512)
+    for s in (4, 8, 16, 32, 48, 96, 192, 100, 7):
+        ref = torch.nn.functional.interpolate(oh512.cpu(), size=(s, s), mode="nearest").argmax(1)
+        assert torch.equal(pyr.at(s, s).cpu().long(), ref), s
+    for who in ("source", "target"):
+        raw = cu(torch.from_numpy(golden[f"mask/{who}_raw19"]))
+        assert np.array_equal(celeba19_to_12(raw).cpu().numpy(), golden[f"mask/{who}_cls12"])
+
+
+def test_region_mean(golden):
+    from e4s_b200.encoders.psp_encoders import FSEncoder_PSP
+    feats, m5 = O.region_mean_case()                       # classes 3 and 4 are empty regions
+    enc = FSEncoder_PSP.__new__(FSEncoder_PSP)
+    out = FSEncoder_PSP.get_per_comp_styleCode(enc, cu(feats), cu(m5))
+    assert_close(out, golden["region_mean/y"], 1e-5)
+    assert float(out[:, 3:].abs().max()) == 0.0
+
+
+# ------------------------------------------------------------- modulated conv building blocks
+def _load(module, salt):
+    st = O.synthetic_state({k: tuple(v.shape) for k, v in module.state_dict().items()}, salt)
+    module.load_state_dict(st)
+    return st
+
+
+def test_modulated_conv_golden(golden):
+    from e4s_b200.stylegan2.model import ModulatedConv2d
+    for tag, (cin, cout, k, demod, up, hw) in O.MODCONV_CASES.items():
+        m = ModulatedConv2d(cin, cout, k, 512, demodulate=demod, upsample=up)
+        _load(m, len(tag))
+        x, w = O.modconv_case(tag)
+        with torch.no_grad():
+            y = m.to(DEV)(cu(x), cu(w))
+        assert_close(y, golden[f"modconv/{tag}/y"], 1e-5, tag)
+
+
+def test_styled_conv_and_torgb_golden(golden):
+    from e4s_b200.stylegan2.model import StyledConv, ToRGB
+    for tag, (cin, cout, up, hw) in O.STYLEDCONV_CASES.items():
+        m = StyledConv(cin, cout, 3, 512, upsample=up, mask_op=True)
+        _load(m, 7 + len(tag))
+        x, nz, codes, mask = O.styledconv_case(tag)
+        with torch.no_grad():
+            y = m.to(DEV)(cu(x), cu(codes[:, :, 0]), cu(mask), noise=cu(nz))
+        assert_close(y, golden[f"styledconv/{tag}/y"], 1e-5, tag)
+    m = ToRGB(24, 512, upsample=True, mask_op=True)
+    _load(m, 11)
+    x, skip, codes, mask = O.torgb_case()
+    with torch.no_grad():
+        y = m.to(DEV)(cu(x), cu(codes[:, :, 1]), cu(mask), cu(skip))
+    assert_close(y, golden["torgb/y"], 1e-5, "torgb")
+
+
+@pytest.mark.parametrize("kind", ["blobs", "iid"])
+def test_styled_conv_and_torgb_vs_oracle(kind):
+    """More shapes than the goldens hold: channel counts that do not fill a tile, mixed-class tiles (iid)."""
+    from e4s_b200.stylegan2.model import StyledConv, ToRGB
+    g = torch.Generator().manual_seed(11)
+    ncls = 5
+    codes, mask, _, _ = O.synthetic_inputs(2, ncls, 16, 32, seed=3, kind=kind)
+    for tag, cin, cout, up, hw in [("plain", 16, 24, False, 8), ("up", 24, 16, True, 8), ("wide", 72, 40, False, 20),
+                                   ("tiny", 8, 8, True, 4)]:
+        m = StyledConv(cin, cout, 3, 512, upsample=up, mask_op=True)
+        st = _load(m, 7 + len(tag))
+        x = torch.randn(2, cin, hw, hw, generator=g)
+        hout = 2 * hw if up else hw
+        nz = torch.randn(2, 1, hout, hout, generator=g)
+        with torch.no_grad():
+            y = m.to(DEV)(cu(x), cu(codes[:, :, 0]), cu(mask), noise=cu(nz))
+        assert_close(y, O.styled_conv(x, codes[:, :, 0], mask, nz, st, "", up, True), 1e-5, f"{kind}/{tag}")
+    for cin in (24, 48, 136):
+        m = ToRGB(cin, 512, upsample=True, mask_op=True)
+        st = _load(m, 11)
+        x = torch.randn(2, cin, 16, 16, generator=g)
+        skip = torch.randn(2, 3, 8, 8, generator=g)
+        with torch.no_grad():
+            y = m.to(DEV)(cu(x), cu(codes[:, :, 1]), cu(mask), cu(skip))
+        assert_close(y, O.to_rgb(x, codes[:, :, 1], mask, skip, st, "", True), 1e-5, f"{kind}/torgb{cin}")
+
+
+# -------------------------------------------------------------------------------- Generator
+def _generator(size, K):
+    from e4s_b200.stylegan2.model import Generator
+    G = Generator(size, 512, 8, split_layer_idx=5, remaining_layer_idx=K).eval()
+    st = O.synthetic_state({k: tuple(v.shape) for k, v in G.state_dict().items()}, salt=size)
+    G.load_state_dict(st)
+    return G.to(DEV), st
+
+
+@pytest.mark.parametrize("tag,size,K,B,nc,msz,kind", [
+    ("g64_k5", 64, 5, 2, 5, 32, "blobs"),
+    ("g32_k13_iid", 32, 13, 1, 12, 64, "iid"),
+    ("g256_k13", 256, 13, 1, 12, 512, "blobs"),          # BASELINE.json configs[0]
+])
+def test_generator_golden(golden, tag, size, K, B, nc, msz, kind):
+    """Same seeded parameters/latents/masks/noise as oracle/make_golden.py fed to the reference."""
+    G, _ = _generator(size, K)
+    codes, mask, _, noise = O.synthetic_inputs(B, nc, size, msz, seed=size + K, kind=kind)
+    with torch.no_grad():
+        img, lat, feats = G([cu(codes)], None, cu(mask), input_is_latent=True, noise=[cu(n) for n in noise])
+    assert lat is None
+    e = assert_close(img, golden[f"generator/{tag}/image"], REL_TOL, tag)
+    assert_close(feats[:, ::16, ::2, ::2], golden[f"generator/{tag}/feats_sub"], REL_TOL, tag + " feats")
+    print(f"{tag}: image max-rel err {e:.2e}")
+
+
+def test_generator_api_surface():
+    G, _ = _generator(32, 13)
+    assert G.n_latent == 8 and G.num_layers == 7 and len(G.convs) == 6 and len(G.to_rgbs) == 3
+    assert [n.shape[-1] for n in G.make_noise()] == [4, 8, 8, 16, 16, 32, 32]
+    codes, mask, _, noise = O.synthetic_inputs(2, 12, 32, 32, seed=1)
+    with torch.no_grad():
+        img, lat, feats = G([cu(codes)], None, cu(mask), input_is_latent=True, return_latents=True)   # fresh noise
+        img2, _, _ = G([cu(codes)], None, cu(mask), input_is_latent=True, randomize_noise=False)
+    assert img.shape == (2, 3, 32, 32) and feats.shape == (2, 512, 16, 16) and lat.shape == codes.shape
+    assert torch.isfinite(img).all() and torch.isfinite(img2).all()
+
+
+def _net3():
+    from e4s_b200.networks import Net3
+    opts = types.SimpleNamespace(fsencoder_type="psp", remaining_layer_idx=13, num_seg_cls=12, out_size=64,
+                                 train_G=False, start_from_latent_avg=True, learn_in_w=False)
+    net = Net3(opts).eval()
+    st = O.synthetic_state({k: tuple(v.shape) for k, v in net.state_dict().items()}, salt=5)
+    net.load_state_dict(st)
+    return net.to(DEV), st
+
+
+def test_net3_gen_img_and_style_codes(golden):
+    net, st = _net3()
+    sv, lat, _, _ = O.net3_case()
+    net.latent_avg = cu(lat)
+    with torch.no_grad():
+        codes = net.cal_style_codes(cu(sv))
+    assert_close(codes[:, :, :, ::8], golden["net3/style_codes_sub"], 1e-4, "cal_style_codes")
+    _, mask, _, noise = O.synthetic_inputs(2, 12, 64, 128, seed=9)
+    gst = {k[2:]: v for k, v in st.items() if k.startswith("G.")}
+    with torch.no_grad():
+        img, minus1, feats = net.gen_img(None, codes, cu(mask), noise=[cu(n) for n in noise])
+    assert minus1 == -1
+    ref_img, _ = O.generator_forward(gst, O.cal_style_codes(st, sv, lat, 13), mask, noise, 64, 13)
+    assert_close(img, ref_img, REL_TOL, "gen_img")
+
+
+def test_get_style_vectors_golden(golden):
+    net, _ = _net3()
+    _, _, img, mask = O.net3_case()
+    with torch.no_grad():
+        vec, struct = net.get_style_vectors(cu(img), cu(mask))
+    assert vec.shape == (1, 12, 1280) and float(struct.abs().max()) == 0.0
+    assert_close(vec, golden["net3/style_vectors"], REL_TOL, "get_style_vectors")
