@@ -1,0 +1,45 @@
+"""Point the reference's import paths at this package, so its scripts run unchanged on the B200 kernels.
+
+    import e4s_b200.dropin; e4s_b200.dropin.install()      # before `from src.models.networks import Net3`
+
+After `install()`, these reference module names resolve to the mirrors in this package:
+
+    src.models.stylegan2.op            -> e4s_b200.stylegan2.op            (upfirdn2d, fused_act, conv2d_gradfix)
+    src.models.stylegan2.model         -> e4s_b200.stylegan2.model         (Generator, StyledConv, ToRGB, ...)
+    src.models.encoders.psp_encoders   -> e4s_b200.encoders.psp_encoders   (FSEncoder_PSP)
+    src.models.encoders.helpers        -> e4s_b200.encoders.helpers
+    src.models.networks                -> e4s_b200.networks                (Net3, LocalMLP)
+    src.utils.torch_utils.labelMap2OneHot is left alone (it already runs on the GPU); e4s_b200.masks has the kernel.
+
+Everything else of the reference tree (scripts, options, datasets, criteria, pretrained/*) keeps importing from
+the reference checkout, which must be on sys.path as usual.
+"""
+import importlib
+import sys
+import types
+
+_MAP = {
+    "src.models.stylegan2.op": "e4s_b200.stylegan2.op",
+    "src.models.stylegan2.op.upfirdn2d": "e4s_b200.stylegan2.op.upfirdn2d",
+    "src.models.stylegan2.op.fused_act": "e4s_b200.stylegan2.op.fused_act",
+    "src.models.stylegan2.op.conv2d_gradfix": "e4s_b200.stylegan2.op.conv2d_gradfix",
+    "src.models.stylegan2.model": "e4s_b200.stylegan2.model",
+    "src.models.encoders.psp_encoders": "e4s_b200.encoders.psp_encoders",
+    "src.models.encoders.helpers": "e4s_b200.encoders.helpers",
+    "src.models.networks": "e4s_b200.networks",
+}
+
+
+def install() -> None:
+    for parent in ("src", "src.models", "src.models.stylegan2", "src.models.encoders"):
+        if parent not in sys.modules:
+            try:
+                importlib.import_module(parent)          # the reference checkout, if it is on sys.path
+            except Exception:
+                sys.modules[parent] = types.ModuleType(parent)
+                sys.modules[parent].__path__ = []        # namespace stand-in
+    for ref_name, ours in _MAP.items():
+        sys.modules[ref_name] = importlib.import_module(ours)
+        parent, _, leaf = ref_name.rpartition(".")
+        if parent in sys.modules:
+            setattr(sys.modules[parent], leaf, sys.modules[ref_name])

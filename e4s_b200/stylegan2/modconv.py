@@ -102,6 +102,7 @@ class PreparedConv:
         self.wt = None      # [nphase, 9, Cin, Cout] (3x3) - scaled by 1/sqrt(fan_in)
         self.wsq = None     # [Cout, Cin] sum_k (scale*W)^2
         self.wrgb = None    # [Cout, Cin] for 1x1 convs
+        self.w_hilo = None  # bf16 [2 (hi, lo), nphase, 9, Cout, Cin] operand planes of the tensor-core kernel
 
     def get(self, weight: Tensor, upsample: bool, blur: Optional[Tensor]):
         key = (weight.data_ptr(), weight._version, str(weight.device),
@@ -124,6 +125,13 @@ class PreparedConv:
                 # -> [nphase, tap, Cin, Cout]
                 self.wt = wk.permute(0, 3, 4, 2, 1).reshape(wk.shape[0], 9, cin, cout).contiguous()
                 self.wrgb = None
+                if K.tc_eligible(cin, cout):
+                    wk_k = wk.permute(0, 3, 4, 1, 2).reshape(wk.shape[0], 9, cout, cin)     # K-major rows [.., Cout, Cin]
+                    hi = wk_k.to(torch.bfloat16)
+                    lo = (wk_k - hi.float()).to(torch.bfloat16)
+                    self.w_hilo = torch.stack([hi, lo]).contiguous()
+                else:
+                    self.w_hilo = None
         self.key = key
         return self
 
@@ -139,6 +147,20 @@ def warn_frozen(weight: Tensor):
         _warned_weight_grad = True
 
 
+DEFAULT_CONV_MODE = "simt"      # flipped to "auto" once the tcgen05 kernel is verified on hardware
+
+
+def use_tensor_cores(prep: "PreparedConv", x_pm: Tensor) -> bool:
+    """Kernel choice for one layer.  E4S_B200_CONV=simt|tc|auto (default auto): the tcgen05 kernel takes every
+    eligible shape from 16x16 up; below that a 128-pixel tile is mostly halo and the fp32 SIMT kernel is used."""
+    mode = os.environ.get("E4S_B200_CONV", DEFAULT_CONV_MODE)
+    if prep.w_hilo is None or mode == "simt":
+        return False
+    if mode == "tc":
+        return True
+    return x_pm.shape[1] * x_pm.shape[2] >= 256
+
+
 # ================================================================================== autograd
 class StyledConvFn(Function):
     """y = act(demod * conv(x*s) + noise_w*noise + bias) on pixel-major tensors; differentiable wrt x, s, noise."""
@@ -146,7 +168,11 @@ class StyledConvFn(Function):
     @staticmethod
     def forward(ctx, x_pm, s, noise, noise_w, bias, label, prep, up, demodulate, act):
         dm = K.demod(s, prep.wsq) if demodulate else None
-        y = K.modconv3x3_fwd(x_pm, prep.wt, s.contiguous(), dm, label, noise, noise_w, bias, up, act)
+        if use_tensor_cores(prep, x_pm):
+            y = K.modconv3x3_tc_fwd(x_pm, prep.w_hilo, s.contiguous(), dm, label, noise, noise_w, bias, up, act,
+                                    shift_mode=int(os.environ.get("E4S_B200_TC_SHIFT_MODE", "0")))
+        else:
+            y = K.modconv3x3_fwd(x_pm, prep.wt, s.contiguous(), dm, label, noise, noise_w, bias, up, act)
         ctx.set_materialize_grads(False)
         if any(ctx.needs_input_grad[:3]):
             from . import modconv_bwd
