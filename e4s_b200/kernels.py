@@ -285,3 +285,43 @@ def torgb_fwd(x_pm: Tensor, wrgb: Tensor, s: Tensor, label: Optional[Tensor], bi
         _call("e4s_torgb_fwd_f32", _lib.load().e4s_torgb_fwd_f32, ptr(x_pm), ptr(wrgb), ptr(s), ptr(label), ptr(bias), ptr(skip), ptr(fir), ptr(out),
                                             b, h, w, cin, s.shape[1], stream_ptr(), work=4.0 * b * h * w * (cin + 3))
     return out
+
+
+# ------------------------------------------------------------------------------ backward
+def modconv3x3_bwd(gy: Tensor, y: Optional[Tensor], x_pm: Optional[Tensor], wd: Tensor, s: Tensor, dm: Optional[Tensor],
+                   label: Optional[Tensor], up: bool, act: bool, need_gx: bool, need_gs: bool):
+    """Returns (gx [B,H,W,Cin] | None, gs_conv [B,ncls,Cin] | None)."""
+    b, ho, wo, cout = gy.shape
+    m = 2 if up else 1
+    h, w = ho // m, wo // m
+    cin = wd.shape[-1]
+    ncls = s.shape[1]
+    gx = torch.empty((b, h, w, cin), device=gy.device, dtype=torch.float32) if need_gx else None
+    gs = torch.zeros((b, ncls, cin), device=gy.device, dtype=torch.float32) if need_gs else None
+    with torch.cuda.device(gy.device):
+        _call("e4s_modconv3x3_bwd_f32", _lib.load().e4s_modconv3x3_bwd_f32, ptr(gy), ptr(y), ptr(x_pm), ptr(wd), ptr(s),
+              ptr(dm), ptr(label), ptr(gx), ptr(gs), b, h, w, cin, cout, ncls, int(up), int(act), stream_ptr(),
+              work=2.0 * 9 * cin * cout * b * h * w)
+    return gx, gs
+
+
+def class_reduce(gy: Tensor, y: Tensor, label: Optional[Tensor], noise: Optional[Tensor], noise_w: Optional[Tensor],
+                 bias: Optional[Tensor], ncls: int, act: bool) -> Tensor:
+    b, ho, wo, cout = gy.shape
+    gdu = torch.zeros((b, ncls, cout), device=gy.device, dtype=torch.float32)
+    nb = noise.shape[0] if noise is not None else 1
+    with torch.cuda.device(gy.device):
+        _call("e4s_class_reduce_f32", _lib.load().e4s_class_reduce_f32, ptr(gy), ptr(y), ptr(label), ptr(noise), ptr(noise_w),
+              ptr(bias), ptr(gdu), b, ncls, ho, wo, cout, nb, int(act), stream_ptr(), work=8.0 * gy.numel())
+    return gdu
+
+
+def torgb_bwd(g: Tensor, x_pm: Tensor, wrgb: Tensor, s: Tensor, label: Optional[Tensor], need_gx: bool, need_gs: bool):
+    b, h, w, cin = x_pm.shape
+    ncls = s.shape[1]
+    gx = torch.empty_like(x_pm) if need_gx else None
+    gs = torch.zeros((b, ncls, cin), device=g.device, dtype=torch.float32) if need_gs else None
+    with torch.cuda.device(g.device):
+        _call("e4s_torgb_bwd_f32", _lib.load().e4s_torgb_bwd_f32, ptr(g), ptr(x_pm), ptr(wrgb), ptr(s), ptr(label), ptr(gx),
+              ptr(gs), b, h, w, cin, ncls, stream_ptr(), work=4.0 * b * h * w * (2 * cin + 3))
+    return gx, gs

@@ -1,0 +1,65 @@
+"""Per-face texture-vector optimisation (inversion) inner loop on the e4s_b200 kernels.
+
+Mirror of the hot loop of ``Optimizer.invertion`` (scripts/optimization.py:209-232) and of its optimiser set-up
+(``setup_W_optimizer`` :125-161): Adam (or sgd / sgdm / adamax) on a clone of the per-region texture vectors
+[1, ncls, 1280]; every step maps them to W+ codes with the LocalMLPs, synthesises the face with fresh noise,
+evaluates the loss against the target image and back-propagates through the generator.
+
+Loss: the reference sums l2 (:98-101) with LPIPS, ArcFace-ID and a parsing-net loss (:92-116), each switchable by
+its lambda.  Those three are third-party pretrained networks (out of scope; section 8f.1 "next") and their
+checkpoints cannot be downloaded here, so this loop provides the l2 term natively and accepts the others as
+callables ``extra_losses = [(weight, fn(recon, target) -> scalar)]``.
+"""
+from __future__ import annotations
+
+from functools import partial
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn.functional as F
+
+OPTIMIZERS = {"sgd": torch.optim.SGD, "adam": torch.optim.Adam, "sgdm": partial(torch.optim.SGD, momentum=0.9),
+              "adamax": torch.optim.Adamax}
+
+
+def setup_W_optimizer(W_init: torch.Tensor, opt_name: str = "adam", lr: float = 1e-2, noise_init=None):
+    """Clone the initial texture vectors (and optionally noise maps) as leaves and build the optimiser."""
+    latent = W_init.clone().detach().requires_grad_(True)
+    params = [latent]
+    noises = None
+    if noise_init is not None:
+        noises = [n.clone().detach().requires_grad_(True) for n in noise_init]
+        params += noises
+    opt = OPTIMIZERS[opt_name](params, lr=lr)
+    return (opt, latent, noises) if noises is not None else (opt, latent)
+
+
+def invert(net, target: torch.Tensor, onehot: torch.Tensor, style_vectors: Optional[torch.Tensor] = None,
+           steps: int = 200, lr: float = 1e-2, opt_name: str = "adam", l2_lambda: float = 1.0,
+           extra_losses: Sequence[Tuple[float, Callable]] = (), noise: Optional[List[torch.Tensor]] = None,
+           callback: Optional[Callable] = None):
+    """Optimise the texture vectors of ONE batch of faces so that net.gen_img reproduces `target`.
+
+    net: e4s_b200.networks.Net3 (eval, latent_avg set).  target [B,3,S,S]; onehot [B,ncls,Hm,Wm].
+    style_vectors: initial [B,ncls,1280] (default: the encoder's, as scripts/optimization.py:178-180).
+    noise: fixed noise list, or None for fresh noise every step (the reference's behaviour, :216).
+    Returns (latent [B,ncls,1280], final reconstruction, list of per-step loss values as 0-d tensors).
+    """
+    if style_vectors is None:
+        with torch.no_grad():
+            style_vectors, _ = net.get_style_vectors(target, onehot)
+    opt, latent = setup_W_optimizer(style_vectors, opt_name, lr)
+    history, recon = [], None
+    for step in range(steps):
+        opt.zero_grad(set_to_none=True)
+        codes = net.cal_style_codes(latent)
+        recon, _, _ = net.gen_img(None, codes, onehot, noise=noise) if noise is not None else net.gen_img(None, codes, onehot)
+        loss = l2_lambda * F.mse_loss(recon, target) if l2_lambda > 0 else recon.new_zeros(())
+        for weight, fn in extra_losses:
+            loss = loss + weight * fn(recon, target)
+        loss.backward()
+        opt.step()
+        history.append(loss.detach())
+        if callback is not None:
+            callback(step, loss, recon, latent)
+    return latent.detach(), recon.detach(), history

@@ -1,18 +1,74 @@
-"""Backward of the fused StyledConv / ToRGB ops (input-, style- and noise-gradients; weights are frozen)."""
+"""Backward of the fused StyledConv / ToRGB ops: input-, style- (and noise-) gradients; weights are frozen.
+
+Math and kernels: csrc/modconv_bwd.cu.  What the reference does instead: autograd through per-region
+F.conv2d / F.conv_transpose2d with per-sample modulated weights (model.py:277-316) - a cuDNN dgrad and wgrad
+per region per layer - plus the elementwise chain of mask-multiply, noise, bias-act.
+"""
 from __future__ import annotations
 
+import torch
 
-def save_for_styled_backward(ctx, *a):
-    raise NotImplementedError("e4s_b200: gradients through StyledConv are not available in this build")
+from .. import kernels as K
+from .op.upfirdn2d import _plan
+
+SQRT2 = 2 ** 0.5
+
+
+def _dgrad_weights(prep):
+    """[nphase, 9, Cin, Cout] forward weights -> [nphase, 9, Cout, Cin] with the taps spatially flipped."""
+    if getattr(prep, "wd", None) is None or prep.wd_key != prep.key:
+        prep.wd = prep.wt.flip(1).permute(0, 1, 3, 2).contiguous()
+        prep.wd_key = prep.key
+    return prep.wd
+
+
+def save_for_styled_backward(ctx, x_pm, s, dm, noise, noise_w, bias, label, prep, up, demodulate, act, y):
+    ctx.save_for_backward(x_pm, s, dm, noise, noise_w, bias, label, y)
+    ctx.cfg = (prep, up, demodulate, act)
 
 
 def styled_backward(ctx, gy):
-    raise NotImplementedError
+    x_pm, s, dm, noise, noise_w, bias, label, y = ctx.saved_tensors
+    prep, up, demodulate, act = ctx.cfg
+    none10 = [None] * 10
+    if gy is None:
+        return tuple(none10)
+    need_gx, need_gs, need_gn = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+    gy = gy.contiguous().float()
+    s = s.contiguous()
+    gx, gs = K.modconv3x3_bwd(gy, y if act else None, x_pm if need_gs else None, _dgrad_weights(prep), s, dm, label,
+                              up, act, need_gx, need_gs)
+    if need_gs and demodulate:
+        # demodulation path: d = rsqrt(s^2 Wsq^T + eps)  ->  d(loss)/ds_i -= s_i * sum_o gdu[o] d[o]^2 Wsq[o,i]
+        gdu = K.class_reduce(gy, y, label, noise, noise_w, bias, s.shape[1], act)
+        gs = gs - s * torch.matmul(gdu * dm * dm, prep.wsq)
+    gn = None
+    if need_gn and noise is not None:
+        gv = gy * torch.where(y > 0, SQRT2, 0.2 * SQRT2) if act else gy
+        gn = (gv.sum(-1) * noise_w).unsqueeze(1)
+        if noise.shape[0] == 1 and gn.shape[0] != 1:
+            gn = gn.sum(0, keepdim=True)
+    none10[0], none10[1], none10[2] = gx, gs, gn
+    return tuple(none10)
 
 
-def save_for_torgb_backward(ctx, *a):
-    raise NotImplementedError("e4s_b200: gradients through ToRGB are not available in this build")
+def save_for_torgb_backward(ctx, x_pm, s, skip, label, prep, fir):
+    ctx.save_for_backward(x_pm, s, label, fir)
+    ctx.cfg = (prep, None if skip is None else tuple(skip.shape))
 
 
 def torgb_backward(ctx, g):
-    raise NotImplementedError
+    x_pm, s, label, fir = ctx.saved_tensors
+    prep, skip_shape = ctx.cfg
+    out = [None] * 7
+    if g is None:
+        return tuple(out)
+    g = g.contiguous().float()
+    need_gx, need_gs, need_gskip = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+    if need_gx or need_gs:
+        out[0], out[1] = K.torgb_bwd(g, x_pm, prep.wrgb, s.contiguous(), label, need_gx, need_gs)
+    if need_gskip and skip_shape is not None:
+        # adjoint of Upsample (upfirdn2d up=2, pad=(2,1), model.py:34-53): flipped FIR, down=2, padding of upfirdn2d.py:108-113
+        _, g_pad = _plan(skip_shape[2], skip_shape[3], 4, 4, (2, 2), (1, 1), (2, 1, 2, 1))
+        out[2] = K.upfirdn2d_raw(g, torch.flip(fir, [0, 1]), 1, 1, 2, 2, *g_pad)
+    return tuple(out)

@@ -132,6 +132,25 @@ int e4s_torgb_fwd_f32(const float* x, const float* wrgb, const float* s, const u
                       const float* bias, const float* skip, const float* fir4x4, float* out, int batch, int h,
                       int w, int cin, int ncls, void* stream);
 
+/* ---- backward (first order; generator weights are frozen, networks.py:69-71) -----------------
+ * Input- and style-gradient of e4s_modconv3x3_fwd_f32 (replaces autograd through F.conv2d/conv_transpose2d with
+ * per-sample weights, model.py:277-316, i.e. one cuDNN dgrad + wgrad per region per layer in the reference).
+ * gy, y: pixel-major [B, Ho, Wo, Cout] (y = forward output, needed when act != 0); x: forward input;
+ * wd: [nphase, 9, Cout, Cin] = forward weights with taps flipped and channels transposed; gx [B, H, W, Cin] is
+ * overwritten (may be NULL); gs [B, ncls, Cin] receives the CONV-PATH style gradient by atomic accumulation
+ * (caller zeroes it; may be NULL).  The demodulation-path term is assembled from e4s_class_reduce_f32. */
+int e4s_modconv3x3_bwd_f32(const float* gy, const float* y, const float* x, const float* wd, const float* s,
+                           const float* demod, const uint8_t* label, float* gx, float* gs, int batch, int h, int w,
+                           int cin, int cout, int ncls, int up, int act, void* stream);
+/* gdu[b,c,o] += sum over pixels of region c of act'(y)*gy * (act^-1(y) - noise_w*noise - bias): the per-region
+ * reduction behind d(loss)/d(demod).  gdu [B, ncls, Cout] is accumulated atomically (caller zeroes it). */
+int e4s_class_reduce_f32(const float* gy, const float* y, const uint8_t* label, const float* noise,
+                         const float* noise_w, const float* bias, float* gdu, int batch, int ncls, int ho, int wo,
+                         int cout, int noise_b, int act, void* stream);
+/* Backward of e4s_torgb_fwd_f32 wrt x and s (the skip gradient is an upfirdn2d call).  g: planar [B, 3, H, W]. */
+int e4s_torgb_bwd_f32(const float* g, const float* x, const float* wrgb, const float* s, const uint8_t* label,
+                      float* gx, float* gs, int batch, int h, int w, int cin, int ncls, void* stream);
+
 /* Layout shuffles between planar and pixel-major (boundary of the module-level API). */
 int e4s_planar_to_pixel_f32(const float* x, float* y, int batch, int c, int h, int w, void* stream);
 int e4s_pixel_to_planar_f32(const float* x, float* y, int batch, int c, int h, int w, void* stream);

@@ -1,0 +1,141 @@
+"""GPU parity of the backward kernels (input/style gradients) and of the inversion loop against the CPU oracle's autograd."""
+import types
+
+import pytest
+import torch
+
+from oracle import e4s_oracle as O
+from conftest import REL_TOL, assert_close
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def cu(t):
+    return t.to(DEV)
+
+
+def _load(module, salt):
+    st = O.synthetic_state({k: tuple(v.shape) for k, v in module.state_dict().items()}, salt)
+    module.load_state_dict(st)
+    for p in module.parameters():
+        p.requires_grad = False
+    return st
+
+
+@pytest.mark.parametrize("kind", ["blobs", "iid"])
+@pytest.mark.parametrize("tag,cin,cout,up,hw,masked", [
+    ("plain", 16, 24, False, 8, True), ("up", 24, 16, True, 8, True), ("wide", 72, 40, False, 12, True),
+    ("global", 32, 32, False, 10, False), ("global_up", 16, 8, True, 6, False)])
+def test_styled_conv_gradients(kind, tag, cin, cout, up, hw, masked):
+    from e4s_b200.stylegan2.model import StyledConv
+    g = torch.Generator().manual_seed(17 + hw)
+    ncls = 5
+    codes, mask, _, _ = O.synthetic_inputs(2, ncls, 16, 32, seed=3, kind=kind)
+    m = StyledConv(cin, cout, 3, 512, upsample=up, mask_op=masked)
+    st = _load(m, 7 + len(tag))
+    x = torch.randn(2, cin, hw, hw, generator=g)
+    style = codes[:, :, 0] if masked else codes[:, 0, 0]
+    hout = 2 * hw if up else hw
+    nz = torch.randn(2, 1, hout, hout, generator=g)
+    go = torch.randn(2, cout, hout, hout, generator=g)
+    # oracle autograd (CPU)
+    xr, sr = x.clone().requires_grad_(True), style.clone().requires_grad_(True)
+    O.styled_conv(xr, sr, mask, nz, st, "", up, masked).backward(go)
+    # ours
+    xg, sg = cu(x).requires_grad_(True), cu(style).requires_grad_(True)
+    y = m.to(DEV)(xg, sg, cu(mask), noise=cu(nz))
+    y.backward(cu(go))
+    assert_close(xg.grad, xr.grad, 1e-4, f"{kind}/{tag} d/dx")
+    assert_close(sg.grad, sr.grad, 1e-4, f"{kind}/{tag} d/dstyle")
+
+
+def test_styled_conv_noise_gradient():
+    from e4s_b200.stylegan2.model import StyledConv
+    g = torch.Generator().manual_seed(5)
+    m = StyledConv(16, 24, 3, 512, mask_op=False)
+    st = _load(m, 3)
+    x, style = torch.randn(2, 16, 8, 8, generator=g), torch.randn(2, 512, generator=g)
+    nz, go = torch.randn(2, 1, 8, 8, generator=g), torch.randn(2, 24, 8, 8, generator=g)
+    nr = nz.clone().requires_grad_(True)
+    O.styled_conv(x, style, None, nr, st, "", False, False).backward(go)
+    ng = cu(nz).requires_grad_(True)
+    m.to(DEV)(cu(x), cu(style), None, noise=ng).backward(cu(go))
+    assert_close(ng.grad, nr.grad, 1e-4, "d/dnoise")
+
+
+@pytest.mark.parametrize("masked", [True, False])
+def test_torgb_gradients(masked):
+    from e4s_b200.stylegan2.model import ToRGB
+    g = torch.Generator().manual_seed(23)
+    codes, mask, _, _ = O.synthetic_inputs(2, 5, 16, 32, seed=3, kind="iid")
+    m = ToRGB(24, 512, upsample=True, mask_op=masked)
+    st = _load(m, 11)
+    x, skip = torch.randn(2, 24, 16, 16, generator=g), torch.randn(2, 3, 8, 8, generator=g)
+    style = codes[:, :, 1] if masked else codes[:, 0, 1]
+    go = torch.randn(2, 3, 16, 16, generator=g)
+    xr, sr, kr = x.clone().requires_grad_(True), style.clone().requires_grad_(True), skip.clone().requires_grad_(True)
+    O.to_rgb(xr, sr, mask, kr, st, "", masked).backward(go)
+    xg, sg, kg = cu(x).requires_grad_(True), cu(style).requires_grad_(True), cu(skip).requires_grad_(True)
+    m.to(DEV)(xg, sg, cu(mask), kg).backward(cu(go))
+    assert_close(xg.grad, xr.grad, 1e-4, "d/dx")
+    assert_close(sg.grad, sr.grad, 1e-4, "d/dstyle")
+    assert_close(kg.grad, kr.grad, 1e-4, "d/dskip")
+
+
+def test_generator_gradient_golden(golden):
+    """d<image, R>/d(codes) for the 32x32, K=13, iid-mask case - the reference's own autograd result."""
+    from e4s_b200.stylegan2.model import Generator
+    size, K = 32, 13
+    G = Generator(size, 512, 8, split_layer_idx=5, remaining_layer_idx=K).eval()
+    _load(G, size)
+    G = G.to(DEV)
+    codes, mask, _, noise = O.synthetic_inputs(1, 12, size, 64, seed=size + K, kind="iid")
+    cg = cu(codes).requires_grad_(True)
+    img, _, _ = G([cg], None, cu(mask), input_is_latent=True, noise=[cu(n) for n in noise])
+    R = torch.randn(img.shape, generator=torch.Generator().manual_seed(99))
+    (img * cu(R)).sum().backward()
+    assert_close(cg.grad, golden["generator/g32_k13_iid/dcodes"], REL_TOL, "dcodes")
+
+
+def test_inversion_loop_matches_oracle():
+    """Three Adam steps of the texture-vector optimisation (scripts/optimization.py:209-232, l2 term, fixed noise):
+    losses and the updated latent against the same loop run through the CPU oracle."""
+    from e4s_b200.networks import Net3
+    from e4s_b200.optimization import invert
+    size, ncls, K = 32, 12, 13
+    opts = types.SimpleNamespace(fsencoder_type="psp", remaining_layer_idx=K, num_seg_cls=ncls, out_size=size,
+                                 train_G=False, start_from_latent_avg=True, learn_in_w=False)
+    net = Net3(opts).eval()
+    st = O.synthetic_state({k: tuple(v.shape) for k, v in net.state_dict().items()}, salt=5)
+    net.load_state_dict(st)
+    for p in net.parameters():
+        p.requires_grad = False
+    net = net.to(DEV)
+    lat = 0.1 * torch.randn(18, 512, generator=torch.Generator().manual_seed(77))
+    net.latent_avg = cu(lat)
+    g = torch.Generator().manual_seed(8)
+    sv0 = 0.5 * torch.randn(1, ncls, 1280, generator=g)
+    _, mask, _, noise = O.synthetic_inputs(1, ncls, size, 64, seed=12)
+    gst = {k[2:]: v for k, v in st.items() if k.startswith("G.")}
+    with torch.no_grad():
+        target, _ = O.generator_forward(gst, O.cal_style_codes(st, 0.5 * torch.randn(1, ncls, 1280, generator=g), lat, K),
+                                        mask, noise, size, K)
+    # oracle loop
+    latent = sv0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([latent], lr=1e-2)
+    ref_losses = []
+    for _ in range(3):
+        opt.zero_grad()
+        rec, _ = O.generator_forward(gst, O.cal_style_codes(st, latent, lat, K), mask, noise, size, K)
+        loss = torch.nn.functional.mse_loss(rec, target)
+        loss.backward()
+        opt.step()
+        ref_losses.append(float(loss))
+    out_latent, recon, hist = invert(net, cu(target), cu(mask), style_vectors=cu(sv0), steps=3, lr=1e-2,
+                                     noise=[cu(n) for n in noise])
+    ours = [float(h) for h in hist]
+    for a, b in zip(ours, ref_losses):
+        assert abs(a - b) <= 1e-3 * abs(b), (ours, ref_losses)
+    assert_close(out_latent, latent.detach(), 1e-3, "latent after 3 Adam steps")
+    assert ours[-1] < ours[0]
