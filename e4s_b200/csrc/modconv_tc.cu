@@ -125,6 +125,7 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 // start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | base_offset [49,52) | layout [61,64) (2 = SW128)
 __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr, uint32_t base_offset) {
     uint64_t d = (uint64_t)((addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;                       // LBO = 16 B (canonical K-major value; unused by swizzled layouts)
     d |= (uint64_t)(1024u >> 4) << 32;
     d |= (uint64_t)1 << 46;
     d |= (uint64_t)(base_offset & 7u) << 49;

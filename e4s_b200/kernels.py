@@ -63,6 +63,8 @@ def to_pixel_major(x: Tensor) -> Tensor:
     xp = x.permute(0, 2, 3, 1)
     if xp.is_contiguous() and x.dtype == torch.float32:
         return xp
+    if x.requires_grad and torch.is_grad_enabled():
+        return xp.float().contiguous()             # module-boundary path: let autograd track the layout change
     x = _f32c(x, "input")
     b, c, h, w = x.shape
     y = torch.empty((b, h, w, c), device=x.device, dtype=torch.float32)
@@ -261,7 +263,7 @@ def tc_eligible(cin: int, cout: int) -> bool:
 
 def modconv3x3_tc_fwd(x_pm: Tensor, w_hilo: Tensor, s: Tensor, dm: Optional[Tensor], label: Optional[Tensor],
                       noise: Optional[Tensor], noise_w: Optional[Tensor], bias: Optional[Tensor], up: bool, act: bool,
-                      shift_mode: int = 0) -> Tensor:
+                      shift_mode: int = 1) -> Tensor:
     """Tensor-core path; w_hilo: bf16 [2, nphase, 9, Cout, Cin].  Same contract as modconv3x3_fwd."""
     b, h, w, cin = x_pm.shape
     cout = w_hilo.shape[3]

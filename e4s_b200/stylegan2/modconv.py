@@ -170,7 +170,7 @@ class StyledConvFn(Function):
         dm = K.demod(s, prep.wsq) if demodulate else None
         if use_tensor_cores(prep, x_pm):
             y = K.modconv3x3_tc_fwd(x_pm, prep.w_hilo, s.contiguous(), dm, label, noise, noise_w, bias, up, act,
-                                    shift_mode=int(os.environ.get("E4S_B200_TC_SHIFT_MODE", "0")))
+                                    shift_mode=int(os.environ.get("E4S_B200_TC_SHIFT_MODE", "1")))
         else:
             y = K.modconv3x3_fwd(x_pm, prep.wt, s.contiguous(), dm, label, noise, noise_w, bias, up, act)
         ctx.set_materialize_grads(False)

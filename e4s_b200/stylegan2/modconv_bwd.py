@@ -36,8 +36,10 @@ def styled_backward(ctx, gy):
     need_gx, need_gs, need_gn = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
     gy = gy.contiguous().float()
     s = s.contiguous()
-    gx, gs = K.modconv3x3_bwd(gy, y if act else None, x_pm if need_gs else None, _dgrad_weights(prep), s, dm, label,
-                              up, act, need_gx, need_gs)
+    gx = gs = None
+    if need_gx or need_gs:
+        gx, gs = K.modconv3x3_bwd(gy, y if act else None, x_pm if need_gs else None, _dgrad_weights(prep), s, dm, label,
+                                  up, act, need_gx, need_gs)
     if need_gs and demodulate:
         # demodulation path: d = rsqrt(s^2 Wsq^T + eps)  ->  d(loss)/ds_i -= s_i * sum_o gdu[o] d[o]^2 Wsq[o,i]
         gdu = K.class_reduce(gy, y, label, noise, noise_w, bias, s.shape[1], act)

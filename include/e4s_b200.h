@@ -116,8 +116,9 @@ int e4s_modconv3x3_fwd_f32(const float* x, const float* wt, const float* s, cons
  * cin % 64 == 0 and cout in {32, 64, 128, 256, 384, 512, ...}.  Weights arrive pre-split into bf16 planes
  * w_hilo_bf16 = [2 (hi, lo)][nphase][9][Cout][Cin] with w = hi + lo to ~2^-17 relative (prepared once);
  * activations are split on the fly, three bf16 MMAs per tap accumulate in fp32 (error ~1e-5 relative to fp32).
- * shift_mode selects how tap-shifted operand descriptors encode their swizzle phase (0 = base_offset field,
- * the documented form; 1 = none) - a self-test knob, callers pass 0. */
+ * shift_mode selects how tap-shifted operand descriptors encode their swizzle phase: 1 = start address only (the
+ * swizzle is a function of absolute shared-memory address bits - verified on B200), 0 = also set the descriptor's
+ * base_offset field (wrong on B200; kept as a self-test knob).  Callers pass 1. */
 int e4s_modconv3x3_tc_fwd(const float* x, const void* w_hilo_bf16, const float* s, const float* demod,
                           const uint8_t* label, const float* noise, const float* noise_w, const float* bias,
                           float* y, int batch, int h, int w, int cin, int cout, int ncls, int up, int noise_b,

@@ -121,21 +121,29 @@ def test_inversion_loop_matches_oracle():
     with torch.no_grad():
         target, _ = O.generator_forward(gst, O.cal_style_codes(st, 0.5 * torch.randn(1, ncls, 1280, generator=g), lat, K),
                                         mask, noise, size, K)
-    # oracle loop
-    latent = sv0.clone().requires_grad_(True)
-    opt = torch.optim.Adam([latent], lr=1e-2)
-    ref_losses = []
-    for _ in range(3):
-        opt.zero_grad()
-        rec, _ = O.generator_forward(gst, O.cal_style_codes(st, latent, lat, K), mask, noise, size, K)
-        loss = torch.nn.functional.mse_loss(rec, target)
-        loss.backward()
-        opt.step()
-        ref_losses.append(float(loss))
-    out_latent, recon, hist = invert(net, cu(target), cu(mask), style_vectors=cu(sv0), steps=3, lr=1e-2,
-                                     noise=[cu(n) for n in noise])
-    ours = [float(h) for h in hist]
-    for a, b in zip(ours, ref_losses):
-        assert abs(a - b) <= 1e-3 * abs(b), (ours, ref_losses)
-    assert_close(out_latent, latent.detach(), 1e-3, "latent after 3 Adam steps")
-    assert ours[-1] < ours[0]
+    # oracle loops: Adam for the loss trajectory (its sign-like first steps amplify 1e-7 gradient noise on
+    # near-zero-gradient coordinates, so latents are compared under plain SGD, which is linear in the gradient)
+    def oracle_loop(opt_name, lr):
+        latent = sv0.clone().requires_grad_(True)
+        opt = (torch.optim.Adam if opt_name == "adam" else torch.optim.SGD)([latent], lr=lr)
+        losses = []
+        for _ in range(3):
+            opt.zero_grad()
+            rec, _ = O.generator_forward(gst, O.cal_style_codes(st, latent, lat, K), mask, noise, size, K)
+            loss = torch.nn.functional.mse_loss(rec, target)
+            loss.backward()
+            opt.step()
+            losses.append(float(loss.detach()))
+        return latent.detach(), losses
+
+    for opt_name, lr in (("adam", 1e-2), ("sgd", 50.0)):
+        ref_latent, ref_losses = oracle_loop(opt_name, lr)
+        out_latent, recon, hist = invert(net, cu(target), cu(mask), style_vectors=cu(sv0), steps=3, lr=lr, opt_name=opt_name,
+                                         noise=[cu(n) for n in noise])
+        ours = [float(h) for h in hist]
+        for a, b in zip(ours, ref_losses):
+            assert abs(a - b) <= 1e-3 * abs(b), (opt_name, ours, ref_losses)
+        if opt_name == "sgd":
+            assert_close(out_latent - cu(sv0), ref_latent - sv0, 2e-3, "SGD update of the texture vectors after 3 steps")
+        else:
+            assert ours[-1] < ours[0]
