@@ -1,0 +1,570 @@
+// Region-selected modulated 3x3 convolution on tcgen05 tensor cores - persistent, fully pipelined version (sm_100a).
+//
+// Same contract and the same implicit-GEMM formulation as modconv_tc.cu (read its header first: 8x16 pixel tile
+// with 14 valid columns, taps as row-shifted descriptors over ONE staged halo tile, split-bf16 x3 accumulation,
+// one main-loop pass per region present in the tile).  What changes is the execution structure - the v1 kernel
+// runs load -> transform -> MMA -> epilogue serially inside a one-tile CTA, which ncu shows at 24-60 % tensor
+// pipe and ~9 % warp occupancy (profiles/r1_ncu_tc_v1_summary.md):
+//
+//   * persistent CTAs (one per SM) walk a static list of work items (pixel tile x N tile), so the pipeline never
+//     drains between tiles;
+//   * ten warps in four roles: 0 = TMA producer of weight planes, 1 = MMA issuer / TMEM owner, 2-5 = activation
+//     transform (A producers), 6-9 = epilogue.  Transform of the next item overlaps the MMAs of the current one,
+//     and the accumulator is double-buffered in TMEM (2 x N columns) so the epilogue of pass i overlaps the MMAs
+//     of pass i+1;
+//   * up-sampling layers put the four output parities along N: D[128 x 4*NTc] - the halo tile is staged and
+//     transformed once for all four parity kernels (v1 did it four times in four CTAs);
+//   * weight planes are ring slots of one (tap, hi|lo) plane each; MMA order per tap is (Ahi,Alo) x Bhi then
+//     Ahi x Blo, so a slot is released as soon as its plane is consumed.  When every plane of the CTA's N tile fits
+//     in the ring (the 32->32 layer at 1024^2: 36 KB) the weights are loaded once and stay resident;
+//   * K chunks of 64 channels (128-byte swizzle) or 32 channels (64-byte swizzle, for Cin = 32).
+//
+// Swizzle phase of row-shifted descriptors: the MMA unit applies the swizzle XOR to ABSOLUTE shared-memory address
+// bits, so a start address moved by whole rows needs nothing else (base_offset = 0) - established on hardware,
+// profiles/r1_tc_probe.log.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace tcp {
+
+constexpr int TH = 8, TWP = 16, TW = 14;
+constexpr int A_ROWS = 168;                   // 160 halo rows + 1 leading row + slack; keeps planes 1024-B aligned
+constexpr int NSTAGE_A = 2;
+constexpr int NUM_THREADS = 320;              // 10 warps
+constexpr int NUM_XFORM = 128, NUM_EPI = 128;
+constexpr int SMEM_BUDGET = 227 * 1024 - 2048;
+
+struct Params {
+    const float* x;
+    const float* s;
+    const float* demod;
+    const uint8_t* label;
+    const float* noise;
+    const float* noise_w;
+    const float* bias;
+    float* y;
+    int batch, h, w, cin, cout, ncls, noise_b, act;
+    int tiles_x, tiles_y, n_tiles, items, nslot_b, resident;
+};
+
+// ------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug traps (clean CUDA error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    for (;;) {
+#pragma unroll 1
+        for (int i = 0; i < 256; ++i)
+            if (mbar_try_wait(bar, parity)) return;
+        if (clock64() - t0 > 8000000000ll) __trap();
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+        "l"(map), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// K-major operand descriptor (cute::UMMA::SmemDescriptor): 128-B swizzle -> 8-row atoms 1024 B apart, layout code 2;
+// 64-B swizzle -> 8-row atoms 512 B apart, layout code 4.
+template <int KC>
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
+    uint64_t d = (uint64_t)((addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)((KC == 64 ? 1024u : 512u) >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)(KC == 64 ? 2 : 4) << 61;
+    return d;
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo_elem, float hi_elem) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+    return r;
+}
+__device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+// Work item -> coordinates.  Pixel tile is the fastest index so that all SMs stream the same weight planes together.
+struct Item {
+    int b, ty, tx, nt;
+};
+__device__ __forceinline__ Item decode_item(const Params& p, int it) {
+    Item r;
+    const int ptiles = p.tiles_x * p.tiles_y * p.batch;
+    r.nt = it / ptiles;
+    int pt = it - r.nt * ptiles;
+    r.tx = pt % p.tiles_x;
+    pt /= p.tiles_x;
+    r.ty = pt % p.tiles_y;
+    r.b = pt / p.tiles_y;
+    return r;
+}
+
+// Classes present among the valid output pixels of a tile, computed by one whole warp (every role recomputes it:
+// ~450 byte loads from L1/L2 per tile, and no cross-role broadcast is needed).
+template <int NPH>
+__device__ __forceinline__ uint32_t tile_class_mask(const Params& p, const Item& it, int lane) {
+    if (!p.label) return 1u;
+    constexpr int MUL = NPH == 4 ? 2 : 1;
+    const int ho = p.h * MUL, wo = p.w * MUL;
+    uint32_t m = 0;
+    for (int e = lane; e < TH * TW * NPH; e += 32) {
+        const int ph = e % NPH, pix = e / NPH;
+        const int ty = pix / TW, tx = pix - ty * TW;
+        const int iy = it.ty * TH + ty, ix = it.tx * TW + tx;
+        if (iy < p.h && ix < p.w) {
+            const int cl = p.label[((int64_t)it.b * ho + iy * MUL + (ph >> 1)) * wo + ix * MUL + (ph & 1)];
+            m |= 1u << min(cl, p.ncls - 1);
+        }
+    }
+    return __reduce_or_sync(0xffffffffu, m);
+}
+
+// ---------------------------------------------------------------------------------------- kernel
+// NTC  = output channels per parity handled by one work item; N = NPH * NTC accumulator columns.
+// KC   = input channels per K chunk (64 -> 128-B swizzle rows, 32 -> 64-B swizzle rows).
+// NPH  = 1 (plain conv) or 4 (up-sampling conv: the four parity kernels side by side along N).
+template <int NTC, int KC, int NPH>
+__global__ void __launch_bounds__(NUM_THREADS, 1) modconv3x3_tcp_kernel(const __grid_constant__ CUtensorMap wmap, Params p) {
+    constexpr int N = NTC * NPH;
+    constexpr int ROWB = KC * 2;                     // bytes per operand row
+    constexpr int A_PLANE = A_ROWS * ROWB;
+    constexpr int A_STAGE = 2 * A_PLANE;
+    constexpr int B_SLOT = N * ROWB;                 // one (tap, hi|lo) weight plane
+    constexpr int NACC = (2 * N <= 512) ? 2 : 1;
+    constexpr int TMEM_COLS = (NACC * N <= 32) ? 32 : (NACC * N <= 64) ? 64 : (NACC * N <= 128) ? 128 : (NACC * N <= 256) ? 256 : 512;
+    constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    constexpr int KSTEPS = KC / 16;
+    constexpr int MUL = NPH == 4 ? 2 : 1;
+    constexpr int MAX_SLOTS = 40;
+    static_assert(N <= 256 && N % 16 == 0, "UMMA N");
+    static_assert(A_PLANE % 1024 == 0 || KC == 32, "plane alignment");
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* a_buf = smem;                                              // [NSTAGE_A][hi|lo][A_ROWS][ROWB]
+    uint8_t* b_buf = a_buf + ((NSTAGE_A * A_STAGE + 1023) & ~1023);     // [nslot_b][N][ROWB]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(b_buf + (size_t)p.nslot_b * B_SLOT);
+    // barrier layout
+    const int A_FULL = 0, A_EMPTY = A_FULL + NSTAGE_A, ACC_FULL = A_EMPTY + NSTAGE_A, ACC_EMPTY = ACC_FULL + NACC,
+              B_FULL = ACC_EMPTY + NACC, B_EMPTY = B_FULL + p.nslot_b, NBARS = B_EMPTY + p.nslot_b;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBARS);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ho = p.h * MUL, wo = p.w * MUL;
+    const int nchunks = p.cin / KC;
+    const int planes_per_pass = nchunks * 18;          // (chunk, tap, hi|lo)
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NSTAGE_A; ++i) mbar_init(smem_u32(&bars[A_FULL + i]), NUM_XFORM), mbar_init(smem_u32(&bars[A_EMPTY + i]), 1);
+        for (int i = 0; i < NACC; ++i) mbar_init(smem_u32(&bars[ACC_FULL + i]), 1), mbar_init(smem_u32(&bars[ACC_EMPTY + i]), NUM_EPI);
+        for (int i = 0; i < p.nslot_b; ++i) mbar_init(smem_u32(&bars[B_FULL + i]), 1), mbar_init(smem_u32(&bars[B_EMPTY + i]), 1);
+        fence_barrier_init();
+    }
+    if (warp == 0 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&wmap) : "memory");
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================================================================== weight-plane producer (TMA)
+        int slot = 0;
+        uint32_t ph = 0;
+        bool loaded_resident = false;
+        const int rows_lo = (NPH * 9) * p.cout;          // row offset of the lo plane set in the weight tensor
+        for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
+            const Item item = decode_item(p, it);
+            const uint32_t classes = tile_class_mask<NPH>(p, item, lane);
+            if (p.resident && loaded_resident && true) {
+                // weights of this CTA's N tile are already in shared memory (nt is constant when resident: n_tiles == 1)
+                continue;
+            }
+            const int npass = p.resident ? 1 : __popc(classes);
+            if (lane == 0) {
+                for (int pass = 0; pass < npass; ++pass) {
+                    for (int kc = 0; kc < nchunks; ++kc) {
+                        for (int tap = 0; tap < 9; ++tap) {
+                            for (int hl = 0; hl < 2; ++hl) {
+                                if (!p.resident) mbar_wait(smem_u32(&bars[B_EMPTY + slot]), ph ^ 1);
+                                const uint32_t full = smem_u32(&bars[B_FULL + slot]);
+                                mbar_expect_tx(full, B_SLOT);
+                                const uint32_t dst = smem_u32(b_buf + (size_t)slot * B_SLOT);
+#pragma unroll
+                                for (int q = 0; q < NPH; ++q) {
+                                    const int row = hl * rows_lo + (q * 9 + tap) * p.cout + item.nt * NTC;
+                                    tma_load_2d(dst + q * NTC * ROWB, &wmap, kc * KC, row, full);
+                                }
+                                if (++slot == p.nslot_b) slot = 0, ph ^= 1;
+                            }
+                        }
+                    }
+                }
+            }
+            loaded_resident = true;
+            __syncwarp();
+        }
+    } else if (warp == 1) {
+        // ===================================================================== MMA issuer
+        int sa = 0, slot = 0, acc = 0;
+        uint32_t pa = 0, pb = 0, pacc[2] = {0, 0};
+        bool first_resident_pass = true;
+        for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
+            const Item item = decode_item(p, it);
+            const uint32_t classes = tile_class_mask<NPH>(p, item, lane);
+            if (lane == 0) {
+                for (uint32_t cm = classes; cm; cm &= cm - 1) {
+                    mbar_wait(smem_u32(&bars[ACC_EMPTY + acc]), pacc[acc] ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * N);
+                    uint32_t accumulate = 0;
+                    if (p.resident) slot = 0;
+                    for (int kc = 0; kc < nchunks; ++kc) {
+                        mbar_wait(smem_u32(&bars[A_FULL + sa]), pa);
+                        tc_fence_after();
+                        const uint32_t a_hi = smem_u32(a_buf + sa * A_STAGE), a_lo = a_hi + A_PLANE;
+                        for (int tap = 0; tap < 9; ++tap) {
+                            const int dy = tap / 3, dx = tap - 3 * dy;
+                            const uint32_t row_off = (uint32_t)(dy * TWP + dx + 1) * ROWB;
+                            // ---- hi plane of the weights: (A_hi + A_lo) x B_hi
+                            if (!p.resident || first_resident_pass) mbar_wait(smem_u32(&bars[B_FULL + slot]), pb);
+                            tc_fence_after();
+                            uint32_t bb = smem_u32(b_buf + (size_t)slot * B_SLOT);
+#pragma unroll
+                            for (int k = 0; k < KSTEPS; ++k) {
+                                const uint64_t db = smem_desc<KC>(bb + k * 32);
+                                umma_bf16(d_tmem, smem_desc<KC>(a_hi + row_off + k * 32), db, IDESC, accumulate);
+                                umma_bf16(d_tmem, smem_desc<KC>(a_lo + row_off + k * 32), db, IDESC, 1u);
+                                accumulate = 1u;
+                            }
+                            if (!p.resident) umma_commit(smem_u32(&bars[B_EMPTY + slot]));
+                            if (++slot == p.nslot_b) slot = 0, pb ^= 1;
+                            // ---- lo plane of the weights: A_hi x B_lo
+                            if (!p.resident || first_resident_pass) mbar_wait(smem_u32(&bars[B_FULL + slot]), pb);
+                            tc_fence_after();
+                            bb = smem_u32(b_buf + (size_t)slot * B_SLOT);
+#pragma unroll
+                            for (int k = 0; k < KSTEPS; ++k)
+                                umma_bf16(d_tmem, smem_desc<KC>(a_hi + row_off + k * 32), smem_desc<KC>(bb + k * 32), IDESC, 1u);
+                            if (!p.resident) umma_commit(smem_u32(&bars[B_EMPTY + slot]));
+                            if (++slot == p.nslot_b) slot = 0, pb ^= 1;
+                        }
+                        umma_commit(smem_u32(&bars[A_EMPTY + sa]));
+                        if (++sa == NSTAGE_A) sa = 0, pa ^= 1;
+                    }
+                    umma_commit(smem_u32(&bars[ACC_FULL + acc]));
+                    pacc[acc] ^= 1;
+                    if (NACC == 2) acc ^= 1;
+                    first_resident_pass = false;
+                }
+            }
+            __syncwarp();
+        }
+    } else if (warp < 6) {
+        // ===================================================================== activation transform (A producers)
+        const int t = threadIdx.x - 64;                  // 0..127
+        constexpr int CPR = KC / 8;                      // 16-byte chunks per row (8 or 4)
+        constexpr int PPI = 128 / CPR;                   // halo pixels covered per sweep (16 or 32)
+        constexpr int NSWEEP = 160 / PPI;                // 10 or 5
+        const int c8 = t % CPR;
+        const int pbase = t / CPR;
+        int sa = 0;
+        uint32_t pa = 0;
+        for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
+            const Item item = decode_item(p, it);
+            const uint32_t classes = tile_class_mask<NPH>(p, item, lane);
+            const float* xb = p.x + (int64_t)item.b * p.h * p.w * p.cin;
+            const int y0 = item.ty * TH, x0 = item.tx * TW;
+            for (uint32_t cm = classes; cm; cm &= cm - 1) {
+                const int cls = __ffs(cm) - 1;
+                const float* sc = p.s + ((int64_t)item.b * p.ncls + cls) * p.cin;
+                for (int kc = 0; kc < nchunks; ++kc) {
+                    const int ch = kc * KC + 8 * c8;
+                    const float4 s0 = __ldg(reinterpret_cast<const float4*>(sc + ch));
+                    const float4 s1 = __ldg(reinterpret_cast<const float4*>(sc + ch + 4));
+                    uint8_t* hi_plane = a_buf + sa * A_STAGE;
+                    uint8_t* lo_plane = hi_plane + A_PLANE;
+                    bool waited = false;
+#pragma unroll 1
+                    for (int half = 0; half < 2; ++half) {
+                        constexpr int HS = (NSWEEP + 1) / 2;
+                        float4 v0[HS], v1[HS];
+#pragma unroll
+                        for (int i = 0; i < HS; ++i) {
+                            const int sw = half * HS + i;
+                            const int hp = pbase + PPI * sw;
+                            const int gy = y0 - 1 + (hp >> 4), gx = x0 - 1 + (hp & 15);
+                            v0[i] = make_float4(0.f, 0.f, 0.f, 0.f), v1[i] = v0[i];
+                            if (sw < NSWEEP && gy >= 0 && gy < p.h && gx >= 0 && gx < p.w) {
+                                const float* src = xb + ((int64_t)gy * p.w + gx) * p.cin + ch;
+                                v0[i] = __ldg(reinterpret_cast<const float4*>(src));
+                                v1[i] = __ldg(reinterpret_cast<const float4*>(src + 4));
+                            }
+                        }
+                        if (!waited) {
+                            mbar_wait(smem_u32(&bars[A_EMPTY + sa]), pa ^ 1);
+                            waited = true;
+                        }
+#pragma unroll
+                        for (int i = 0; i < HS; ++i) {
+                            const int sw = half * HS + i;
+                            if (sw >= NSWEEP) continue;
+                            const int row = pbase + PPI * sw + 1;
+                            float f[8] = {v0[i].x * s0.x, v0[i].y * s0.y, v0[i].z * s0.z, v0[i].w * s0.w,
+                                          v1[i].x * s1.x, v1[i].y * s1.y, v1[i].z * s1.z, v1[i].w * s1.w};
+                            uint32_t hi[4], lo[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float h0 = bf16_round(f[2 * j]), h1 = bf16_round(f[2 * j + 1]);
+                                hi[j] = pack_bf16x2(h0, h1);
+                                lo[j] = pack_bf16x2(f[2 * j] - h0, f[2 * j + 1] - h1);
+                            }
+                            // swizzle: XOR the 16-byte chunk index with address bits [7,10) (128-B rows) / [7,9) (64-B rows)
+                            const uint32_t sx = KC == 64 ? (uint32_t)(row & 7) : (uint32_t)((row >> 1) & 3);
+                            const uint32_t off = (uint32_t)row * ROWB + (((uint32_t)c8 ^ sx) << 4);
+                            *reinterpret_cast<uint4*>(hi_plane + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                            *reinterpret_cast<uint4*>(lo_plane + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                        }
+                    }
+                    fence_proxy_async();
+                    mbar_arrive(smem_u32(&bars[A_FULL + sa]));
+                    if (++sa == NSTAGE_A) sa = 0, pa ^= 1;
+                }
+            }
+        }
+    } else {
+        // ===================================================================== epilogue
+        const uint32_t quarter = (uint32_t)(warp & 3);
+        const int m_row = quarter * 32 + lane;
+        const int ty = m_row >> 4, tx = m_row & 15;
+        int acc = 0;
+        uint32_t pacc[2] = {0, 0};
+        const float nw = (p.noise && p.noise_w) ? __ldg(p.noise_w) : 0.f;
+        for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
+            const Item item = decode_item(p, it);
+            const uint32_t classes = tile_class_mask<NPH>(p, item, lane);
+            const int iy = item.ty * TH + ty, ix = item.tx * TW + tx;
+            const bool in_img = tx < TW && iy < p.h && ix < p.w;
+            const int n0 = item.nt * NTC;
+            // class of each of this thread's output pixels (one per parity)
+            int pcls[NPH];
+#pragma unroll
+            for (int q = 0; q < NPH; ++q) {
+                pcls[q] = -1;
+                if (in_img) {
+                    const int oy = iy * MUL + (q >> 1), ox = ix * MUL + (q & 1);
+                    pcls[q] = p.label ? min((int)p.label[((int64_t)item.b * ho + oy) * wo + ox], p.ncls - 1) : 0;
+                }
+            }
+            for (uint32_t cm = classes; cm; cm &= cm - 1) {
+                const int cls = __ffs(cm) - 1;
+                mbar_wait(smem_u32(&bars[ACC_FULL + acc]), pacc[acc]);
+                pacc[acc] ^= 1;
+                tc_fence_after();
+                const float* dm = p.demod ? p.demod + ((int64_t)item.b * p.ncls + cls) * p.cout + n0 : nullptr;
+#pragma unroll
+                for (int q = 0; q < NPH; ++q) {
+                    const bool mine = (pcls[q] == cls);
+                    if (!__any_sync(0xffffffffu, mine)) continue;          // warp-uniform skip
+                    const int oy = iy * MUL + (q >> 1), ox = ix * MUL + (q & 1);
+                    float nz = 0.f;
+                    if (mine && p.noise) nz = nw * __ldg(p.noise + ((int64_t)(p.noise_b == 1 ? 0 : item.b) * ho + oy) * wo + ox);
+                    float* dst = p.y + (((int64_t)item.b * ho + oy) * wo + ox) * p.cout + n0;
+#pragma unroll 1
+                    for (int j = 0; j < NTC / 32; ++j) {
+                        uint32_t r[32];
+                        tmem_ld32(tmem_base + ((quarter * 32u) << 16) + (uint32_t)(acc * N + q * NTC + j * 32), r);
+                        if (mine) {
+#pragma unroll
+                            for (int g = 0; g < 8; ++g) {
+                                const int co = j * 32 + 4 * g;
+                                const float4 d = dm ? __ldg(reinterpret_cast<const float4*>(dm + co)) : make_float4(1.f, 1.f, 1.f, 1.f);
+                                const float4 bv = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n0 + co)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                                float4 o;
+                                o.x = __uint_as_float(r[4 * g + 0]) * d.x + nz + bv.x;
+                                o.y = __uint_as_float(r[4 * g + 1]) * d.y + nz + bv.y;
+                                o.z = __uint_as_float(r[4 * g + 2]) * d.z + nz + bv.z;
+                                o.w = __uint_as_float(r[4 * g + 3]) * d.w + nz + bv.w;
+                                if (p.act) {
+                                    const float k = 1.41421356237309515f;
+                                    o.x = lrelu_scaled(o.x, 0.2f, k), o.y = lrelu_scaled(o.y, 0.2f, k);
+                                    o.z = lrelu_scaled(o.z, 0.2f, k), o.w = lrelu_scaled(o.w, 0.2f, k);
+                                }
+                                *reinterpret_cast<float4*>(dst + co) = o;
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(smem_u32(&bars[ACC_EMPTY + acc]));
+                if (NACC == 2) acc ^= 1;
+            }
+        }
+    }
+
+    // ---- teardown
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+        else
+            cudaGetLastError();
+    });
+    return fn;
+}
+
+static int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = E4S_NUM_SMS;
+    }
+    return n;
+}
+
+template <int NTC, int KC, int NPH>
+static int launch(const void* w_hilo, Params p, cudaStream_t st) {
+    constexpr int N = NTC * NPH, ROWB = KC * 2;
+    constexpr int A_BYTES = ((NSTAGE_A * 2 * A_ROWS * ROWB) + 1023) & ~1023;
+    constexpr int B_SLOT = N * ROWB;
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return E4S_ERR_ARCH;
+    CUtensorMap map;
+    cuuint64_t dims[2] = {(cuuint64_t)p.cin, (cuuint64_t)2 * NPH * 9 * p.cout};
+    cuuint64_t strides[1] = {(cuuint64_t)p.cin * 2};
+    cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)NTC};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult cr = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w_hilo), dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return 700 + (int)cr;
+
+    p.tiles_x = (int)e4s_ceil_div(p.w, TW);
+    p.tiles_y = (int)e4s_ceil_div(p.h, TH);
+    p.n_tiles = p.cout / NTC;
+    const int64_t items = (int64_t)p.tiles_x * p.tiles_y * p.batch * p.n_tiles;
+    if (items >= (1ll << 31)) return E4S_ERR_SHAPE;
+    p.items = (int)items;
+    const int planes = (p.cin / KC) * 18;
+    int max_slots = (SMEM_BUDGET - A_BYTES - 1024) / B_SLOT;
+    if (max_slots > 36) max_slots = 36;
+    if (max_slots < 2) return E4S_ERR_SHAPE;
+    p.resident = (p.n_tiles == 1 && planes <= max_slots) ? 1 : 0;
+    p.nslot_b = p.resident ? planes : (max_slots > 8 ? 8 : max_slots);
+    const size_t smem = 1024 + A_BYTES + (size_t)p.nslot_b * B_SLOT + (size_t)(2 * NSTAGE_A + 4 + 2 * p.nslot_b) * 8 + 64;
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        if (cudaFuncSetAttribute(modconv3x3_tcp_kernel<NTC, KC, NPH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return (int)cudaGetLastError();
+        smem_set = smem;
+    }
+    const int grid = p.items < num_sms() ? p.items : num_sms();
+    modconv3x3_tcp_kernel<NTC, KC, NPH><<<grid, NUM_THREADS, smem, st>>>(map, p);
+    return e4s_launch_status();
+}
+
+}  // namespace tcp
+
+extern "C" int e4s_modconv3x3_tcp_fwd(const float* x, const void* w_hilo_bf16, const float* s, const float* demod,
+                                      const uint8_t* label, const float* noise, const float* noise_w, const float* bias,
+                                      float* y, int batch, int h, int w, int cin, int cout, int ncls, int up, int noise_b,
+                                      int act, void* stream) {
+    E4S_REQUIRE(x && w_hilo_bf16 && s && y, E4S_ERR_ARG);
+    E4S_REQUIRE(batch > 0 && h > 0 && w > 0 && cin > 0 && cout > 0 && ncls > 0 && ncls <= 32, E4S_ERR_ARG);
+    E4S_REQUIRE((cin % 32) == 0 && (cout % 32) == 0, E4S_ERR_SHAPE);
+    E4S_REQUIRE(label || ncls == 1, E4S_ERR_ARG);
+    E4S_REQUIRE(!noise || (noise_w && (noise_b == 1 || noise_b == batch)), E4S_ERR_ARG);
+    E4S_REQUIRE(e4s_aligned16(x) && e4s_aligned16(w_hilo_bf16) && e4s_aligned16(s) && e4s_aligned16(y) &&
+                    (!demod || e4s_aligned16(demod)) && (!bias || e4s_aligned16(bias)),
+                E4S_ERR_ALIGN);
+    tcp::Params p{x, s, demod, label, noise, noise_w, bias, y, batch, h, w, cin, cout, ncls, noise_b, act, 0, 0, 0, 0, 0, 0};
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool k64 = (cin % 64) == 0;
+    if (!up) {
+        if (k64) {
+            if (cout % 256 == 0) return tcp::launch<256, 64, 1>(w_hilo_bf16, p, st);
+            if (cout % 128 == 0) return tcp::launch<128, 64, 1>(w_hilo_bf16, p, st);
+            if (cout % 64 == 0) return tcp::launch<64, 64, 1>(w_hilo_bf16, p, st);
+            return tcp::launch<32, 64, 1>(w_hilo_bf16, p, st);
+        }
+        if (cout % 64 == 0) return tcp::launch<64, 32, 1>(w_hilo_bf16, p, st);
+        return tcp::launch<32, 32, 1>(w_hilo_bf16, p, st);
+    }
+    if (k64) {
+        if (cout % 64 == 0) return tcp::launch<64, 64, 4>(w_hilo_bf16, p, st);
+        return tcp::launch<32, 64, 4>(w_hilo_bf16, p, st);
+    }
+    return tcp::launch<32, 32, 4>(w_hilo_bf16, p, st);
+}

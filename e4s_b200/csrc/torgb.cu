@@ -95,6 +95,62 @@ __global__ void __launch_bounds__(256) torgb_kernel(TorgbParams p) {
     }
 }
 
+// Thread-per-pixel variant for the high-resolution layers (Cin <= 64): no cross-lane reduction, weights already
+// multiplied by the region's style sit in shared memory as [cls][3][cin] (broadcast reads), planar stores are
+// coalesced because consecutive threads own consecutive pixels.
+__global__ void __launch_bounds__(256) torgb_pixel_kernel(TorgbParams p) {
+    extern __shared__ __align__(16) float sm[];
+    float* ws = sm;                        // [ncls][3][cin]
+    __shared__ float sfir[16];
+    const int b = blockIdx.y;
+    for (int i = threadIdx.x; i < p.ncls * 3 * p.cin; i += 256) {
+        const int c = i / (3 * p.cin), rem = i - c * 3 * p.cin, ci = rem % p.cin;
+        ws[i] = p.wrgb[rem] * p.s[((int64_t)b * p.ncls + c) * p.cin + ci];
+    }
+    if (threadIdx.x < 16) sfir[threadIdx.x] = p.fir ? p.fir[threadIdx.x] : 0.f;
+    __syncthreads();
+    const int64_t hw = (int64_t)p.h * p.w;
+    const float* xb = p.x + (int64_t)b * hw * p.cin;
+    const int hs = p.h / 2, ws_ = p.w / 2;
+    const float b0 = p.bias ? __ldg(p.bias) : 0.f, b1 = p.bias ? __ldg(p.bias + 1) : 0.f, b2 = p.bias ? __ldg(p.bias + 2) : 0.f;
+    for (int64_t pix = (int64_t)blockIdx.x * 256 + threadIdx.x; pix < hw; pix += (int64_t)gridDim.x * 256) {
+        const int cls = p.label ? min((int)p.label[(int64_t)b * hw + pix], p.ncls - 1) : 0;
+        const float* w0 = ws + cls * 3 * p.cin;
+        const float* xp = xb + pix * p.cin;
+        float a0 = b0, a1 = b1, a2 = b2;
+        for (int c = 0; c < p.cin; c += 4) {
+            const float4 v = ld_stream_f4(xp + c);
+            const float4 u0 = *reinterpret_cast<const float4*>(w0 + c);
+            const float4 u1 = *reinterpret_cast<const float4*>(w0 + p.cin + c);
+            const float4 u2 = *reinterpret_cast<const float4*>(w0 + 2 * p.cin + c);
+            a0 += v.x * u0.x + v.y * u0.y + v.z * u0.z + v.w * u0.w;
+            a1 += v.x * u1.x + v.y * u1.y + v.z * u1.z + v.w * u1.w;
+            a2 += v.x * u2.x + v.y * u2.y + v.z * u2.z + v.w * u2.w;
+        }
+        if (p.skip) {
+            const int yy = (int)(pix / p.w), xx = (int)(pix - (int64_t)yy * p.w);
+            const float* sk = p.skip + (int64_t)b * 3 * hs * ws_;
+#pragma unroll
+            for (int ky = 0; ky < 4; ++ky) {
+                const int u = yy + ky - 2;
+                if (u < 0 || (u & 1) || (u >> 1) >= hs) continue;
+#pragma unroll
+                for (int kx = 0; kx < 4; ++kx) {
+                    const int t = xx + kx - 2;
+                    if (t < 0 || (t & 1) || (t >> 1) >= ws_) continue;
+                    const float f = sfir[(3 - ky) * 4 + (3 - kx)];
+                    const int64_t o = (int64_t)(u >> 1) * ws_ + (t >> 1);
+                    a0 = fmaf(__ldg(sk + o), f, a0);
+                    a1 = fmaf(__ldg(sk + (int64_t)hs * ws_ + o), f, a1);
+                    a2 = fmaf(__ldg(sk + 2 * (int64_t)hs * ws_ + o), f, a2);
+                }
+            }
+        }
+        float* ob = p.out + (int64_t)b * 3 * hw + pix;
+        ob[0] = a0, ob[hw] = a1, ob[2 * hw] = a2;
+    }
+}
+
 template <int LPP>
 int launch_torgb(const TorgbParams& p, cudaStream_t st) {
     size_t smem = sizeof(float) * (size_t)(3 + p.ncls) * p.cin;
@@ -125,6 +181,14 @@ extern "C" int e4s_torgb_fwd_f32(const float* x, const float* wrgb, const float*
     E4S_REQUIRE((size_t)(3 + ncls) * cin * sizeof(float) <= 200 * 1024, E4S_ERR_SHAPE);
     TorgbParams p{x, wrgb, s, label, bias, skip, fir4x4, out, batch, h, w, cin, ncls};
     cudaStream_t st = (cudaStream_t)stream;
+    if (cin <= 64 && (size_t)ncls * 3 * cin * sizeof(float) <= 40 * 1024) {
+        const int64_t hw = (int64_t)h * w;
+        int64_t want = e4s_ceil_div(hw, 256), cap = e4s_ceil_div((int64_t)E4S_NUM_SMS * 16, batch);
+        if (cap < 1) cap = 1;
+        dim3 grid((unsigned)(want < cap ? want : cap), batch);
+        torgb_pixel_kernel<<<grid, 256, (size_t)ncls * 3 * cin * sizeof(float), st>>>(p);
+        return e4s_launch_status();
+    }
     if (cin >= 128) return launch_torgb<32>(p, st);
     if (cin >= 64) return launch_torgb<16>(p, st);
     if (cin >= 32) return launch_torgb<8>(p, st);

@@ -87,24 +87,35 @@ __global__ void __launch_bounds__(256) upfirdn2d_fir4_kernel(const float* __rest
 #pragma unroll
         for (int b = 0; b < 4; ++b) kf[a][b] = __ldg(fir + (3 - a) * 4 + (3 - b));
 
-    // Stage the input tile: consecutive threads -> consecutive floats of a row (coalesced); all loads
-    // of a thread are issued before the first shared store so ~18 requests per thread are in flight.
-    constexpr int NELEM = SH * SW;
-    constexpr int NITER = (NELEM + 255) / 256;
-    float stage[NITER];
+    // Stage the input tile, one warp per tile row: lane -> consecutive floats (coalesced), row/column validity is
+    // a handful of compares per row instead of a div/mod per element.  All loads of a thread are issued before its
+    // first shared store, so ~20-30 requests per thread are in flight.
+    {
+        constexpr int RPW = (SH + 7) / 8;            // rows per warp
+        constexpr int CPL = (SW + 31) / 32;          // columns per lane
+        const int wrp = threadIdx.x >> 5, ln = threadIdx.x & 31;
+        float stage[RPW][CPL];
 #pragma unroll
-    for (int it = 0; it < NITER; ++it) {
-        int e = threadIdx.x + it * 256;
-        int r = e / SW, c = e - r * SW;
-        int iy = iy0 + r, ix = ix0 + c;
-        float v = 0.f;
-        if (e < NELEM && iy >= 0 && iy < p.in_h && ix >= 0 && ix < p.in_w) v = ld_stream_f1(xp + (int64_t)iy * p.in_w + ix);
-        stage[it] = v;
-    }
+        for (int a = 0; a < RPW; ++a) {
+            const int r = wrp + 8 * a;
+            const int iy = iy0 + r;
+            const bool rowok = (r < SH) && iy >= 0 && iy < p.in_h;
+            const float* src = xp + (int64_t)iy * p.in_w + ix0;
 #pragma unroll
-    for (int it = 0; it < NITER; ++it) {
-        int e = threadIdx.x + it * 256;
-        if (e < NELEM) tile[e] = stage[it];
+            for (int c = 0; c < CPL; ++c) {
+                const int col = ln + 32 * c, ix = ix0 + col;
+                stage[a][c] = (rowok && col < SW && ix >= 0 && ix < p.in_w) ? ld_stream_f1(src + col) : 0.f;
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < RPW; ++a) {
+            const int r = wrp + 8 * a;
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) {
+                const int col = ln + 32 * c;
+                if (r < SH && col < SW) tile[r * SW + col] = stage[a][c];
+            }
+        }
     }
     __syncthreads();
 

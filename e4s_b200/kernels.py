@@ -257,8 +257,29 @@ def modconv3x3_fwd(x_pm: Tensor, wt: Tensor, s: Tensor, dm: Optional[Tensor], la
 
 
 def tc_eligible(cin: int, cout: int) -> bool:
-    """Shapes the tcgen05 kernel takes: 64-channel K chunks, N tile of 32/64/128 output channels."""
+    """Shapes the first-generation tcgen05 kernel takes: 64-channel K chunks, N tile of 32/64/128 output channels."""
     return cin % 64 == 0 and cout % 32 == 0 and (cout <= 128 and cout in (32, 64, 128) or cout % 128 == 0)
+
+
+def tcp_eligible(cin: int, cout: int) -> bool:
+    """Shapes the persistent tcgen05 kernel takes (K chunks of 64 or 32 channels, N tiles of 32..256 channels)."""
+    return cin % 32 == 0 and cout % 32 == 0
+
+
+def modconv3x3_tcp_fwd(x_pm: Tensor, w_hilo: Tensor, s: Tensor, dm: Optional[Tensor], label: Optional[Tensor],
+                       noise: Optional[Tensor], noise_w: Optional[Tensor], bias: Optional[Tensor], up: bool, act: bool) -> Tensor:
+    """Persistent tensor-core path; w_hilo: bf16 [2, nphase, 9, Cout, Cin].  Same contract as modconv3x3_fwd."""
+    b, h, w, cin = x_pm.shape
+    cout = w_hilo.shape[3]
+    ncls = s.shape[1]
+    m = 2 if up else 1
+    y = torch.empty((b, h * m, w * m, cout), device=x_pm.device, dtype=torch.float32)
+    nb = noise.shape[0] if noise is not None else 1
+    with torch.cuda.device(x_pm.device):
+        _call("e4s_modconv3x3_tcp_fwd", _lib.load().e4s_modconv3x3_tcp_fwd, ptr(x_pm), ptr(w_hilo), ptr(s), ptr(dm), ptr(label),
+              ptr(noise), ptr(noise_w), ptr(bias), ptr(y), b, h, w, cin, cout, ncls, int(up), nb, int(act), stream_ptr(),
+              work=2.0 * 9 * cin * cout * b * h * w)
+    return y
 
 
 def modconv3x3_tc_fwd(x_pm: Tensor, w_hilo: Tensor, s: Tensor, dm: Optional[Tensor], label: Optional[Tensor],

@@ -125,7 +125,7 @@ class PreparedConv:
                 # -> [nphase, tap, Cin, Cout]
                 self.wt = wk.permute(0, 3, 4, 2, 1).reshape(wk.shape[0], 9, cin, cout).contiguous()
                 self.wrgb = None
-                if K.tc_eligible(cin, cout):
+                if K.tcp_eligible(cin, cout):
                     wk_k = wk.permute(0, 3, 4, 1, 2).reshape(wk.shape[0], 9, cout, cin)     # K-major rows [.., Cout, Cin]
                     hi = wk_k.to(torch.bfloat16)
                     lo = (wk_k - hi.float()).to(torch.bfloat16)
@@ -147,18 +147,22 @@ def warn_frozen(weight: Tensor):
         _warned_weight_grad = True
 
 
-DEFAULT_CONV_MODE = "simt"      # flipped to "auto" once the tcgen05 kernel is verified on hardware
+DEFAULT_CONV_MODE = "auto"
 
 
-def use_tensor_cores(prep: "PreparedConv", x_pm: Tensor) -> bool:
-    """Kernel choice for one layer.  E4S_B200_CONV=simt|tc|auto (default auto): the tcgen05 kernel takes every
-    eligible shape from 16x16 up; below that a 128-pixel tile is mostly halo and the fp32 SIMT kernel is used."""
+def conv_path(prep: "PreparedConv", x_pm: Tensor) -> str:
+    """Kernel choice for one layer: 'tcp' (persistent tcgen05), 'tc' (first-generation tcgen05) or 'simt' (fp32).
+    E4S_B200_CONV=auto|tcp|tc|simt.  auto: the persistent tensor-core kernel for every eligible shape from 16x16 up;
+    below that a 128-pixel tile is mostly halo and the exact-fp32 SIMT kernel is used."""
     mode = os.environ.get("E4S_B200_CONV", DEFAULT_CONV_MODE)
     if prep.w_hilo is None or mode == "simt":
-        return False
+        return "simt"
+    cout, cin = prep.w_hilo.shape[3], prep.w_hilo.shape[4]
     if mode == "tc":
-        return True
-    return x_pm.shape[1] * x_pm.shape[2] >= 256
+        return "tc" if K.tc_eligible(cin, cout) else "simt"
+    if mode == "tcp":
+        return "tcp"
+    return "tcp" if x_pm.shape[1] * x_pm.shape[2] >= 256 else "simt"
 
 
 # ================================================================================== autograd
@@ -168,9 +172,11 @@ class StyledConvFn(Function):
     @staticmethod
     def forward(ctx, x_pm, s, noise, noise_w, bias, label, prep, up, demodulate, act):
         dm = K.demod(s, prep.wsq) if demodulate else None
-        if use_tensor_cores(prep, x_pm):
-            y = K.modconv3x3_tc_fwd(x_pm, prep.w_hilo, s.contiguous(), dm, label, noise, noise_w, bias, up, act,
-                                    shift_mode=int(os.environ.get("E4S_B200_TC_SHIFT_MODE", "1")))
+        path = conv_path(prep, x_pm)
+        if path == "tcp":
+            y = K.modconv3x3_tcp_fwd(x_pm, prep.w_hilo, s.contiguous(), dm, label, noise, noise_w, bias, up, act)
+        elif path == "tc":
+            y = K.modconv3x3_tc_fwd(x_pm, prep.w_hilo, s.contiguous(), dm, label, noise, noise_w, bias, up, act)
         else:
             y = K.modconv3x3_fwd(x_pm, prep.wt, s.contiguous(), dm, label, noise, noise_w, bias, up, act)
         ctx.set_materialize_grads(False)

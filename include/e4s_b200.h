@@ -124,6 +124,14 @@ int e4s_modconv3x3_tc_fwd(const float* x, const void* w_hilo_bf16, const float* 
                           float* y, int batch, int h, int w, int cin, int cout, int ncls, int up, int noise_b,
                           int act, int shift_mode, void* stream);
 
+/* Persistent, fully pipelined tcgen05 implementation (csrc/modconv_tcp.cu): same contract and weight format as
+ * e4s_modconv3x3_tc_fwd; additionally takes cin % 32 == 0 (64-byte-swizzle K chunks) and puts the four output
+ * parities of an up-sampling layer along the MMA's N dimension.  This is the kernel the synthesis network uses. */
+int e4s_modconv3x3_tcp_fwd(const float* x, const void* w_hilo_bf16, const float* s, const float* demod,
+                           const uint8_t* label, const float* noise, const float* noise_w, const float* bias,
+                           float* y, int batch, int h, int w, int cin, int cout, int ncls, int up, int noise_b,
+                           int act, void* stream);
+
 /* Region-selected 1x1 modulated conv to RGB + bias + up-sampled skip: one ToRGB.forward
  * (model.py:422-448).  x: pixel-major [B, H, W, Cin]; wrgb: [3, Cin] (already scaled by
  * 1/sqrt(Cin)); s: [B, ncls, Cin]; label: [B, H, W] or NULL (ncls==1); bias: [3];

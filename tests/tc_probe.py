@@ -7,26 +7,25 @@ import traceback
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import torch
-from test_parity_gpu import _tc_case
+from test_parity_gpu import _tc_case, TC_CASES, TCP_EXTRA
 
-CASES = [(1, 64, 64, 16, False, 1, "blobs"), (1, 64, 32, 24, False, 1, "blobs"), (2, 128, 128, 32, False, 1, "blobs"),
-         (1, 128, 64, 16, False, 6, "iid"), (2, 64, 128, 16, True, 4, "blobs"), (1, 512, 512, 16, True, 3, "iid")]
+CASES = TC_CASES + TCP_EXTRA
 
-for mode in (0, 1):
+for mode in ("tcp",):
     for case in CASES:
         try:
             K, prep, x, args = _tc_case(*case, seed=sum(c for c in case if isinstance(c, int)))
             ref = K.modconv3x3_fwd(x, prep.wt, *args)
-            out = K.modconv3x3_tc_fwd(x, prep.w_hilo, *args, shift_mode=mode)
+            out = K.modconv3x3_tcp_fwd(x, prep.w_hilo, *args)
             torch.cuda.synchronize()
             err = float((out - ref).abs().max() / ref.abs().max())
             bad = int(((out - ref).abs() > 1e-3 * ref.abs().max()).sum())
-            print(f"shift_mode={mode} case={case}: max-rel err {err:.3e}, elements off {bad}/{out.numel()}", flush=True)
+            print(f"kernel={mode} case={case}: max-rel err {err:.3e}, elements off {bad}/{out.numel()}", flush=True)
             if err > 1e-3:
                 d = (out - ref).abs().amax(dim=3)[0]            # per pixel error map of sample 0
                 rows = (d > 1e-3 * ref.abs().max()).nonzero()
                 print("   first bad pixels:", rows[:12].tolist(), flush=True)
         except Exception:
             traceback.print_exc()
-            print(f"shift_mode={mode} case={case}: EXCEPTION", flush=True)
+            print(f"kernel={mode} case={case}: EXCEPTION", flush=True)
             sys.exit(1)          # a trapped kernel poisons the context

@@ -317,18 +317,28 @@ def _tc_case(b, cin, cout, hw, up, ncls, kind, seed, act=True):
     return K, prep, x, args
 
 
-@pytest.mark.parametrize("b,cin,cout,hw,up,ncls,kind", [
+TC_CASES = [
     (1, 64, 64, 16, False, 1, "blobs"),       # smallest: one K chunk, single class
     (2, 128, 128, 32, False, 1, "blobs"),     # two chunks, N = 128
     (1, 64, 32, 24, False, 1, "blobs"),       # N = 32, partial tiles in both directions
-    (2, 192, 256, 20, False, 5, "blobs"),     # two N tiles, masked, mostly single-class tiles
+    (2, 192, 256, 20, False, 5, "blobs"),     # N = 256 (persistent) / two N tiles (v1), masked
     (1, 128, 64, 16, False, 6, "iid"),        # every tile holds every class -> 6 passes per tile
     (2, 64, 128, 16, True, 4, "blobs"),       # up-sampling layer: 4 parity kernels
     (1, 512, 512, 16, True, 3, "iid"),        # full-width layer, up, mixed classes
-])
+]
+TCP_EXTRA = [
+    (2, 32, 32, 40, False, 1, "blobs"),       # 32-channel chunks (64-byte swizzle), resident weights, many tiles per CTA
+    (1, 32, 64, 18, False, 4, "iid"),         # 32-channel chunks, masked
+    (1, 64, 32, 36, True, 1, "blobs"),        # up, N = 4 x 32
+    (1, 96, 32, 16, True, 3, "iid"),          # 32-channel chunks x3, up, masked
+    (3, 512, 512, 64, False, 12, "blobs"),    # production shape c7@64: > 148 work items, two N tiles, 12 regions
+]
+
+
+@pytest.mark.parametrize("b,cin,cout,hw,up,ncls,kind", TC_CASES)
 def test_tc_kernel_matches_simt(b, cin, cout, hw, up, ncls, kind):
-    """The tcgen05 implicit-GEMM kernel against the exact-fp32 SIMT kernel of the same library (which the tests
-    above pin to the reference vectors).  Split-bf16 x3 keeps the error ~1e-5, far inside the 1e-3 bar."""
+    """The first-generation tcgen05 implicit-GEMM kernel against the exact-fp32 SIMT kernel of the same library
+    (which the tests above pin to the reference vectors).  Split-bf16 x3 keeps the error ~1e-5."""
     K, prep, x, args = _tc_case(b, cin, cout, hw, up, ncls, kind, seed=cin + cout + hw)
     ref = K.modconv3x3_fwd(x, prep.wt, *args)
     out = K.modconv3x3_tc_fwd(x, prep.w_hilo, *args)
@@ -337,9 +347,21 @@ def test_tc_kernel_matches_simt(b, cin, cout, hw, up, ncls, kind):
     print(f"tc-vs-simt rel err {e:.2e}")
 
 
+@pytest.mark.parametrize("b,cin,cout,hw,up,ncls,kind", TC_CASES + TCP_EXTRA)
+def test_tcp_kernel_matches_simt(b, cin, cout, hw, up, ncls, kind):
+    """The persistent tcgen05 kernel (the one the generator uses) against the exact-fp32 SIMT kernel."""
+    K, prep, x, args = _tc_case(b, cin, cout, hw, up, ncls, kind, seed=cin + cout + hw)
+    ref = K.modconv3x3_fwd(x, prep.wt, *args)
+    out = K.modconv3x3_tcp_fwd(x, prep.w_hilo, *args)
+    torch.cuda.synchronize()
+    e = assert_close(out, ref, 1e-4, f"tcp vs simt {b},{cin},{cout},{hw},{up},{ncls},{kind}")
+    print(f"tcp-vs-simt rel err {e:.2e}")
+
+
 def test_generator_golden_tensor_core_path(golden, monkeypatch):
-    """Whole generator with every eligible layer forced onto the tcgen05 kernel, against the reference vectors."""
-    monkeypatch.setenv("E4S_B200_CONV", "tc")
+    """Whole generator with every eligible layer forced onto the persistent tcgen05 kernel (also at 4x4..8x8, where
+    the default policy would pick the SIMT kernel), against the reference vectors."""
+    monkeypatch.setenv("E4S_B200_CONV", "tcp")
     for tag, size, K_, B, nc, msz, kind in [("g64_k5", 64, 5, 2, 5, 32, "blobs"), ("g256_k13", 256, 13, 1, 12, 512, "blobs")]:
         G, _ = _generator(size, K_)
         codes, mask, _, noise = O.synthetic_inputs(B, nc, size, msz, seed=size + K_, kind=kind)

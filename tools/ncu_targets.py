@@ -28,7 +28,8 @@ x = torch.randn(B, 32, 1025, 1025, device=DEV)
 upfirdn2d(x, fir, pad=(1, 1))                      # the model's largest blur call
 del x
 
-for name, cin, cout, r, up in [("c11@256", 128, 128, 256, False), ("c7@64", 512, 512, 64, False), ("c12^512", 128, 64, 256, True)]:
+for name, cin, cout, r, up in [("c11@256", 128, 128, 256, False), ("c7@64", 512, 512, 64, False), ("c12^512", 128, 64, 256, True),
+                               ("c14^1024", 64, 32, 512, True), ("c15@1024", 32, 32, 1024, False)]:
     w = torch.randn(1, cout, cin, 3, 3, device=DEV)
     prep = PreparedConv().get(w, up, fir if up else None)
     xpm = torch.randn(B, r, r, cin, device=DEV)
@@ -40,6 +41,8 @@ for name, cin, cout, r, up in [("c11@256", 128, 128, 256, False), ("c7@64", 512,
     for mode in args.conv.split(","):
         if mode == "tc" and prep.w_hilo is not None:
             K.modconv3x3_tc_fwd(xpm, prep.w_hilo, s, dm, None, noise, nw, bias, up, True)
+        elif mode == "tcp" and prep.w_hilo is not None:
+            K.modconv3x3_tcp_fwd(xpm, prep.w_hilo, s, dm, None, noise, nw, bias, up, True)
         elif mode == "simt":
             K.modconv3x3_fwd(xpm, prep.wt, s, dm, None, noise, nw, bias, up, True)
     torch.cuda.synchronize()

@@ -45,6 +45,7 @@ def main():
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "opbench.json"))
     ap.add_argument("--conv", default="simt,tc")
     ap.add_argument("--layers", default="all")
+    ap.add_argument("--unmasked", action="store_true", help="time the masked layers with a single region (no class passes)")
     args = ap.parse_args()
     B = args.batch
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
@@ -101,6 +102,8 @@ def main():
     blur = fir
     total = {m: 0.0 for m in args.conv.split(",")}
     for name, cin, cout, r, up, masked in layers:
+        if args.unmasked:
+            masked = 0
         ncls = 12 if masked else 1
         w = torch.randn(1, cout, cin, 3, 3, device=DEV)
         prep = PreparedConv().get(w, bool(up), blur if up else None)
@@ -115,9 +118,13 @@ def main():
         flops = 2.0 * 9 * cin * cout * B * r * r
         for mode in args.conv.split(","):
             if mode == "tc":
-                if prep.w_hilo is None:
+                if prep.w_hilo is None or not K.tc_eligible(cin, cout):
                     continue
                 fn = lambda: K.modconv3x3_tc_fwd(xpm, prep.w_hilo, s, dm, label, noise, nw, bias, bool(up), True)
+            elif mode == "tcp":
+                if prep.w_hilo is None:
+                    continue
+                fn = lambda: K.modconv3x3_tcp_fwd(xpm, prep.w_hilo, s, dm, label, noise, nw, bias, bool(up), True)
             else:
                 fn = lambda: K.modconv3x3_fwd(xpm, prep.wt, s, dm, label, noise, nw, bias, bool(up), True)
             ms = timeit(fn, iters=3, warmup=1, flush=flush)
