@@ -46,8 +46,11 @@ struct Params {
     const float* noise_w;
     const float* bias;
     float* y;
-    int batch, h, w, cin, cout, ncls, noise_b, act;
+    int batch, h, w, cin, cout, ncls, noise_b, act;       // act: 0 none, 1 sqrt(2)*lrelu(0.2), 2 PReLU(slope[c])
     int tiles_x, tiles_y, n_tiles, items, nslot_b, resident;
+    const float* shift;       // optional [B, ncls, Cin] added to in-image activations after the scale (encoder InstanceNorm)
+    const float* slope;       // PReLU slopes [Cout] when act == 2
+    int out_stride;           // 1, or 2 = keep only even output pixels (stride-2 convolution), plain convs only
 };
 
 // ------------------------------------------------------------------------------------ PTX helpers
@@ -330,11 +333,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) modconv3x3_tcp_kernel(const __
             const int y0 = item.ty * TH, x0 = item.tx * TW;
             for (uint32_t cm = classes; cm; cm &= cm - 1) {
                 const int cls = __ffs(cm) - 1;
-                const float* sc = p.s + ((int64_t)item.b * p.ncls + cls) * p.cin;
+                const float* sc = p.s ? p.s + ((int64_t)item.b * p.ncls + cls) * p.cin : nullptr;
+                const float* sh = p.shift ? p.shift + ((int64_t)item.b * p.ncls + cls) * p.cin : nullptr;
                 for (int kc = 0; kc < nchunks; ++kc) {
                     const int ch = kc * KC + 8 * c8;
-                    const float4 s0 = __ldg(reinterpret_cast<const float4*>(sc + ch));
-                    const float4 s1 = __ldg(reinterpret_cast<const float4*>(sc + ch + 4));
+                    const float4 one4 = make_float4(1.f, 1.f, 1.f, 1.f), zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float4 s0 = sc ? __ldg(reinterpret_cast<const float4*>(sc + ch)) : one4;
+                    const float4 s1 = sc ? __ldg(reinterpret_cast<const float4*>(sc + ch + 4)) : one4;
+                    const float4 t0 = sh ? __ldg(reinterpret_cast<const float4*>(sh + ch)) : zero4;
+                    const float4 t1 = sh ? __ldg(reinterpret_cast<const float4*>(sh + ch + 4)) : zero4;
                     uint8_t* hi_plane = a_buf + sa * A_STAGE;
                     uint8_t* lo_plane = hi_plane + A_PLANE;
                     bool waited = false;
@@ -342,13 +349,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) modconv3x3_tcp_kernel(const __
                     for (int half = 0; half < 2; ++half) {
                         constexpr int HS = (NSWEEP + 1) / 2;
                         float4 v0[HS], v1[HS];
+                        bool inb[HS];
 #pragma unroll
                         for (int i = 0; i < HS; ++i) {
                             const int sw = half * HS + i;
                             const int hp = pbase + PPI * sw;
                             const int gy = y0 - 1 + (hp >> 4), gx = x0 - 1 + (hp & 15);
                             v0[i] = make_float4(0.f, 0.f, 0.f, 0.f), v1[i] = v0[i];
-                            if (sw < NSWEEP && gy >= 0 && gy < p.h && gx >= 0 && gx < p.w) {
+                            inb[i] = sw < NSWEEP && gy >= 0 && gy < p.h && gx >= 0 && gx < p.w;
+                            if (inb[i]) {
                                 const float* src = xb + ((int64_t)gy * p.w + gx) * p.cin + ch;
                                 v0[i] = __ldg(reinterpret_cast<const float4*>(src));
                                 v1[i] = __ldg(reinterpret_cast<const float4*>(src + 4));
@@ -365,6 +374,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) modconv3x3_tcp_kernel(const __
                             const int row = pbase + PPI * sw + 1;
                             float f[8] = {v0[i].x * s0.x, v0[i].y * s0.y, v0[i].z * s0.z, v0[i].w * s0.w,
                                           v1[i].x * s1.x, v1[i].y * s1.y, v1[i].z * s1.z, v1[i].w * s1.w};
+                            if (sh && inb[i]) {      // zero padding applies to the NORMALISED tensor: shift in-image pixels only
+                                f[0] += t0.x, f[1] += t0.y, f[2] += t0.z, f[3] += t0.w;
+                                f[4] += t1.x, f[5] += t1.y, f[6] += t1.z, f[7] += t1.w;
+                            }
                             uint32_t hi[4], lo[4];
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
@@ -397,7 +410,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) modconv3x3_tcp_kernel(const __
             const Item item = decode_item(p, it);
             const uint32_t classes = tile_class_mask<NPH>(p, item, lane);
             const int iy = item.ty * TH + ty, ix = item.tx * TW + tx;
-            const bool in_img = tx < TW && iy < p.h && ix < p.w;
+            const bool strided = (NPH == 1 && p.out_stride == 2);
+            const bool in_img = tx < TW && iy < p.h && ix < p.w && (!strided || ((iy | ix) & 1) == 0);
             const int n0 = item.nt * NTC;
             // class of each of this thread's output pixels (one per parity)
             int pcls[NPH];
@@ -419,10 +433,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) modconv3x3_tcp_kernel(const __
                 for (int q = 0; q < NPH; ++q) {
                     const bool mine = (pcls[q] == cls);
                     if (!__any_sync(0xffffffffu, mine)) continue;          // warp-uniform skip
-                    const int oy = iy * MUL + (q >> 1), ox = ix * MUL + (q & 1);
+                    const int oy = strided ? (iy >> 1) : iy * MUL + (q >> 1), ox = strided ? (ix >> 1) : ix * MUL + (q & 1);
+                    const int oh = strided ? (p.h >> 1) : ho, ow = strided ? (p.w >> 1) : wo;
                     float nz = 0.f;
-                    if (mine && p.noise) nz = nw * __ldg(p.noise + ((int64_t)(p.noise_b == 1 ? 0 : item.b) * ho + oy) * wo + ox);
-                    float* dst = p.y + (((int64_t)item.b * ho + oy) * wo + ox) * p.cout + n0;
+                    if (mine && p.noise) nz = nw * __ldg(p.noise + ((int64_t)(p.noise_b == 1 ? 0 : item.b) * oh + oy) * ow + ox);
+                    float* dst = p.y + (((int64_t)item.b * oh + oy) * ow + ox) * p.cout + n0;
 #pragma unroll 1
                     for (int j = 0; j < NTC / 32; ++j) {
                         uint32_t r[32];
@@ -438,10 +453,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) modconv3x3_tcp_kernel(const __
                                 o.y = __uint_as_float(r[4 * g + 1]) * d.y + nz + bv.y;
                                 o.z = __uint_as_float(r[4 * g + 2]) * d.z + nz + bv.z;
                                 o.w = __uint_as_float(r[4 * g + 3]) * d.w + nz + bv.w;
-                                if (p.act) {
+                                if (p.act == 1) {
                                     const float k = 1.41421356237309515f;
                                     o.x = lrelu_scaled(o.x, 0.2f, k), o.y = lrelu_scaled(o.y, 0.2f, k);
                                     o.z = lrelu_scaled(o.z, 0.2f, k), o.w = lrelu_scaled(o.w, 0.2f, k);
+                                } else if (p.act == 2) {
+                                    const float4 sl = __ldg(reinterpret_cast<const float4*>(p.slope + n0 + co));
+                                    o.x = o.x > 0.f ? o.x : o.x * sl.x, o.y = o.y > 0.f ? o.y : o.y * sl.y;
+                                    o.z = o.z > 0.f ? o.z : o.z * sl.z, o.w = o.w > 0.f ? o.w : o.w * sl.w;
                                 }
                                 *reinterpret_cast<float4*>(dst + co) = o;
                             }
@@ -535,6 +554,8 @@ static int launch(const void* w_hilo, Params p, cudaStream_t st) {
     return e4s_launch_status();
 }
 
+int dispatch(const void* w_hilo_bf16, Params p, int up, cudaStream_t st);
+
 }  // namespace tcp
 
 extern "C" int e4s_modconv3x3_tcp_fwd(const float* x, const void* w_hilo_bf16, const float* s, const float* demod,
@@ -549,8 +570,32 @@ extern "C" int e4s_modconv3x3_tcp_fwd(const float* x, const void* w_hilo_bf16, c
     E4S_REQUIRE(e4s_aligned16(x) && e4s_aligned16(w_hilo_bf16) && e4s_aligned16(s) && e4s_aligned16(y) &&
                     (!demod || e4s_aligned16(demod)) && (!bias || e4s_aligned16(bias)),
                 E4S_ERR_ALIGN);
-    tcp::Params p{x, s, demod, label, noise, noise_w, bias, y, batch, h, w, cin, cout, ncls, noise_b, act, 0, 0, 0, 0, 0, 0};
-    cudaStream_t st = (cudaStream_t)stream;
+    tcp::Params p{x, s, demod, label, noise, noise_w, bias, y, batch, h, w, cin, cout, ncls, noise_b, act ? 1 : 0,
+                  0, 0, 0, 0, 0, 0, nullptr, nullptr, 1};
+    return tcp::dispatch(w_hilo_bf16, p, up, (cudaStream_t)stream);
+}
+
+/* Plain 3x3 convolution (pad 1, stride 1 or 2) on the same kernel, for the RGI encoder's conv stack
+ * (src/models/encoders/helpers.py:122-144): optional per-(sample, channel) input affine (InstanceNorm folded onto
+ * the operand), optional PReLU epilogue. */
+extern "C" int e4s_conv3x3_tcp_f32(const float* x, const void* w_hilo_bf16, const float* scale, const float* shift,
+                                   const float* prelu_slope, float* y, int batch, int h, int w, int cin, int cout,
+                                   int out_stride, void* stream) {
+    E4S_REQUIRE(x && w_hilo_bf16 && y, E4S_ERR_ARG);
+    E4S_REQUIRE(batch > 0 && h > 0 && w > 0 && cin > 0 && cout > 0, E4S_ERR_ARG);
+    E4S_REQUIRE((cin % 32) == 0 && (cout % 32) == 0, E4S_ERR_SHAPE);
+    E4S_REQUIRE(out_stride == 1 || (out_stride == 2 && (h % 2) == 0 && (w % 2) == 0), E4S_ERR_SHAPE);
+    E4S_REQUIRE(e4s_aligned16(x) && e4s_aligned16(w_hilo_bf16) && e4s_aligned16(y) && (!scale || e4s_aligned16(scale)) &&
+                    (!shift || e4s_aligned16(shift)) && (!prelu_slope || e4s_aligned16(prelu_slope)),
+                E4S_ERR_ALIGN);
+    tcp::Params p{x, scale, nullptr, nullptr, nullptr, nullptr, nullptr, y, batch, h, w, cin, cout, 1, 1, prelu_slope ? 2 : 0,
+                  0, 0, 0, 0, 0, 0, shift, prelu_slope, out_stride};
+    return tcp::dispatch(w_hilo_bf16, p, 0, (cudaStream_t)stream);
+}
+
+namespace tcp {
+int dispatch(const void* w_hilo_bf16, Params p, int up, cudaStream_t st) {
+    const int cin = p.cin, cout = p.cout;
     const bool k64 = (cin % 64) == 0;
     if (!up) {
         if (k64) {
@@ -568,3 +613,4 @@ extern "C" int e4s_modconv3x3_tcp_fwd(const float* x, const void* w_hilo_bf16, c
     }
     return tcp::launch<32, 32, 4>(w_hilo_bf16, p, st);
 }
+}  // namespace tcp

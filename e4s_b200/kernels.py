@@ -348,3 +348,47 @@ def torgb_bwd(g: Tensor, x_pm: Tensor, wrgb: Tensor, s: Tensor, label: Optional[
         _call("e4s_torgb_bwd_f32", _lib.load().e4s_torgb_bwd_f32, ptr(g), ptr(x_pm), ptr(wrgb), ptr(s), ptr(label), ptr(gx),
               ptr(gs), b, h, w, cin, ncls, stream_ptr(), work=4.0 * b * h * w * (2 * cin + 3))
     return gx, gs
+
+
+# ------------------------------------------------------------------------------ encoder conv stack
+def split_bf16(w: Tensor) -> Tensor:
+    """fp32 -> stacked (hi, lo) bf16 planes with hi + lo == w to ~2^-17 relative."""
+    hi = w.to(torch.bfloat16)
+    lo = (w - hi.float()).to(torch.bfloat16)
+    return torch.stack([hi, lo]).contiguous()
+
+
+def conv3x3_tcp(x_pm: Tensor, w_hilo: Tensor, scale: Optional[Tensor] = None, shift: Optional[Tensor] = None,
+                prelu: Optional[Tensor] = None, out_stride: int = 1) -> Tensor:
+    """x_pm [B,H,W,Cin]; w_hilo bf16 [2,1,9,Cout,Cin]; scale/shift [B,Cin]; prelu [Cout] -> [B,H/s,W/s,Cout]."""
+    b, h, w, cin = x_pm.shape
+    cout = w_hilo.shape[3]
+    y = torch.empty((b, h // out_stride, w // out_stride, cout), device=x_pm.device, dtype=torch.float32)
+    with torch.cuda.device(x_pm.device):
+        _call("e4s_conv3x3_tcp_f32", _lib.load().e4s_conv3x3_tcp_f32, ptr(x_pm), ptr(w_hilo), ptr(scale), ptr(shift), ptr(prelu),
+              ptr(y), b, h, w, cin, cout, out_stride, stream_ptr(), work=2.0 * 9 * cin * cout * b * h * w)
+    return y
+
+
+def instnorm_affine(x_pm: Tensor, eps: float = 1e-5):
+    """InstanceNorm2d statistics of x_pm [B,H,W,C] as (scale, shift), each [B, C]."""
+    b, h, w, c = x_pm.shape
+    ws = torch.empty((b, c, 2), device=x_pm.device, dtype=torch.float32)
+    scale = torch.empty((b, c), device=x_pm.device, dtype=torch.float32)
+    shift = torch.empty((b, c), device=x_pm.device, dtype=torch.float32)
+    with torch.cuda.device(x_pm.device):
+        _call("e4s_instnorm_affine_f32", _lib.load().e4s_instnorm_affine_f32, ptr(x_pm), ptr(ws), ptr(scale), ptr(shift), b, h, w,
+              c, eps, stream_ptr(), work=4.0 * x_pm.numel())
+    return scale, shift
+
+
+def norm_residual(y: Tensor, y_scale: Tensor, y_shift: Tensor, alpha: float, shortcut: Optional[Tensor] = None,
+                  sc_scale: Optional[Tensor] = None, sc_shift: Optional[Tensor] = None, sc_stride: int = 1,
+                  prelu: Optional[Tensor] = None) -> Tensor:
+    b, h, w, c = y.shape
+    out = torch.empty_like(y)
+    with torch.cuda.device(y.device):
+        _call("e4s_norm_residual_f32", _lib.load().e4s_norm_residual_f32, ptr(y), ptr(y_scale), ptr(y_shift), float(alpha),
+              ptr(shortcut), ptr(sc_scale), ptr(sc_shift), int(sc_stride), ptr(prelu), ptr(out), b, h, w, c, stream_ptr(),
+              work=12.0 * y.numel())
+    return out

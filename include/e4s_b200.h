@@ -132,6 +132,24 @@ int e4s_modconv3x3_tcp_fwd(const float* x, const void* w_hilo_bf16, const float*
                            float* y, int batch, int h, int w, int cin, int cout, int ncls, int up, int noise_b,
                            int act, void* stream);
 
+/* ---- RGI encoder conv stack (src/models/encoders/helpers.py:122-144, psp_encoders.py:285-309) ------------------
+ * Plain 3x3 convolution, padding 1, stride 1 or 2 (out_stride), on the persistent tensor-core kernel.
+ * x: pixel-major [B, H, W, Cin]; w_hilo_bf16: [2][1][9][Cout][Cin]; scale/shift: optional per-(sample, channel)
+ * affine [B, Cin] applied to in-image pixels while staging (InstanceNorm folded onto the operand; zero padding
+ * stays zero); prelu_slope: optional [Cout] PReLU epilogue; y: [B, H/out_stride, W/out_stride, Cout]. */
+int e4s_conv3x3_tcp_f32(const float* x, const void* w_hilo_bf16, const float* scale, const float* shift,
+                        const float* prelu_slope, float* y, int batch, int h, int w, int cin, int cout, int out_stride,
+                        void* stream);
+/* InstanceNorm2d statistics (biased variance, eps) of a pixel-major tensor as an affine: scale = rstd,
+ * shift = -mean*rstd, both [B, C].  sums_ws: [B, C, 2] workspace. */
+int e4s_instnorm_affine_f32(const float* x, float* sums_ws, float* scale, float* shift, int batch, int h, int w, int c,
+                            float eps, void* stream);
+/* out = act(alpha * (y*y_scale + y_shift) + shortcut), shortcut = shortcut[b, sc_stride*p, c] (* sc_scale + sc_shift
+ * when given); act = PReLU(prelu_slope) when given.  One residual-unit tail of bottleneck_IR_SE_Ours. */
+int e4s_norm_residual_f32(const float* y, const float* y_scale, const float* y_shift, float alpha, const float* shortcut,
+                          const float* sc_scale, const float* sc_shift, int sc_stride, const float* prelu_slope, float* out,
+                          int batch, int h, int w, int c, void* stream);
+
 /* Region-selected 1x1 modulated conv to RGB + bias + up-sampled skip: one ToRGB.forward
  * (model.py:422-448).  x: pixel-major [B, H, W, Cin]; wrgb: [3, Cin] (already scaled by
  * 1/sqrt(Cin)); s: [B, ncls, Cin]; label: [B, H, W] or NULL (ncls==1); bias: [3];

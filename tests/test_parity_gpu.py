@@ -369,3 +369,30 @@ def test_generator_golden_tensor_core_path(golden, monkeypatch):
             img, _, feats = G([cu(codes)], None, cu(mask), input_is_latent=True, noise=[cu(n) for n in noise])
         e = assert_close(img, golden[f"generator/{tag}/image"], REL_TOL, tag + " (tc)")
         print(f"{tag} tensor-core path: image max-rel err {e:.2e}")
+
+
+# ------------------------------------------------------------------------------ RGI encoder kernels
+def test_encoder_building_blocks():
+    """conv3x3 (stride 1/2, folded InstanceNorm, PReLU), instnorm statistics and the unit tail against torch CPU."""
+    import torch.nn.functional as F
+    from e4s_b200 import kernels as K
+    g = torch.Generator().manual_seed(41)
+    x = torch.randn(2, 64, 24, 20, generator=g) * 2.0 + 0.7
+    w = torch.randn(96, 64, 3, 3, generator=g) / 24.0
+    slope = 0.25 + 0.05 * torch.randn(96, generator=g)
+    xpm = cu(x).permute(0, 2, 3, 1).contiguous()
+    planes = K.split_bf16(cu(w).permute(2, 3, 0, 1).reshape(1, 9, 96, 64))
+    sc, sh = K.instnorm_affine(xpm)
+    mean, var = x.mean((2, 3)), x.var((2, 3), unbiased=False)
+    assert_close(sc, torch.rsqrt(var + 1e-5), 1e-5, "instnorm scale")
+    assert_close(sh, -mean * torch.rsqrt(var + 1e-5), 1e-4, "instnorm shift")
+    for stride in (1, 2):
+        y = K.conv3x3_tcp(xpm, planes, sc, sh, cu(slope), out_stride=stride)
+        ref = F.prelu(F.conv2d(F.instance_norm(x, eps=1e-5), w, stride=stride, padding=1), slope)
+        assert_close(y.permute(0, 3, 1, 2), ref, 1e-4, f"IN->conv->PReLU stride {stride}")
+    y = torch.randn(2, 12, 10, 96, generator=g)
+    short = torch.randn(2, 24, 20, 96, generator=g)
+    ys, yt = torch.rand(2, 96, generator=g) + 0.5, torch.randn(2, 96, generator=g)
+    out = K.norm_residual(cu(y), cu(ys), cu(yt), 0.5, shortcut=cu(short), sc_stride=2)
+    ref = 0.5 * (y * ys[:, None, None] + yt[:, None, None]) + short[:, ::2, ::2]
+    assert_close(out, ref, 1e-6, "unit tail")
