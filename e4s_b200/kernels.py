@@ -266,8 +266,15 @@ def tcp_eligible(cin: int, cout: int) -> bool:
     return cin % 32 == 0 and cout % 32 == 0
 
 
-def modconv3x3_tcp_fwd(x_pm: Tensor, w_hilo: Tensor, s: Tensor, dm: Optional[Tensor], label: Optional[Tensor],
+def modconv3x3_tcq_fwd(x_pm: Tensor, w_hilo: Tensor, s: Tensor, dm: Optional[Tensor], label: Optional[Tensor],
                        noise: Optional[Tensor], noise_w: Optional[Tensor], bias: Optional[Tensor], up: bool, act: bool) -> Tensor:
+    """Third-generation tensor-core path (TMA-staged activations, single pass on mixed-region tiles)."""
+    return modconv3x3_tcp_fwd(x_pm, w_hilo, s, dm, label, noise, noise_w, bias, up, act, entry="e4s_modconv3x3_tcq_fwd")
+
+
+def modconv3x3_tcp_fwd(x_pm: Tensor, w_hilo: Tensor, s: Tensor, dm: Optional[Tensor], label: Optional[Tensor],
+                       noise: Optional[Tensor], noise_w: Optional[Tensor], bias: Optional[Tensor], up: bool, act: bool,
+                       entry: str = "e4s_modconv3x3_tcp_fwd") -> Tensor:
     """Persistent tensor-core path; w_hilo: bf16 [2, nphase, 9, Cout, Cin].  Same contract as modconv3x3_fwd."""
     b, h, w, cin = x_pm.shape
     cout = w_hilo.shape[3]
@@ -276,7 +283,7 @@ def modconv3x3_tcp_fwd(x_pm: Tensor, w_hilo: Tensor, s: Tensor, dm: Optional[Ten
     y = torch.empty((b, h * m, w * m, cout), device=x_pm.device, dtype=torch.float32)
     nb = noise.shape[0] if noise is not None else 1
     with torch.cuda.device(x_pm.device):
-        _call("e4s_modconv3x3_tcp_fwd", _lib.load().e4s_modconv3x3_tcp_fwd, ptr(x_pm), ptr(w_hilo), ptr(s), ptr(dm), ptr(label),
+        _call(entry, getattr(_lib.load(), entry), ptr(x_pm), ptr(w_hilo), ptr(s), ptr(dm), ptr(label),
               ptr(noise), ptr(noise_w), ptr(bias), ptr(y), b, h, w, cin, cout, ncls, int(up), nb, int(act), stream_ptr(),
               work=2.0 * 9 * cin * cout * b * h * w)
     return y
@@ -361,11 +368,13 @@ def split_bf16(w: Tensor) -> Tensor:
 def conv3x3_tcp(x_pm: Tensor, w_hilo: Tensor, scale: Optional[Tensor] = None, shift: Optional[Tensor] = None,
                 prelu: Optional[Tensor] = None, out_stride: int = 1) -> Tensor:
     """x_pm [B,H,W,Cin]; w_hilo bf16 [2,1,9,Cout,Cin]; scale/shift [B,Cin]; prelu [Cout] -> [B,H/s,W/s,Cout]."""
+    import os
+    entry = "e4s_conv3x3_tcp_f32" if os.environ.get("E4S_B200_CONV", "auto") == "tcp" else "e4s_conv3x3_tcq_f32"
     b, h, w, cin = x_pm.shape
     cout = w_hilo.shape[3]
     y = torch.empty((b, h // out_stride, w // out_stride, cout), device=x_pm.device, dtype=torch.float32)
     with torch.cuda.device(x_pm.device):
-        _call("e4s_conv3x3_tcp_f32", _lib.load().e4s_conv3x3_tcp_f32, ptr(x_pm), ptr(w_hilo), ptr(scale), ptr(shift), ptr(prelu),
+        _call(entry, getattr(_lib.load(), entry), ptr(x_pm), ptr(w_hilo), ptr(scale), ptr(shift), ptr(prelu),
               ptr(y), b, h, w, cin, cout, out_stride, stream_ptr(), work=2.0 * 9 * cin * cout * b * h * w)
     return y
 

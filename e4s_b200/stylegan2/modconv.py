@@ -151,18 +151,18 @@ DEFAULT_CONV_MODE = "auto"
 
 
 def conv_path(prep: "PreparedConv", x_pm: Tensor) -> str:
-    """Kernel choice for one layer: 'tcp' (persistent tcgen05), 'tc' (first-generation tcgen05) or 'simt' (fp32).
-    E4S_B200_CONV=auto|tcp|tc|simt.  auto: the persistent tensor-core kernel for every eligible shape from 16x16 up;
-    below that a 128-pixel tile is mostly halo and the exact-fp32 SIMT kernel is used."""
+    """Kernel choice for one layer: 'tcq' / 'tcp' / 'tc' (third / second / first generation tcgen05 kernels) or 'simt'
+    (exact fp32).  E4S_B200_CONV=auto|tcq|tcp|tc|simt.  auto: the third-generation tensor-core kernel for every
+    eligible shape from 16x16 up; below that a 128-pixel tile is mostly halo and the SIMT kernel is used."""
     mode = os.environ.get("E4S_B200_CONV", DEFAULT_CONV_MODE)
     if prep.w_hilo is None or mode == "simt":
         return "simt"
     cout, cin = prep.w_hilo.shape[3], prep.w_hilo.shape[4]
     if mode == "tc":
         return "tc" if K.tc_eligible(cin, cout) else "simt"
-    if mode == "tcp":
-        return "tcp"
-    return "tcp" if x_pm.shape[1] * x_pm.shape[2] >= 256 else "simt"
+    if mode in ("tcp", "tcq"):
+        return mode
+    return "tcq" if x_pm.shape[1] * x_pm.shape[2] >= 256 else "simt"
 
 
 # ================================================================================== autograd
@@ -173,7 +173,9 @@ class StyledConvFn(Function):
     def forward(ctx, x_pm, s, noise, noise_w, bias, label, prep, up, demodulate, act):
         dm = K.demod(s, prep.wsq) if demodulate else None
         path = conv_path(prep, x_pm)
-        if path == "tcp":
+        if path == "tcq":
+            y = K.modconv3x3_tcq_fwd(x_pm, prep.w_hilo, s.contiguous(), dm, label, noise, noise_w, bias, up, act)
+        elif path == "tcp":
             y = K.modconv3x3_tcp_fwd(x_pm, prep.w_hilo, s.contiguous(), dm, label, noise, noise_w, bias, up, act)
         elif path == "tc":
             y = K.modconv3x3_tc_fwd(x_pm, prep.w_hilo, s.contiguous(), dm, label, noise, noise_w, bias, up, act)

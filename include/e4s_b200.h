@@ -132,6 +132,18 @@ int e4s_modconv3x3_tcp_fwd(const float* x, const void* w_hilo_bf16, const float*
                            float* y, int batch, int h, int w, int cin, int cout, int ncls, int up, int noise_b,
                            int act, void* stream);
 
+/* Third-generation tcgen05 implementation (csrc/modconv_tcq.cu): raw activation tiles streamed by 4-D TMA through a
+ * shared-memory ring, 32-channel K chunks everywhere, and ONE main-loop pass for tiles that mix regions (row-class
+ * operand staging).  Same contract and weight format; this is the kernel the synthesis network uses by default. */
+int e4s_modconv3x3_tcq_fwd(const float* x, const void* w_hilo_bf16, const float* s, const float* demod,
+                           const uint8_t* label, const float* noise, const float* noise_w, const float* bias,
+                           float* y, int batch, int h, int w, int cin, int cout, int ncls, int up, int noise_b,
+                           int act, void* stream);
+/* e4s_conv3x3_tcp_f32 on the third-generation kernel. */
+int e4s_conv3x3_tcq_f32(const float* x, const void* w_hilo_bf16, const float* scale, const float* shift,
+                        const float* prelu_slope, float* y, int batch, int h, int w, int cin, int cout, int out_stride,
+                        void* stream);
+
 /* ---- RGI encoder conv stack (src/models/encoders/helpers.py:122-144, psp_encoders.py:285-309) ------------------
  * Plain 3x3 convolution, padding 1, stride 1 or 2 (out_stride), on the persistent tensor-core kernel.
  * x: pixel-major [B, H, W, Cin]; w_hilo_bf16: [2][1][9][Cout][Cin]; scale/shift: optional per-(sample, channel)

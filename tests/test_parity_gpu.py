@@ -358,10 +358,25 @@ def test_tcp_kernel_matches_simt(b, cin, cout, hw, up, ncls, kind):
     print(f"tcp-vs-simt rel err {e:.2e}")
 
 
+@pytest.mark.parametrize("b,cin,cout,hw,up,ncls,kind", TC_CASES + TCP_EXTRA + [
+    (2, 64, 128, 30, True, 5, "blobs"),       # up-sampling with region borders: row-class pass + fix-up passes
+    (1, 160, 256, 28, False, 12, "iid"),      # every row its own region: pure row-class mode, 5 K chunks
+    (2, 256, 64, 16, True, 12, "iid"),        # up + iid: many fix-up passes
+])
+def test_tcq_kernel_matches_simt(b, cin, cout, hw, up, ncls, kind):
+    """The third-generation tcgen05 kernel (TMA-staged activations, single pass on mixed tiles) vs the fp32 SIMT kernel."""
+    K, prep, x, args = _tc_case(b, cin, cout, hw, up, ncls, kind, seed=cin + cout + hw)
+    ref = K.modconv3x3_fwd(x, prep.wt, *args)
+    out = K.modconv3x3_tcq_fwd(x, prep.w_hilo, *args)
+    torch.cuda.synchronize()
+    e = assert_close(out, ref, 1e-4, f"tcq vs simt {b},{cin},{cout},{hw},{up},{ncls},{kind}")
+    print(f"tcq-vs-simt rel err {e:.2e}")
+
+
 def test_generator_golden_tensor_core_path(golden, monkeypatch):
     """Whole generator with every eligible layer forced onto the persistent tcgen05 kernel (also at 4x4..8x8, where
     the default policy would pick the SIMT kernel), against the reference vectors."""
-    monkeypatch.setenv("E4S_B200_CONV", "tcp")
+    monkeypatch.setenv("E4S_B200_CONV", "tcq")
     for tag, size, K_, B, nc, msz, kind in [("g64_k5", 64, 5, 2, 5, 32, "blobs"), ("g256_k13", 256, 13, 1, 12, 512, "blobs")]:
         G, _ = _generator(size, K_)
         codes, mask, _, noise = O.synthetic_inputs(B, nc, size, msz, seed=size + K_, kind=kind)

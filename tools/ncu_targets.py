@@ -43,6 +43,8 @@ for name, cin, cout, r, up in [("c11@256", 128, 128, 256, False), ("c7@64", 512,
             K.modconv3x3_tc_fwd(xpm, prep.w_hilo, s, dm, None, noise, nw, bias, up, True)
         elif mode == "tcp" and prep.w_hilo is not None:
             K.modconv3x3_tcp_fwd(xpm, prep.w_hilo, s, dm, None, noise, nw, bias, up, True)
+        elif mode == "tcq" and prep.w_hilo is not None:
+            K.modconv3x3_tcq_fwd(xpm, prep.w_hilo, s, dm, None, noise, nw, bias, up, True)
         elif mode == "simt":
             K.modconv3x3_fwd(xpm, prep.wt, s, dm, None, noise, nw, bias, up, True)
     torch.cuda.synchronize()

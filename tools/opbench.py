@@ -121,10 +121,11 @@ def main():
                 if prep.w_hilo is None or not K.tc_eligible(cin, cout):
                     continue
                 fn = lambda: K.modconv3x3_tc_fwd(xpm, prep.w_hilo, s, dm, label, noise, nw, bias, bool(up), True)
-            elif mode == "tcp":
+            elif mode in ("tcp", "tcq"):
                 if prep.w_hilo is None:
                     continue
-                fn = lambda: K.modconv3x3_tcp_fwd(xpm, prep.w_hilo, s, dm, label, noise, nw, bias, bool(up), True)
+                f = K.modconv3x3_tcp_fwd if mode == "tcp" else K.modconv3x3_tcq_fwd
+                fn = lambda f=f: f(xpm, prep.w_hilo, s, dm, label, noise, nw, bias, bool(up), True)
             else:
                 fn = lambda: K.modconv3x3_fwd(xpm, prep.wt, s, dm, label, noise, nw, bias, bool(up), True)
             ms = timeit(fn, iters=3, warmup=1, flush=flush)
