@@ -49,6 +49,9 @@ def parse_args():
     ap.add_argument("--mask", default="faces", choices=["faces", "iid"], help="region-mask distribution")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--inversion-steps", type=int, default=20,
+                    help="also time this many steps of the texture-vector optimisation (scripts/optimization.py:209-232, "
+                         "l2 loss) on one face per GPU; 0 disables")
     return ap.parse_args()
 
 
@@ -290,6 +293,34 @@ def run_ours(args):
                             "(split-bf16 for fp32 parity) and 4x MACs on up-sampling layers, so tensor-pipe activity is ~3-12x "
                             "this fraction (ncu sm__pipe_tensor_cycles_active in profiles/)"}
 
+    # ---- BASELINE configs[2]: regional latent optimisation of one face per GPU (forward + backward + Adam per step)
+    inversion = None
+    if args.inversion_steps > 0:
+        from e4s_b200.optimization import invert
+        for prm in net.parameters():
+            prm.requires_grad = False
+        g2 = torch.Generator().manual_seed(300 + rank)
+        sv = 0.5 * torch.randn(1, ncls, 1280, generator=g2).to(dev)
+        onehot1 = onehot_dev[:1].contiguous()
+        with torch.no_grad():
+            target, _, _ = net.gen_img(None, net.cal_style_codes(0.5 * torch.randn(1, ncls, 1280, generator=g2).to(dev)), onehot1)
+        invert(net, target, onehot1, style_vectors=sv, steps=3)                      # warm-up (allocator, weight prep)
+        barrier()
+        K.LaunchStats.reset(False)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _, _, hist = invert(net, target, onehot1, style_vectors=sv, steps=args.inversion_steps)
+        e1.record()
+        barrier()
+        ims = e0.elapsed_time(e1) / args.inversion_steps
+        if world > 1:
+            tt = torch.tensor([ims], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ims = float(tt.item())
+        inversion = {"steps_timed": args.inversion_steps, "ms_per_step": ims, "launches_per_step": K.LaunchStats.launches / args.inversion_steps,
+                     "faces_per_sec_100_steps": world / (ims * 100 * 1e-3), "loss_first": float(hist[0]), "loss_last": float(hist[-1]),
+                     "config": f"one {size}x{size} face per GPU, {ncls} regions, Adam lr 1e-2, l2 loss, fresh noise per step"}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         pick_cpu_threads(ncls)                                        # also warms the thread pool / allocator
@@ -308,7 +339,7 @@ def run_ours(args):
                            "l2": "activations per layer (>= 0.5 GB at the top resolutions) exceed the 126 MB L2; no flush needed",
                            "parallelism": f"dp{world}: faces sharded, NCCL all-gather of final images" if world > 1 else "single GPU"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-                "kernels": kernels, "hbm_peak_gbs": hbm_gbs}
+                "kernels": kernels, "hbm_peak_gbs": hbm_gbs, "inversion": inversion}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -1,0 +1,678 @@
+// Region-selected modulated 3x3 convolution on tcgen05 tensor cores - fourth generation (sm_100a).
+//
+// Contract and implicit-GEMM formulation: modconv_tc.cu's header (8x16 pixel tile with 14 valid columns, taps as
+// row-shifted descriptors over one staged halo tile, split-bf16 x3 accumulation in fp32 TMEM, weights streamed by TMA
+// or resident).  Pipeline as the second generation (modconv_tcp.cu: persistent CTAs, TMA weight ring, double-buffered
+// TMEM accumulator, parities of an up-sampling layer along N), with the two lessons of the measurements under
+// profiles/ built in:
+//
+//  * ONE main-loop pass per tile, whatever the number of regions in it.  Region-pure tiles use the row-shift trick
+//    (operand staged once per K chunk, scaled by the region's style).  Mixed tiles switch to ROW-CLASS staging: the
+//    transform warps materialise the operand of every (tap, parity) separately and scale each row by the style of
+//    the region of that row's own output pixel; the MMAs then run per (tap, parity) with N = NTC.  That is 9x (36x
+//    for up-sampling layers) the staging work, done by eight transform warps out of L1, and it replaces 2-5 full
+//    passes per mixed tile (second generation) - the MMA work becomes independent of the mask.
+//  * A tight MMA issue loop.  ncu showed the 32->32 layer at 8 % tensor activity with one thread spending ~10k cycles
+//    per tile building descriptors and polling barriers for 54 MMAs of 16 cycles each.  Descriptor words are now
+//    precomputed (high word constant, low word = base + immediate), the tap / k loops are fully unrolled, and the
+//    resident / streamed and pure / mixed variants are separate straight-line code paths.
+//
+// K chunk: 64 channels (128-byte swizzle) when Cin % 64 == 0, else 32 channels (64-byte swizzle).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace tcr {
+
+constexpr int TH = 8, TWP = 16, TW = 14;
+constexpr int A_ROWS = 168;
+constexpr int NSTAGE_A = 2;
+constexpr int NUM_THREADS = 448;              // 14 warps: 0 weights, 1 MMA, 2-9 transform, 10-13 epilogue
+constexpr int NUM_XFORM = 256, NUM_EPI = 128;
+constexpr int SMEM_BUDGET = 227 * 1024 - 2048;
+
+struct Params {
+    const float* x;
+    const float* s;
+    const float* demod;
+    const uint8_t* label;
+    const float* noise;
+    const float* noise_w;
+    const float* bias;
+    float* y;
+    int batch, h, w, cin, cout, ncls, noise_b, act;       // act: 0 none, 1 sqrt(2)*lrelu(0.2), 2 PReLU(slope[c])
+    int tiles_x, tiles_y, n_tiles, items, nslot_b, resident;
+    const float* shift;
+    const float* slope;
+    int out_stride;
+};
+
+// ------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug traps (clean CUDA error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    for (;;) {
+#pragma unroll 1
+        for (int i = 0; i < 256; ++i)
+            if (mbar_try_wait(bar, parity)) return;
+        if (clock64() - t0 > 8000000000ll) __trap();
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+        "l"(map), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo_elem, float hi_elem) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+    return r;
+}
+__device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+
+struct Item {
+    int b, ty, tx, nt;
+};
+__device__ __forceinline__ Item decode_item(const Params& p, int it) {
+    Item r;
+    const int ptiles = p.tiles_x * p.tiles_y * p.batch;
+    r.nt = it / ptiles;
+    int pt = it - r.nt * ptiles;
+    r.tx = pt % p.tiles_x;
+    pt /= p.tiles_x;
+    r.ty = pt % p.tiles_y;
+    r.b = pt / p.tiles_y;
+    return r;
+}
+
+// Regions present among the valid (pixel, parity) outputs of a tile; one whole warp, every role recomputes it.
+template <int NPH>
+__device__ __forceinline__ uint32_t tile_class_mask(const Params& p, const Item& it, int lane) {
+    if (!p.label) return 1u;
+    constexpr int MUL = NPH == 4 ? 2 : 1;
+    const int ho = p.h * MUL, wo = p.w * MUL;
+    uint32_t m = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = lane + 32 * i;
+        const int iy = it.ty * TH + (r >> 4), ix = it.tx * TW + (r & 15);
+        if ((r & 15) < TW && iy < p.h && ix < p.w) {
+            const uint8_t* lp = p.label + ((int64_t)it.b * ho + iy * MUL) * wo + ix * MUL;
+            m |= 1u << min((int)lp[0], p.ncls - 1);
+            if (NPH == 4) m |= (1u << min((int)lp[1], p.ncls - 1)) | (1u << min((int)lp[wo], p.ncls - 1)) | (1u << min((int)lp[wo + 1], p.ncls - 1));
+        }
+    }
+    return __reduce_or_sync(0xffffffffu, m);
+}
+
+__device__ __forceinline__ void xform_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------- kernel
+template <int NTC, int KC, int NPH>
+__global__ void __launch_bounds__(NUM_THREADS, 1) modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, Params p) {
+    constexpr int N = NTC * NPH;
+    constexpr int ROWB = KC * 2;
+    constexpr int A_PLANE = A_ROWS * ROWB;
+    constexpr int A_STAGE = 2 * A_PLANE;
+    constexpr int B_SLOT = N * ROWB;
+    constexpr int NACC = (2 * N <= 512) ? 2 : 1;
+    constexpr int TMEM_COLS = (NACC * N <= 32) ? 32 : (NACC * N <= 64) ? 64 : (NACC * N <= 128) ? 128 : (NACC * N <= 256) ? 256 : 512;
+    constexpr uint32_t IDESC_BASE = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 4) << 24);
+    constexpr uint32_t IDESC_N = IDESC_BASE | ((uint32_t)(N >> 3) << 17);         // all parities in one MMA
+    constexpr uint32_t IDESC_Q = IDESC_BASE | ((uint32_t)(NTC >> 3) << 17);       // one parity
+    constexpr uint32_t DESC_HI = (uint32_t)((KC == 64 ? 1024u : 512u) >> 4) | (1u << 14) | ((KC == 64 ? 2u : 4u) << 29);
+    constexpr int KSTEPS = KC / 16;
+    constexpr int MUL = NPH == 4 ? 2 : 1;
+    constexpr int CPR = KC / 8;                       // 16-byte chunks per operand row
+    constexpr int PPS = NUM_XFORM / CPR;              // pixels (rows) covered per sweep of the transform threads
+    static_assert(N <= 256 && N % 16 == 0 && NTC % 16 == 0, "UMMA N");
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* a_buf = smem;                                                // [NSTAGE_A][hi|lo][A_ROWS][ROWB]
+    uint8_t* b_buf = a_buf + ((NSTAGE_A * A_STAGE + 1023) & ~1023);       // [nslot_b][N][ROWB]
+    float* s_tab = reinterpret_cast<float*>(b_buf + (size_t)p.nslot_b * B_SLOT);   // [2][ncls][KC] styles of the current chunk
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_tab + 2 * p.ncls * KC);
+    const int A_FULL = 0, A_EMPTY = A_FULL + NSTAGE_A, ACC_FULL = A_EMPTY + NSTAGE_A, ACC_EMPTY = ACC_FULL + NACC,
+              B_FULL = ACC_EMPTY + NACC, B_EMPTY = B_FULL + p.nslot_b, NBARS = B_EMPTY + p.nslot_b;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBARS);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ho = p.h * MUL, wo = p.w * MUL;
+    const int nchunks = p.cin / KC;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NSTAGE_A; ++i) mbar_init(smem_u32(&bars[A_FULL + i]), NUM_XFORM), mbar_init(smem_u32(&bars[A_EMPTY + i]), 1);
+        for (int i = 0; i < NACC; ++i) mbar_init(smem_u32(&bars[ACC_FULL + i]), 1), mbar_init(smem_u32(&bars[ACC_EMPTY + i]), NUM_EPI);
+        for (int i = 0; i < p.nslot_b; ++i) mbar_init(smem_u32(&bars[B_FULL + i]), 1), mbar_init(smem_u32(&bars[B_EMPTY + i]), 1);
+        fence_barrier_init();
+    }
+    if (warp == 0 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&wmap) : "memory");
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================================================================== weight-plane producer (TMA): one pass per tile
+        int slot = 0;
+        uint32_t ph = 0;
+        const int rows_lo = (NPH * 9) * p.cout;
+        bool loaded_resident = false;
+        if (lane == 0) {
+            for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
+                if (p.resident && loaded_resident) break;
+                const Item item = decode_item(p, it);
+                for (int kc = 0; kc < nchunks; ++kc)
+                    for (int tap = 0; tap < 9; ++tap)
+                        for (int hl = 0; hl < 2; ++hl) {
+                            if (!p.resident) mbar_wait(smem_u32(&bars[B_EMPTY + slot]), ph ^ 1);
+                            const uint32_t full = smem_u32(&bars[B_FULL + slot]);
+                            mbar_expect_tx(full, B_SLOT);
+                            const uint32_t dst = smem_u32(b_buf + (size_t)slot * B_SLOT);
+#pragma unroll
+                            for (int q = 0; q < NPH; ++q)
+                                tma_load_2d(dst + q * NTC * ROWB, &wmap, kc * KC, hl * rows_lo + (q * 9 + tap) * p.cout + item.nt * NTC, full);
+                            if (++slot == p.nslot_b) slot = 0, ph ^= 1;
+                        }
+                loaded_resident = true;
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===================================================================== MMA issuer
+        int sa = 0, slot = 0, acc = 0;
+        uint32_t pa = 0, pb = 0, pacc[2] = {0, 0};
+        bool b_ready = false;                            // resident weights: waited for once
+        const uint32_t bars0 = smem_u32(bars);
+        const uint32_t a0 = smem_u32(a_buf), b0 = smem_u32(b_buf);
+        auto desc = [](uint32_t lo) -> uint64_t { return ((uint64_t)DESC_HI << 32) | lo; };
+        auto lo_of = [](uint32_t addr) -> uint32_t { return (addr >> 4) | 0x10000u; };
+        for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
+            const Item item = decode_item(p, it);
+            const uint32_t classes = tile_class_mask<NPH>(p, item, lane);
+            const bool mixed = (classes & (classes - 1)) != 0;
+            if (lane == 0) {
+                mbar_wait(bars0 + 8 * (ACC_EMPTY + acc), pacc[acc] ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * N);
+                if (p.resident) slot = 0;
+                const bool wait_b = !p.resident || !b_ready;
+                if (!mixed) {
+                    // ---------------- region-pure tile: operand staged once per chunk, taps are row shifts
+                    for (int kc = 0; kc < nchunks; ++kc) {
+                        mbar_wait(bars0 + 8 * (A_FULL + sa), pa);
+                        tc_fence_after();
+                        const uint32_t ah = lo_of(a0 + sa * A_STAGE), al = ah + (A_PLANE >> 4);
+#pragma unroll
+                        for (int tap = 0; tap < 9; ++tap) {
+                            const uint32_t roff = (uint32_t)(((tap / 3) * TWP + (tap % 3) + 1) * ROWB) >> 4;
+                            if (wait_b) mbar_wait(bars0 + 8 * (B_FULL + slot), pb);
+                            tc_fence_after();
+                            uint32_t bl = lo_of(b0 + slot * B_SLOT);
+#pragma unroll
+                            for (int k = 0; k < KSTEPS; ++k) {
+                                umma_bf16(d_tmem, desc(ah + roff + 2 * k), desc(bl + 2 * k), IDESC_N, (kc | tap | k) != 0 ? 1u : 0u);
+                                umma_bf16(d_tmem, desc(al + roff + 2 * k), desc(bl + 2 * k), IDESC_N, 1u);
+                            }
+                            if (!p.resident) umma_commit(bars0 + 8 * (B_EMPTY + slot));
+                            if (++slot == p.nslot_b) slot = 0, pb ^= 1;
+                            if (wait_b) mbar_wait(bars0 + 8 * (B_FULL + slot), pb);
+                            tc_fence_after();
+                            bl = lo_of(b0 + slot * B_SLOT);
+#pragma unroll
+                            for (int k = 0; k < KSTEPS; ++k) umma_bf16(d_tmem, desc(ah + roff + 2 * k), desc(bl + 2 * k), IDESC_N, 1u);
+                            if (!p.resident) umma_commit(bars0 + 8 * (B_EMPTY + slot));
+                            if (++slot == p.nslot_b) slot = 0, pb ^= 1;
+                        }
+                        umma_commit(bars0 + 8 * (A_EMPTY + sa));
+                        if (++sa == NSTAGE_A) sa = 0, pa ^= 1;
+                    }
+                } else {
+                    // ---------------- mixed tile: one operand slot per (tap, parity), MMAs of N = NTC
+                    for (int kc = 0; kc < nchunks; ++kc) {
+#pragma unroll 1
+                        for (int tap = 0; tap < 9; ++tap) {
+                            int slot_lo = slot + 1;
+                            uint32_t pb_lo = pb;
+                            if (slot_lo == p.nslot_b) slot_lo = 0, pb_lo ^= 1;
+                            if (wait_b) {
+                                mbar_wait(bars0 + 8 * (B_FULL + slot), pb);
+                                mbar_wait(bars0 + 8 * (B_FULL + slot_lo), pb_lo);
+                            }
+                            const uint32_t bh = lo_of(b0 + slot * B_SLOT), bl = lo_of(b0 + slot_lo * B_SLOT);
+#pragma unroll
+                            for (int q = 0; q < NPH; ++q) {
+                                mbar_wait(bars0 + 8 * (A_FULL + sa), pa);
+                                tc_fence_after();
+                                const uint32_t ah = lo_of(a0 + sa * A_STAGE), al = ah + (A_PLANE >> 4);
+                                const uint32_t boff = (uint32_t)(q * NTC * ROWB) >> 4;
+                                const uint32_t dq = d_tmem + (uint32_t)(q * NTC);
+#pragma unroll
+                                for (int k = 0; k < KSTEPS; ++k) {
+                                    umma_bf16(dq, desc(ah + 2 * k), desc(bh + boff + 2 * k), IDESC_Q, (kc | tap | k) != 0 ? 1u : 0u);
+                                    umma_bf16(dq, desc(al + 2 * k), desc(bh + boff + 2 * k), IDESC_Q, 1u);
+                                    umma_bf16(dq, desc(ah + 2 * k), desc(bl + boff + 2 * k), IDESC_Q, 1u);
+                                }
+                                umma_commit(bars0 + 8 * (A_EMPTY + sa));
+                                if (++sa == NSTAGE_A) sa = 0, pa ^= 1;
+                            }
+                            if (!p.resident) {
+                                umma_commit(bars0 + 8 * (B_EMPTY + slot));
+                                umma_commit(bars0 + 8 * (B_EMPTY + slot_lo));
+                            }
+                            slot = slot_lo, pb = pb_lo;
+                            if (++slot == p.nslot_b) slot = 0, pb ^= 1;
+                        }
+                    }
+                }
+                umma_commit(bars0 + 8 * (ACC_FULL + acc));
+                pacc[acc] ^= 1;
+                if (NACC == 2) acc ^= 1;
+                b_ready = true;
+            }
+            __syncwarp();
+        }
+    } else if (warp < 10) {
+        // ===================================================================== activation transform (A producers), 256 threads
+        const int t = threadIdx.x - 64;                  // 0..255
+        const int c8 = t % CPR;
+        const int pix0 = t / CPR;                        // 0..PPS-1
+        constexpr int NSW_SHIFT = (160 + PPS - 1) / PPS; // sweeps over the 160 halo pixels (5 or 3)
+        constexpr int NSW_ROWS = 128 / PPS;              // sweeps over the 128 operand rows (4 or 2)
+        int sa = 0;
+        uint32_t pa = 0;
+        uint32_t chunk_ctr = 0;                          // selects the s_tab buffer
+        for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
+            const Item item = decode_item(p, it);
+            const uint32_t classes = tile_class_mask<NPH>(p, item, lane);
+            const bool mixed = (classes & (classes - 1)) != 0;
+            const float* xb = p.x + (int64_t)item.b * p.h * p.w * p.cin;
+            const int y0 = item.ty * TH, x0 = item.tx * TW;
+            if (!mixed) {
+                const int cls = __ffs(classes) - 1;
+                const float* sc = p.s ? p.s + ((int64_t)item.b * p.ncls + cls) * p.cin : nullptr;
+                const float* sh = p.shift ? p.shift + ((int64_t)item.b * p.ncls + cls) * p.cin : nullptr;
+                for (int kc = 0; kc < nchunks; ++kc) {
+                    const int ch = kc * KC + 8 * c8;
+                    const float4 one4 = make_float4(1.f, 1.f, 1.f, 1.f), zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float4 s0 = sc ? __ldg(reinterpret_cast<const float4*>(sc + ch)) : one4;
+                    const float4 s1 = sc ? __ldg(reinterpret_cast<const float4*>(sc + ch + 4)) : one4;
+                    const float4 t0 = sh ? __ldg(reinterpret_cast<const float4*>(sh + ch)) : zero4;
+                    const float4 t1 = sh ? __ldg(reinterpret_cast<const float4*>(sh + ch + 4)) : zero4;
+                    float4 v0[NSW_SHIFT], v1[NSW_SHIFT];
+                    bool inb[NSW_SHIFT];
+#pragma unroll
+                    for (int i = 0; i < NSW_SHIFT; ++i) {
+                        const int hp = pix0 + PPS * i;
+                        const int gy = y0 - 1 + (hp >> 4), gx = x0 - 1 + (hp & 15);
+                        v0[i] = zero4, v1[i] = zero4;
+                        inb[i] = hp < 160 && gy >= 0 && gy < p.h && gx >= 0 && gx < p.w;
+                        if (inb[i]) {
+                            const float* src = xb + ((int64_t)gy * p.w + gx) * p.cin + ch;
+                            v0[i] = __ldg(reinterpret_cast<const float4*>(src));
+                            v1[i] = __ldg(reinterpret_cast<const float4*>(src + 4));
+                        }
+                    }
+                    mbar_wait(smem_u32(&bars[A_EMPTY + sa]), pa ^ 1);
+                    uint8_t* hi_plane = a_buf + sa * A_STAGE;
+                    uint8_t* lo_plane = hi_plane + A_PLANE;
+#pragma unroll
+                    for (int i = 0; i < NSW_SHIFT; ++i) {
+                        const int hp = pix0 + PPS * i;
+                        if (hp >= 160) continue;
+                        const int row = hp + 1;
+                        float f[8] = {v0[i].x * s0.x, v0[i].y * s0.y, v0[i].z * s0.z, v0[i].w * s0.w,
+                                      v1[i].x * s1.x, v1[i].y * s1.y, v1[i].z * s1.z, v1[i].w * s1.w};
+                        if (sh && inb[i]) {      // zero padding applies to the NORMALISED tensor: shift in-image pixels only
+                            f[0] += t0.x, f[1] += t0.y, f[2] += t0.z, f[3] += t0.w;
+                            f[4] += t1.x, f[5] += t1.y, f[6] += t1.z, f[7] += t1.w;
+                        }
+                        uint32_t hi[4], lo[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float h0 = bf16_round(f[2 * j]), h1 = bf16_round(f[2 * j + 1]);
+                            hi[j] = pack_bf16x2(h0, h1);
+                            lo[j] = pack_bf16x2(f[2 * j] - h0, f[2 * j + 1] - h1);
+                        }
+                        const uint32_t sx = KC == 64 ? (uint32_t)(row & 7) : (uint32_t)((row >> 1) & 3);
+                        const uint32_t off = (uint32_t)row * ROWB + (((uint32_t)c8 ^ sx) << 4);
+                        *reinterpret_cast<uint4*>(hi_plane + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                        *reinterpret_cast<uint4*>(lo_plane + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    }
+                    fence_proxy_async();
+                    mbar_arrive(smem_u32(&bars[A_FULL + sa]));
+                    if (++sa == NSTAGE_A) sa = 0, pa ^= 1;
+                }
+            } else {
+                // ---- mixed tile: per (tap, parity) operand tiles, every row scaled by the style of its own output pixel's region
+                uint32_t rcls[NSW_ROWS];                 // 4 x 8-bit regions (one per parity) of each of my rows
+#pragma unroll
+                for (int i = 0; i < NSW_ROWS; ++i) {
+                    const int r = pix0 + PPS * i;
+                    const int iy = y0 + (r >> 4), ix = x0 + (r & 15);
+                    rcls[i] = 0;
+                    if ((r & 15) < TW && iy < p.h && ix < p.w) {
+                        const uint8_t* lp = p.label + ((int64_t)item.b * ho + iy * MUL) * wo + ix * MUL;
+                        uint32_t c0 = min((int)lp[0], p.ncls - 1);
+                        rcls[i] = c0;
+                        if (NPH == 4)
+                            rcls[i] = c0 | ((uint32_t)min((int)lp[1], p.ncls - 1) << 8) | ((uint32_t)min((int)lp[wo], p.ncls - 1) << 16) |
+                                      ((uint32_t)min((int)lp[wo + 1], p.ncls - 1) << 24);
+                    }
+                }
+                const float* sbase = p.s + (int64_t)item.b * p.ncls * p.cin;
+                for (int kc = 0; kc < nchunks; ++kc) {
+                    // styles of every region for this chunk -> shared table (double-buffered across chunks)
+                    float* tab = s_tab + (chunk_ctr & 1) * p.ncls * KC;
+                    ++chunk_ctr;
+                    for (int e = t; e < p.ncls * (KC / 4); e += NUM_XFORM) {
+                        const int c = e / (KC / 4), j = e - c * (KC / 4);
+                        *reinterpret_cast<float4*>(tab + c * KC + 4 * j) =
+                            __ldg(reinterpret_cast<const float4*>(sbase + (int64_t)c * p.cin + kc * KC + 4 * j));
+                    }
+                    xform_barrier();
+                    const int ch = kc * KC + 8 * c8;
+#pragma unroll 1
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const int dy = tap / 3, dx = tap - 3 * dy;
+                        float4 v0[NSW_ROWS], v1[NSW_ROWS];
+#pragma unroll
+                        for (int i = 0; i < NSW_ROWS; ++i) {
+                            const int r = pix0 + PPS * i;
+                            const int gy = y0 - 1 + (r >> 4) + dy, gx = x0 - 1 + (r & 15) + dx;
+                            v0[i] = make_float4(0.f, 0.f, 0.f, 0.f), v1[i] = v0[i];
+                            if (gy >= 0 && gy < p.h && gx >= 0 && gx < p.w) {
+                                const float* src = xb + ((int64_t)gy * p.w + gx) * p.cin + ch;
+                                v0[i] = __ldg(reinterpret_cast<const float4*>(src));
+                                v1[i] = __ldg(reinterpret_cast<const float4*>(src + 4));
+                            }
+                        }
+#pragma unroll
+                        for (int q = 0; q < NPH; ++q) {
+                            mbar_wait(smem_u32(&bars[A_EMPTY + sa]), pa ^ 1);
+                            uint8_t* hi_plane = a_buf + sa * A_STAGE;
+                            uint8_t* lo_plane = hi_plane + A_PLANE;
+#pragma unroll
+                            for (int i = 0; i < NSW_ROWS; ++i) {
+                                const int r = pix0 + PPS * i;
+                                const int cl = (int)((rcls[i] >> (8 * q)) & 0xffu);
+                                const float4 s0 = *reinterpret_cast<const float4*>(tab + cl * KC + 8 * c8);
+                                const float4 s1 = *reinterpret_cast<const float4*>(tab + cl * KC + 8 * c8 + 4);
+                                float f[8] = {v0[i].x * s0.x, v0[i].y * s0.y, v0[i].z * s0.z, v0[i].w * s0.w,
+                                              v1[i].x * s1.x, v1[i].y * s1.y, v1[i].z * s1.z, v1[i].w * s1.w};
+                                uint32_t hi[4], lo[4];
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const float h0 = bf16_round(f[2 * j]), h1 = bf16_round(f[2 * j + 1]);
+                                    hi[j] = pack_bf16x2(h0, h1);
+                                    lo[j] = pack_bf16x2(f[2 * j] - h0, f[2 * j + 1] - h1);
+                                }
+                                const uint32_t sx = KC == 64 ? (uint32_t)(r & 7) : (uint32_t)((r >> 1) & 3);
+                                const uint32_t off = (uint32_t)r * ROWB + (((uint32_t)c8 ^ sx) << 4);
+                                *reinterpret_cast<uint4*>(hi_plane + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                                *reinterpret_cast<uint4*>(lo_plane + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                            }
+                            fence_proxy_async();
+                            mbar_arrive(smem_u32(&bars[A_FULL + sa]));
+                            if (++sa == NSTAGE_A) sa = 0, pa ^= 1;
+                        }
+                    }
+                }
+            }
+        }
+    } else {
+        // ===================================================================== epilogue: one pass per tile, region per (pixel, parity)
+        const uint32_t quarter = (uint32_t)(warp & 3);
+        const int m_row = quarter * 32 + lane;
+        const int ty = m_row >> 4, tx = m_row & 15;
+        int acc = 0;
+        uint32_t pacc[2] = {0, 0};
+        const float nw = (p.noise && p.noise_w) ? __ldg(p.noise_w) : 0.f;
+        for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
+            const Item item = decode_item(p, it);
+            const int iy = item.ty * TH + ty, ix = item.tx * TW + tx;
+            const bool strided = (NPH == 1 && p.out_stride == 2);
+            const bool mine = tx < TW && iy < p.h && ix < p.w && (!strided || ((iy | ix) & 1) == 0);
+            const int n0 = item.nt * NTC;
+            mbar_wait(smem_u32(&bars[ACC_FULL + acc]), pacc[acc]);
+            pacc[acc] ^= 1;
+            tc_fence_after();
+#pragma unroll
+            for (int q = 0; q < NPH; ++q) {
+                const int oy = strided ? (iy >> 1) : iy * MUL + (q >> 1), ox = strided ? (ix >> 1) : ix * MUL + (q & 1);
+                const int oh = strided ? (p.h >> 1) : ho, ow = strided ? (p.w >> 1) : wo;
+                int cls = 0;
+                if (mine && p.label) cls = min((int)p.label[((int64_t)item.b * oh + oy) * ow + ox], p.ncls - 1);
+                const float* dm = p.demod ? p.demod + ((int64_t)item.b * p.ncls + cls) * p.cout + n0 : nullptr;
+                float nz = 0.f;
+                if (mine && p.noise) nz = nw * __ldg(p.noise + ((int64_t)(p.noise_b == 1 ? 0 : item.b) * oh + oy) * ow + ox);
+                float* dst = p.y + (((int64_t)item.b * oh + oy) * ow + ox) * p.cout + n0;
+#pragma unroll 1
+                for (int j = 0; j < NTC / 32; ++j) {
+                    uint32_t r[32];
+                    tmem_ld32(tmem_base + ((quarter * 32u) << 16) + (uint32_t)(acc * N + q * NTC + j * 32), r);
+                    if (mine) {
+#pragma unroll
+                        for (int g = 0; g < 8; ++g) {
+                            const int co = j * 32 + 4 * g;
+                            const float4 d = dm ? __ldg(reinterpret_cast<const float4*>(dm + co)) : make_float4(1.f, 1.f, 1.f, 1.f);
+                            const float4 bv = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n0 + co)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            float4 o;
+                            o.x = __uint_as_float(r[4 * g + 0]) * d.x + nz + bv.x;
+                            o.y = __uint_as_float(r[4 * g + 1]) * d.y + nz + bv.y;
+                            o.z = __uint_as_float(r[4 * g + 2]) * d.z + nz + bv.z;
+                            o.w = __uint_as_float(r[4 * g + 3]) * d.w + nz + bv.w;
+                            if (p.act == 1) {
+                                const float k = 1.41421356237309515f;
+                                o.x = lrelu_scaled(o.x, 0.2f, k), o.y = lrelu_scaled(o.y, 0.2f, k);
+                                o.z = lrelu_scaled(o.z, 0.2f, k), o.w = lrelu_scaled(o.w, 0.2f, k);
+                            } else if (p.act == 2) {
+                                const float4 sl = __ldg(reinterpret_cast<const float4*>(p.slope + n0 + co));
+                                o.x = o.x > 0.f ? o.x : o.x * sl.x, o.y = o.y > 0.f ? o.y : o.y * sl.y;
+                                o.z = o.z > 0.f ? o.z : o.z * sl.z, o.w = o.w > 0.f ? o.w : o.w * sl.w;
+                            }
+                            *reinterpret_cast<float4*>(dst + co) = o;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(smem_u32(&bars[ACC_EMPTY + acc]));
+            if (NACC == 2) acc ^= 1;
+        }
+    }
+
+    // ---- teardown
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+        else
+            cudaGetLastError();
+    });
+    return fn;
+}
+
+static int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = E4S_NUM_SMS;
+    }
+    return n;
+}
+
+template <int NTC, int KC, int NPH>
+static int launch(const void* w_hilo, Params p, cudaStream_t st) {
+    constexpr int N = NTC * NPH, ROWB = KC * 2;
+    constexpr int A_BYTES = ((NSTAGE_A * 2 * A_ROWS * ROWB) + 1023) & ~1023;
+    constexpr int B_SLOT = N * ROWB;
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return E4S_ERR_ARCH;
+    CUtensorMap map;
+    cuuint64_t dims[2] = {(cuuint64_t)p.cin, (cuuint64_t)2 * NPH * 9 * p.cout};
+    cuuint64_t strides[1] = {(cuuint64_t)p.cin * 2};
+    cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)NTC};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult cr = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w_hilo), dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return 700 + (int)cr;
+
+    p.tiles_x = (int)e4s_ceil_div(p.w, TW);
+    p.tiles_y = (int)e4s_ceil_div(p.h, TH);
+    p.n_tiles = p.cout / NTC;
+    const int64_t items = (int64_t)p.tiles_x * p.tiles_y * p.batch * p.n_tiles;
+    if (items >= (1ll << 31)) return E4S_ERR_SHAPE;
+    p.items = (int)items;
+    const int planes = (p.cin / KC) * 18;
+    const int tab_bytes = 2 * p.ncls * KC * 4;
+    int max_slots = (SMEM_BUDGET - A_BYTES - tab_bytes - 1024) / B_SLOT;
+    if (max_slots > 36) max_slots = 36;
+    if (max_slots < 4) return E4S_ERR_SHAPE;
+    p.resident = (p.n_tiles == 1 && planes <= max_slots) ? 1 : 0;
+    p.nslot_b = p.resident ? planes : (max_slots > 8 ? 8 : max_slots);
+    const size_t smem = 1024 + A_BYTES + (size_t)p.nslot_b * B_SLOT + tab_bytes + (size_t)(2 * NSTAGE_A + 4 + 2 * p.nslot_b) * 8 + 64;
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        if (cudaFuncSetAttribute(modconv3x3_tcr_kernel<NTC, KC, NPH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return (int)cudaGetLastError();
+        smem_set = smem;
+    }
+    const int grid = p.items < num_sms() ? p.items : num_sms();
+    modconv3x3_tcr_kernel<NTC, KC, NPH><<<grid, NUM_THREADS, smem, st>>>(map, p);
+    return e4s_launch_status();
+}
+
+int dispatch(const void* w_hilo_bf16, Params p, int up, cudaStream_t st) {
+    const int cin = p.cin, cout = p.cout;
+    const bool k64 = (cin % 64) == 0;
+    if (!up) {
+        if (k64) {
+            if (cout % 256 == 0) {
+                const int rc = launch<256, 64, 1>(w_hilo_bf16, p, st);
+                if (rc != E4S_ERR_SHAPE) return rc;          // too many regions for the style table next to 32-KB weight slots
+            }
+            if (cout % 128 == 0) return launch<128, 64, 1>(w_hilo_bf16, p, st);
+            if (cout % 64 == 0) return launch<64, 64, 1>(w_hilo_bf16, p, st);
+            return launch<32, 64, 1>(w_hilo_bf16, p, st);
+        }
+        if (cout % 64 == 0) return launch<64, 32, 1>(w_hilo_bf16, p, st);
+        return launch<32, 32, 1>(w_hilo_bf16, p, st);
+    }
+    if (k64) {
+        if (cout % 64 == 0) return launch<64, 64, 4>(w_hilo_bf16, p, st);
+        return launch<32, 64, 4>(w_hilo_bf16, p, st);
+    }
+    return launch<32, 32, 4>(w_hilo_bf16, p, st);
+}
+
+}  // namespace tcr
+
+extern "C" int e4s_modconv3x3_tcr_fwd(const float* x, const void* w_hilo_bf16, const float* s, const float* demod,
+                                      const uint8_t* label, const float* noise, const float* noise_w, const float* bias,
+                                      float* y, int batch, int h, int w, int cin, int cout, int ncls, int up, int noise_b,
+                                      int act, void* stream) {
+    E4S_REQUIRE(x && w_hilo_bf16 && s && y, E4S_ERR_ARG);
+    E4S_REQUIRE(batch > 0 && h > 0 && w > 0 && cin > 0 && cout > 0 && ncls > 0 && ncls <= 32, E4S_ERR_ARG);
+    E4S_REQUIRE((cin % 32) == 0 && (cout % 32) == 0, E4S_ERR_SHAPE);
+    E4S_REQUIRE(label || ncls == 1, E4S_ERR_ARG);
+    E4S_REQUIRE(!noise || (noise_w && (noise_b == 1 || noise_b == batch)), E4S_ERR_ARG);
+    E4S_REQUIRE(e4s_aligned16(x) && e4s_aligned16(w_hilo_bf16) && e4s_aligned16(s) && e4s_aligned16(y) &&
+                    (!demod || e4s_aligned16(demod)) && (!bias || e4s_aligned16(bias)),
+                E4S_ERR_ALIGN);
+    tcr::Params p{x, s, demod, label, noise, noise_w, bias, y, batch, h, w, cin, cout, ncls, noise_b, act ? 1 : 0,
+                  0, 0, 0, 0, 0, 0, nullptr, nullptr, 1};
+    return tcr::dispatch(w_hilo_bf16, p, up, (cudaStream_t)stream);
+}
+
+extern "C" int e4s_conv3x3_tcr_f32(const float* x, const void* w_hilo_bf16, const float* scale, const float* shift,
+                                   const float* prelu_slope, float* y, int batch, int h, int w, int cin, int cout,
+                                   int out_stride, void* stream) {
+    E4S_REQUIRE(x && w_hilo_bf16 && y, E4S_ERR_ARG);
+    E4S_REQUIRE(batch > 0 && h > 0 && w > 0 && cin > 0 && cout > 0, E4S_ERR_ARG);
+    E4S_REQUIRE((cin % 32) == 0 && (cout % 32) == 0, E4S_ERR_SHAPE);
+    E4S_REQUIRE(out_stride == 1 || (out_stride == 2 && (h % 2) == 0 && (w % 2) == 0), E4S_ERR_SHAPE);
+    E4S_REQUIRE(e4s_aligned16(x) && e4s_aligned16(w_hilo_bf16) && e4s_aligned16(y) && (!scale || e4s_aligned16(scale)) &&
+                    (!shift || e4s_aligned16(shift)) && (!prelu_slope || e4s_aligned16(prelu_slope)),
+                E4S_ERR_ALIGN);
+    tcr::Params p{x, scale, nullptr, nullptr, nullptr, nullptr, nullptr, y, batch, h, w, cin, cout, 1, 1, prelu_slope ? 2 : 0,
+                  0, 0, 0, 0, 0, 0, shift, prelu_slope, out_stride};
+    return tcr::dispatch(w_hilo_bf16, p, 0, (cudaStream_t)stream);
+}

@@ -266,6 +266,12 @@ def tcp_eligible(cin: int, cout: int) -> bool:
     return cin % 32 == 0 and cout % 32 == 0
 
 
+def modconv3x3_tcr_fwd(x_pm: Tensor, w_hilo: Tensor, s: Tensor, dm: Optional[Tensor], label: Optional[Tensor],
+                       noise: Optional[Tensor], noise_w: Optional[Tensor], bias: Optional[Tensor], up: bool, act: bool) -> Tensor:
+    """Fourth-generation tensor-core path (one pass per tile on any mask, tight MMA issue loop)."""
+    return modconv3x3_tcp_fwd(x_pm, w_hilo, s, dm, label, noise, noise_w, bias, up, act, entry="e4s_modconv3x3_tcr_fwd")
+
+
 def modconv3x3_tcq_fwd(x_pm: Tensor, w_hilo: Tensor, s: Tensor, dm: Optional[Tensor], label: Optional[Tensor],
                        noise: Optional[Tensor], noise_w: Optional[Tensor], bias: Optional[Tensor], up: bool, act: bool) -> Tensor:
     """Third-generation tensor-core path (TMA-staged activations, single pass on mixed-region tiles)."""
@@ -358,6 +364,9 @@ def torgb_bwd(g: Tensor, x_pm: Tensor, wrgb: Tensor, s: Tensor, label: Optional[
 
 
 # ------------------------------------------------------------------------------ encoder conv stack
+ENCODER_CONV_ENTRY = "e4s_conv3x3_tcp_f32"
+
+
 def split_bf16(w: Tensor) -> Tensor:
     """fp32 -> stacked (hi, lo) bf16 planes with hi + lo == w to ~2^-17 relative."""
     hi = w.to(torch.bfloat16)
@@ -369,7 +378,8 @@ def conv3x3_tcp(x_pm: Tensor, w_hilo: Tensor, scale: Optional[Tensor] = None, sh
                 prelu: Optional[Tensor] = None, out_stride: int = 1) -> Tensor:
     """x_pm [B,H,W,Cin]; w_hilo bf16 [2,1,9,Cout,Cin]; scale/shift [B,Cin]; prelu [Cout] -> [B,H/s,W/s,Cout]."""
     import os
-    entry = "e4s_conv3x3_tcp_f32" if os.environ.get("E4S_B200_CONV", "auto") == "tcp" else "e4s_conv3x3_tcq_f32"
+    entry = {"tcp": "e4s_conv3x3_tcp_f32", "tcq": "e4s_conv3x3_tcq_f32", "tcr": "e4s_conv3x3_tcr_f32"}.get(
+        os.environ.get("E4S_B200_CONV", "auto"), ENCODER_CONV_ENTRY)
     b, h, w, cin = x_pm.shape
     cout = w_hilo.shape[3]
     y = torch.empty((b, h // out_stride, w // out_stride, cout), device=x_pm.device, dtype=torch.float32)

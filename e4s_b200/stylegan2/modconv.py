@@ -147,7 +147,10 @@ def warn_frozen(weight: Tensor):
         _warned_weight_grad = True
 
 
-DEFAULT_CONV_MODE = "auto"
+DEFAULT_CONV_MODE = "auto"   # auto -> tcp (second generation) until a later generation beats it end to end
+
+
+AUTO_KERNEL = "tcp"
 
 
 def conv_path(prep: "PreparedConv", x_pm: Tensor) -> str:
@@ -160,9 +163,9 @@ def conv_path(prep: "PreparedConv", x_pm: Tensor) -> str:
     cout, cin = prep.w_hilo.shape[3], prep.w_hilo.shape[4]
     if mode == "tc":
         return "tc" if K.tc_eligible(cin, cout) else "simt"
-    if mode in ("tcp", "tcq"):
+    if mode in ("tcp", "tcq", "tcr"):
         return mode
-    return "tcq" if x_pm.shape[1] * x_pm.shape[2] >= 256 else "simt"
+    return AUTO_KERNEL if x_pm.shape[1] * x_pm.shape[2] >= 256 else "simt"
 
 
 # ================================================================================== autograd
@@ -173,7 +176,9 @@ class StyledConvFn(Function):
     def forward(ctx, x_pm, s, noise, noise_w, bias, label, prep, up, demodulate, act):
         dm = K.demod(s, prep.wsq) if demodulate else None
         path = conv_path(prep, x_pm)
-        if path == "tcq":
+        if path == "tcr":
+            y = K.modconv3x3_tcr_fwd(x_pm, prep.w_hilo, s.contiguous(), dm, label, noise, noise_w, bias, up, act)
+        elif path == "tcq":
             y = K.modconv3x3_tcq_fwd(x_pm, prep.w_hilo, s.contiguous(), dm, label, noise, noise_w, bias, up, act)
         elif path == "tcp":
             y = K.modconv3x3_tcp_fwd(x_pm, prep.w_hilo, s.contiguous(), dm, label, noise, noise_w, bias, up, act)

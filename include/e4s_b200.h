@@ -144,6 +144,16 @@ int e4s_conv3x3_tcq_f32(const float* x, const void* w_hilo_bf16, const float* sc
                         const float* prelu_slope, float* y, int batch, int h, int w, int cin, int cout, int out_stride,
                         void* stream);
 
+/* Fourth-generation tcgen05 implementation (csrc/modconv_tcr.cu): one main-loop pass per tile whatever the number of
+ * regions in it (row-class operand staging on mixed tiles), tight MMA issue loop.  Same contract and weight format. */
+int e4s_modconv3x3_tcr_fwd(const float* x, const void* w_hilo_bf16, const float* s, const float* demod,
+                           const uint8_t* label, const float* noise, const float* noise_w, const float* bias,
+                           float* y, int batch, int h, int w, int cin, int cout, int ncls, int up, int noise_b,
+                           int act, void* stream);
+int e4s_conv3x3_tcr_f32(const float* x, const void* w_hilo_bf16, const float* scale, const float* shift,
+                        const float* prelu_slope, float* y, int batch, int h, int w, int cin, int cout, int out_stride,
+                        void* stream);
+
 /* ---- RGI encoder conv stack (src/models/encoders/helpers.py:122-144, psp_encoders.py:285-309) ------------------
  * Plain 3x3 convolution, padding 1, stride 1 or 2 (out_stride), on the persistent tensor-core kernel.
  * x: pixel-major [B, H, W, Cin]; w_hilo_bf16: [2][1][9][Cout][Cin]; scale/shift: optional per-(sample, channel)

@@ -11,12 +11,12 @@ from test_parity_gpu import _tc_case, TC_CASES, TCP_EXTRA
 
 CASES = TC_CASES + TCP_EXTRA + [(2, 64, 128, 30, True, 5, "blobs"), (1, 160, 256, 28, False, 12, "iid"), (2, 256, 64, 16, True, 12, "iid")]
 
-for mode in ("tcq",):
+for mode in ("tcr",):
     for case in CASES:
         try:
             K, prep, x, args = _tc_case(*case, seed=sum(c for c in case if isinstance(c, int)))
             ref = K.modconv3x3_fwd(x, prep.wt, *args)
-            out = K.modconv3x3_tcq_fwd(x, prep.w_hilo, *args)
+            out = K.modconv3x3_tcr_fwd(x, prep.w_hilo, *args)
             torch.cuda.synchronize()
             err = float((out - ref).abs().max() / ref.abs().max())
             bad = int(((out - ref).abs() > 1e-3 * ref.abs().max()).sum())

@@ -363,6 +363,17 @@ def test_tcp_kernel_matches_simt(b, cin, cout, hw, up, ncls, kind):
     (1, 160, 256, 28, False, 12, "iid"),      # every row its own region: pure row-class mode, 5 K chunks
     (2, 256, 64, 16, True, 12, "iid"),        # up + iid: many fix-up passes
 ])
+def test_tcr_kernel_matches_simt(b, cin, cout, hw, up, ncls, kind):
+    """The fourth-generation tcgen05 kernel (one pass per tile on any mask) vs the fp32 SIMT kernel."""
+    K, prep, x, args = _tc_case(b, cin, cout, hw, up, ncls, kind, seed=cin + cout + hw)
+    ref = K.modconv3x3_fwd(x, prep.wt, *args)
+    out = K.modconv3x3_tcr_fwd(x, prep.w_hilo, *args)
+    torch.cuda.synchronize()
+    e = assert_close(out, ref, 1e-4, f"tcr vs simt {b},{cin},{cout},{hw},{up},{ncls},{kind}")
+    print(f"tcr-vs-simt rel err {e:.2e}")
+
+
+@pytest.mark.parametrize("b,cin,cout,hw,up,ncls,kind", TC_CASES + TCP_EXTRA)
 def test_tcq_kernel_matches_simt(b, cin, cout, hw, up, ncls, kind):
     """The third-generation tcgen05 kernel (TMA-staged activations, single pass on mixed tiles) vs the fp32 SIMT kernel."""
     K, prep, x, args = _tc_case(b, cin, cout, hw, up, ncls, kind, seed=cin + cout + hw)

@@ -38,6 +38,7 @@ for name, cin, cout, r, up in [("c11@256", 128, 128, 256, False), ("c7@64", 512,
     noise = torch.randn(B, 1, ro, ro, device=DEV)
     nw, bias = torch.tensor([0.1], device=DEV), torch.randn(cout, device=DEV)
     dm = K.demod(s, prep.wsq)
+    label = None
     for mode in args.conv.split(","):
         if mode == "tc" and prep.w_hilo is not None:
             K.modconv3x3_tc_fwd(xpm, prep.w_hilo, s, dm, None, noise, nw, bias, up, True)
@@ -45,6 +46,8 @@ for name, cin, cout, r, up in [("c11@256", 128, 128, 256, False), ("c7@64", 512,
             K.modconv3x3_tcp_fwd(xpm, prep.w_hilo, s, dm, None, noise, nw, bias, up, True)
         elif mode == "tcq" and prep.w_hilo is not None:
             K.modconv3x3_tcq_fwd(xpm, prep.w_hilo, s, dm, None, noise, nw, bias, up, True)
+        elif mode == "tcr" and prep.w_hilo is not None:
+            K.modconv3x3_tcr_fwd(xpm, prep.w_hilo, s, dm, label, noise, nw, bias, up, True)
         elif mode == "simt":
             K.modconv3x3_fwd(xpm, prep.wt, s, dm, None, noise, nw, bias, up, True)
     torch.cuda.synchronize()

@@ -121,10 +121,10 @@ def main():
                 if prep.w_hilo is None or not K.tc_eligible(cin, cout):
                     continue
                 fn = lambda: K.modconv3x3_tc_fwd(xpm, prep.w_hilo, s, dm, label, noise, nw, bias, bool(up), True)
-            elif mode in ("tcp", "tcq"):
+            elif mode in ("tcp", "tcq", "tcr"):
                 if prep.w_hilo is None:
                     continue
-                f = K.modconv3x3_tcp_fwd if mode == "tcp" else K.modconv3x3_tcq_fwd
+                f = {"tcp": K.modconv3x3_tcp_fwd, "tcq": K.modconv3x3_tcq_fwd, "tcr": K.modconv3x3_tcr_fwd}[mode]
                 fn = lambda f=f: f(xpm, prep.w_hilo, s, dm, label, noise, nw, bias, bool(up), True)
             else:
                 fn = lambda: K.modconv3x3_fwd(xpm, prep.wt, s, dm, label, noise, nw, bias, bool(up), True)
