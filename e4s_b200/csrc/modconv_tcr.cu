@@ -17,6 +17,11 @@
 //    precomputed (high word constant, low word = base + immediate), the tap / k loops are fully unrolled, and the
 //    resident / streamed and pure / mixed variants are separate straight-line code paths.
 //
+//  * Partial accumulators.  Source-level ncu sampling of the 32->32 layer showed every role waiting on the tensor pipe
+//    while the pipe itself was 11 % active: consecutive tcgen05.mma into the SAME TMEM columns serialise on the MMA
+//    latency (~140 cycles), which a 16-cycle N = 32 MMA cannot cover.  MMAs therefore rotate over PARTS = 256 / N
+//    independent column ranges (8 for N = 32, 4 for N = 64, 2 for N = 128); the epilogue adds the partial sums.
+//
 // K chunk: 64 channels (128-byte swizzle) when Cin % 64 == 0, else 32 channels (64-byte swizzle).
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -182,8 +187,10 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
     constexpr int A_PLANE = A_ROWS * ROWB;
     constexpr int A_STAGE = 2 * A_PLANE;
     constexpr int B_SLOT = N * ROWB;
-    constexpr int NACC = (2 * N <= 512) ? 2 : 1;
-    constexpr int TMEM_COLS = (NACC * N <= 32) ? 32 : (NACC * N <= 64) ? 64 : (NACC * N <= 128) ? 128 : (NACC * N <= 256) ? 256 : 512;
+    constexpr int PARTS = N >= 256 ? 1 : 256 / N;      // independent partial accumulators (see header)
+    constexpr int ACC_COLS = PARTS * N;                // 256
+    constexpr int NACC = 2;
+    constexpr int TMEM_COLS = 512;
     constexpr uint32_t IDESC_BASE = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 4) << 24);
     constexpr uint32_t IDESC_N = IDESC_BASE | ((uint32_t)(N >> 3) << 17);         // all parities in one MMA
     constexpr uint32_t IDESC_Q = IDESC_BASE | ((uint32_t)(NTC >> 3) << 17);       // one parity
@@ -287,9 +294,10 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
             if (lane == 0) {
                 mbar_wait(bars0 + 8 * (ACC_EMPTY + acc), pacc[acc] ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * N);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS);
                 if (p.resident) slot = 0;
                 const bool wait_b = !p.resident || !b_ready;
+                uint32_t mm = 0;                         // MMA counter: rotates over the partial accumulators
                 if (!mixed) {
                     // ---------------- region-pure tile: operand staged once per chunk, taps are row shifts
                     for (int kc = 0; kc < nchunks; ++kc) {
@@ -304,8 +312,10 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                             uint32_t bl = lo_of(b0 + slot * B_SLOT);
 #pragma unroll
                             for (int k = 0; k < KSTEPS; ++k) {
-                                umma_bf16(d_tmem, desc(ah + roff + 2 * k), desc(bl + 2 * k), IDESC_N, (kc | tap | k) != 0 ? 1u : 0u);
-                                umma_bf16(d_tmem, desc(al + roff + 2 * k), desc(bl + 2 * k), IDESC_N, 1u);
+                                umma_bf16(d_tmem + (mm % PARTS) * N, desc(ah + roff + 2 * k), desc(bl + 2 * k), IDESC_N, mm >= PARTS ? 1u : 0u);
+                                ++mm;
+                                umma_bf16(d_tmem + (mm % PARTS) * N, desc(al + roff + 2 * k), desc(bl + 2 * k), IDESC_N, mm >= PARTS ? 1u : 0u);
+                                ++mm;
                             }
                             if (!p.resident) umma_commit(bars0 + 8 * (B_EMPTY + slot));
                             if (++slot == p.nslot_b) slot = 0, pb ^= 1;
@@ -313,7 +323,10 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                             tc_fence_after();
                             bl = lo_of(b0 + slot * B_SLOT);
 #pragma unroll
-                            for (int k = 0; k < KSTEPS; ++k) umma_bf16(d_tmem, desc(ah + roff + 2 * k), desc(bl + 2 * k), IDESC_N, 1u);
+                            for (int k = 0; k < KSTEPS; ++k) {
+                                umma_bf16(d_tmem + (mm % PARTS) * N, desc(ah + roff + 2 * k), desc(bl + 2 * k), IDESC_N, mm >= PARTS ? 1u : 0u);
+                                ++mm;
+                            }
                             if (!p.resident) umma_commit(bars0 + 8 * (B_EMPTY + slot));
                             if (++slot == p.nslot_b) slot = 0, pb ^= 1;
                         }
@@ -322,6 +335,7 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                     }
                 } else {
                     // ---------------- mixed tile: one operand slot per (tap, parity), MMAs of N = NTC
+                    uint32_t inited = 0;                 // bit (part * 4 + parity): that column range already holds a sum
                     for (int kc = 0; kc < nchunks; ++kc) {
 #pragma unroll 1
                         for (int tap = 0; tap < 9; ++tap) {
@@ -340,11 +354,17 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                                 const uint32_t ah = lo_of(a0 + sa * A_STAGE), al = ah + (A_PLANE >> 4);
                                 const uint32_t boff = (uint32_t)(q * NTC * ROWB) >> 4;
                                 const uint32_t dq = d_tmem + (uint32_t)(q * NTC);
+                                auto issue = [&](uint64_t da, uint64_t db) {
+                                    const uint32_t part = mm % PARTS, bit = 1u << (part * 4 + q);
+                                    umma_bf16(dq + part * N, da, db, IDESC_Q, (inited & bit) ? 1u : 0u);
+                                    inited |= bit;
+                                    ++mm;
+                                };
 #pragma unroll
                                 for (int k = 0; k < KSTEPS; ++k) {
-                                    umma_bf16(dq, desc(ah + 2 * k), desc(bh + boff + 2 * k), IDESC_Q, (kc | tap | k) != 0 ? 1u : 0u);
-                                    umma_bf16(dq, desc(al + 2 * k), desc(bh + boff + 2 * k), IDESC_Q, 1u);
-                                    umma_bf16(dq, desc(ah + 2 * k), desc(bl + boff + 2 * k), IDESC_Q, 1u);
+                                    issue(desc(ah + 2 * k), desc(bh + boff + 2 * k));
+                                    issue(desc(al + 2 * k), desc(bh + boff + 2 * k));
+                                    issue(desc(ah + 2 * k), desc(bl + boff + 2 * k));
                                 }
                                 umma_commit(bars0 + 8 * (A_EMPTY + sa));
                                 if (++sa == NSTAGE_A) sa = 0, pa ^= 1;
@@ -564,7 +584,14 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
 #pragma unroll 1
                 for (int j = 0; j < NTC / 32; ++j) {
                     uint32_t r[32];
-                    tmem_ld32(tmem_base + ((quarter * 32u) << 16) + (uint32_t)(acc * N + q * NTC + j * 32), r);
+                    tmem_ld32(tmem_base + ((quarter * 32u) << 16) + (uint32_t)(acc * ACC_COLS + q * NTC + j * 32), r);
+#pragma unroll 1
+                    for (int part = 1; part < PARTS; ++part) {          // add the other partial accumulators
+                        uint32_t r2[32];
+                        tmem_ld32(tmem_base + ((quarter * 32u) << 16) + (uint32_t)(acc * ACC_COLS + part * N + q * NTC + j * 32), r2);
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) + __uint_as_float(r2[e]));
+                    }
                     if (mine) {
 #pragma unroll
                         for (int g = 0; g < 8; ++g) {

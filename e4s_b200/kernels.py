@@ -341,6 +341,23 @@ def modconv3x3_bwd(gy: Tensor, y: Optional[Tensor], x_pm: Optional[Tensor], wd: 
     return gx, gs
 
 
+def modconv3x3_bwd_tc(gy: Tensor, y: Optional[Tensor], x_pm: Optional[Tensor], wd_hilo: Tensor, s: Tensor, dm: Optional[Tensor],
+                      label: Optional[Tensor], up: bool, act: bool, need_gx: bool, need_gs: bool):
+    """Tensor-core backward; wd_hilo bf16 [2, nphase, 9, Cin, Cout].  Returns (gx | None, gs_conv | None)."""
+    b, ho, wo, cout = gy.shape
+    m = 2 if up else 1
+    h, w = ho // m, wo // m
+    cin = wd_hilo.shape[3]
+    ncls = s.shape[1]
+    gx = torch.empty((b, h, w, cin), device=gy.device, dtype=torch.float32) if need_gx else None
+    gs = torch.zeros((b, ncls, cin), device=gy.device, dtype=torch.float32) if need_gs else None
+    with torch.cuda.device(gy.device):
+        _call("e4s_modconv3x3_bwd_tc", _lib.load().e4s_modconv3x3_bwd_tc, ptr(gy), ptr(y), ptr(x_pm), ptr(wd_hilo), ptr(s),
+              ptr(dm), ptr(label), ptr(gx), ptr(gs), b, h, w, cin, cout, ncls, int(up), int(act), stream_ptr(),
+              work=2.0 * 9 * cin * cout * b * h * w)
+    return gx, gs
+
+
 def class_reduce(gy: Tensor, y: Tensor, label: Optional[Tensor], noise: Optional[Tensor], noise_w: Optional[Tensor],
                  bias: Optional[Tensor], ncls: int, act: bool) -> Tensor:
     b, ho, wo, cout = gy.shape

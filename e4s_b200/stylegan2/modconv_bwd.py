@@ -22,6 +22,28 @@ def _dgrad_weights(prep):
     return prep.wd
 
 
+BWD_MODE_DEFAULT = "simt"        # "auto" once the tensor-core dgrad is verified on hardware
+
+
+def _dgrad_planes(prep):
+    """bf16 hi/lo operand planes of the dgrad: [2, nphase, 9, Cin, Cout] (taps flipped, K-major over Cout)."""
+    if getattr(prep, "wd_hilo", None) is None or prep.wd_hilo_key != prep.key:
+        prep.wd_hilo = K.split_bf16(prep.wt.flip(1).contiguous())
+        prep.wd_hilo_key = prep.key
+    return prep.wd_hilo
+
+
+def _use_tc_bwd(prep, gy) -> bool:
+    import os
+    mode = os.environ.get("E4S_B200_BWD", BWD_MODE_DEFAULT)
+    cin, cout = prep.wt.shape[2], prep.wt.shape[3]
+    if mode == "simt" or cin % 32 or cout % 32:
+        return False
+    if mode == "tc":
+        return True
+    return gy.shape[1] * gy.shape[2] >= 256
+
+
 def save_for_styled_backward(ctx, x_pm, s, dm, noise, noise_w, bias, label, prep, up, demodulate, act, y):
     ctx.save_for_backward(x_pm, s, dm, noise, noise_w, bias, label, y)
     ctx.cfg = (prep, up, demodulate, act)
@@ -38,8 +60,12 @@ def styled_backward(ctx, gy):
     s = s.contiguous()
     gx = gs = None
     if need_gx or need_gs:
-        gx, gs = K.modconv3x3_bwd(gy, y if act else None, x_pm if need_gs else None, _dgrad_weights(prep), s, dm, label,
-                                  up, act, need_gx, need_gs)
+        if _use_tc_bwd(prep, gy):
+            gx, gs = K.modconv3x3_bwd_tc(gy, y if act else None, x_pm if need_gs else None, _dgrad_planes(prep), s, dm, label,
+                                         up, act, need_gx, need_gs)
+        else:
+            gx, gs = K.modconv3x3_bwd(gy, y if act else None, x_pm if need_gs else None, _dgrad_weights(prep), s, dm, label,
+                                      up, act, need_gx, need_gs)
     if need_gs and demodulate:
         # demodulation path: d = rsqrt(s^2 Wsq^T + eps)  ->  d(loss)/ds_i -= s_i * sum_o gdu[o] d[o]^2 Wsq[o,i]
         gdu = K.class_reduce(gy, y, label, noise, noise_w, bias, s.shape[1], act)

@@ -191,6 +191,11 @@ int e4s_torgb_fwd_f32(const float* x, const float* wrgb, const float* s, const u
 int e4s_modconv3x3_bwd_f32(const float* gy, const float* y, const float* x, const float* wd, const float* s,
                            const float* demod, const uint8_t* label, float* gx, float* gs, int batch, int h, int w,
                            int cin, int cout, int ncls, int up, int act, void* stream);
+/* Tensor-core (tcgen05) implementation of e4s_modconv3x3_bwd_f32 for cin % 32 == 0 and cout % 32 == 0.
+ * wd_hilo_bf16: [2 (hi, lo)][nphase][9][Cin][Cout] = forward weights with taps flipped, K-major over Cout. */
+int e4s_modconv3x3_bwd_tc(const float* gy, const float* y, const float* x, const void* wd_hilo_bf16, const float* s,
+                          const float* demod, const uint8_t* label, float* gx, float* gs, int batch, int h, int w,
+                          int cin, int cout, int ncls, int up, int act, void* stream);
 /* gdu[b,c,o] += sum over pixels of region c of act'(y)*gy * (act^-1(y) - noise_w*noise - bias): the per-region
  * reduction behind d(loss)/d(demod).  gdu [B, ncls, Cout] is accumulated atomically (caller zeroes it). */
 int e4s_class_reduce_f32(const float* gy, const float* y, const uint8_t* label, const float* noise,

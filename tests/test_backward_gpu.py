@@ -175,3 +175,40 @@ def test_inversion_loop_matches_oracle(monkeypatch):
                         noise=[cu(n) for n in noise])
     for a, b in zip([float(h) for h in hist], ref_losses):
         assert abs(a - b) <= 5e-3 * abs(b), ([float(h) for h in hist], ref_losses)
+
+
+# ------------------------------------------------------------------ tensor-core dgrad vs the fp32 SIMT dgrad
+@pytest.mark.parametrize("b,cin,cout,hw,up,ncls,kind,act", [
+    (1, 64, 64, 16, False, 1, "blobs", True),
+    (2, 128, 64, 24, False, 1, "blobs", False),
+    (1, 64, 128, 16, True, 1, "blobs", True),
+    (2, 96, 160, 20, False, 5, "blobs", True),
+    (1, 128, 64, 16, False, 6, "iid", True),
+    (2, 64, 96, 12, True, 4, "blobs", True),
+    (1, 256, 512, 16, True, 3, "iid", True),
+    (1, 32, 32, 40, False, 1, "blobs", True),
+])
+def test_dgrad_tc_matches_simt(b, cin, cout, hw, up, ncls, kind, act):
+    from e4s_b200 import kernels as K
+    from e4s_b200.stylegan2.modconv import PreparedConv
+    from e4s_b200.stylegan2 import modconv_bwd as MB
+    g = torch.Generator().manual_seed(cin + cout + hw)
+    w = torch.randn(1, cout, cin, 3, 3, generator=g)
+    prep = PreparedConv().get(cu(w), up, cu(O.make_fir((1, 3, 3, 1), 4.0)) if up else None)
+    ho = 2 * hw if up else hw
+    x = cu(torch.randn(b, hw, hw, cin, generator=g))
+    s = cu(1.0 + 0.3 * torch.randn(b, ncls, cin, generator=g))
+    dm = K.demod(s, prep.wsq)
+    gy = cu(torch.randn(b, ho, ho, cout, generator=g))
+    y = cu(torch.randn(b, ho, ho, cout, generator=g))
+    if kind == "iid":
+        label = torch.randint(0, ncls, (b, ho, ho), generator=g, dtype=torch.uint8)
+    else:
+        coarse = torch.randint(0, ncls, (b, 1, max(2, ho // 8), max(2, ho // 8)), generator=g).float()
+        label = torch.nn.functional.interpolate(coarse, size=(ho, ho), mode="nearest")[:, 0].to(torch.uint8)
+    label = cu(label) if ncls > 1 else None
+    gx0, gs0 = K.modconv3x3_bwd(gy, y if act else None, x, MB._dgrad_weights(prep), s, dm, label, up, act, True, True)
+    gx1, gs1 = K.modconv3x3_bwd_tc(gy, y if act else None, x, MB._dgrad_planes(prep), s, dm, label, up, act, True, True)
+    torch.cuda.synchronize()
+    assert_close(gx1, gx0, 1e-4, "gx tc vs simt")
+    assert_close(gs1, gs0, 1e-4, "gs tc vs simt")
