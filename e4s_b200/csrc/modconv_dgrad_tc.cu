@@ -415,8 +415,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) modconv3x3_dgrad_tc_kernel(con
                         for (int g = 0; g < 8; ++g) {
                             float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
                             if (mine) xv = *reinterpret_cast<const float4*>(xr + 4 * g);
-                            float v[4] = {xv.x * __uint_as_float(r[4 * g]), xv.y * __uint_as_float(r[4 * g + 1]),
-                                          xv.z * __uint_as_float(r[4 * g + 2]), xv.w * __uint_as_float(r[4 * g + 3])};
+                            // rows outside the image / spare tile columns hold garbage accumulators (possibly NaN): mask, do not multiply
+                            float v[4] = {0.f, 0.f, 0.f, 0.f};
+                            if (mine) {
+                                v[0] = xv.x * __uint_as_float(r[4 * g]), v[1] = xv.y * __uint_as_float(r[4 * g + 1]);
+                                v[2] = xv.z * __uint_as_float(r[4 * g + 2]), v[3] = xv.w * __uint_as_float(r[4 * g + 3]);
+                            }
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
                                 float sum = v[e];

@@ -280,109 +280,114 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
         __syncwarp();
     } else if (warp == 1) {
         // ===================================================================== MMA issuer
+        // The whole warp walks the loops with warp-uniform state (barrier waits included); only the tcgen05 instructions
+        // themselves are predicated on one lane.  With the loops inside `if (lane == 0)` the compiler treats descriptors
+        // as per-thread values and spends ~30 SASS instructions (R2UR.BROADCAST, BSSY/BSYNC, ...) per MMA - measured as
+        // the bottleneck of the small-N layers (source-level ncu samples, profiles/).
         int sa = 0, slot = 0, acc = 0;
-        uint32_t pa = 0, pb = 0, pacc[2] = {0, 0};
+        uint32_t pa = 0, pb = 0, pacc0 = 0, pacc1 = 0;
         bool b_ready = false;                            // resident weights: waited for once
+        const bool leader = lane == 0;
+        // shfl-from-lane-0 marks values as warp-uniform for the compiler (uniform registers feed UTCHMMA directly)
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
         const uint32_t bars0 = smem_u32(bars);
         const uint32_t a0 = smem_u32(a_buf), b0 = smem_u32(b_buf);
         auto desc = [](uint32_t lo) -> uint64_t { return ((uint64_t)DESC_HI << 32) | lo; };
         auto lo_of = [](uint32_t addr) -> uint32_t { return (addr >> 4) | 0x10000u; };
         for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
             const Item item = decode_item(p, it);
-            const uint32_t classes = tile_class_mask<NPH>(p, item, lane);
+            const uint32_t classes = __shfl_sync(0xffffffffu, tile_class_mask<NPH>(p, item, lane), 0);
             const bool mixed = (classes & (classes - 1)) != 0;
-            if (lane == 0) {
-                mbar_wait(bars0 + 8 * (ACC_EMPTY + acc), pacc[acc] ^ 1);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS);
-                if (p.resident) slot = 0;
-                const bool wait_b = !p.resident || !b_ready;
-                uint32_t mm = 0;                         // MMA counter: rotates over the partial accumulators
-                if (!mixed) {
-                    // ---------------- region-pure tile: operand staged once per chunk, taps are row shifts
-                    for (int kc = 0; kc < nchunks; ++kc) {
-                        mbar_wait(bars0 + 8 * (A_FULL + sa), pa);
+            mbar_wait(bars0 + 8 * (ACC_EMPTY + acc), (acc ? pacc1 : pacc0) ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_u + (uint32_t)(acc * ACC_COLS);
+            if (p.resident) slot = 0;
+            const bool wait_b = !p.resident || !b_ready;
+            uint32_t mm = 0;                             // MMA counter: rotates over the partial accumulators
+            if (!mixed) {
+                // ---------------- region-pure tile: operand staged once per chunk, taps are row shifts
+                for (int kc = 0; kc < nchunks; ++kc) {
+                    mbar_wait(bars0 + 8 * (A_FULL + sa), pa);
+                    tc_fence_after();
+                    const uint32_t ah = lo_of(a0 + sa * A_STAGE), al = ah + (A_PLANE >> 4);
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const uint32_t roff = (uint32_t)(((tap / 3) * TWP + (tap % 3) + 1) * ROWB) >> 4;
+                        if (wait_b) mbar_wait(bars0 + 8 * (B_FULL + slot), pb);
                         tc_fence_after();
-                        const uint32_t ah = lo_of(a0 + sa * A_STAGE), al = ah + (A_PLANE >> 4);
+                        uint32_t bl = lo_of(b0 + slot * B_SLOT);
 #pragma unroll
-                        for (int tap = 0; tap < 9; ++tap) {
-                            const uint32_t roff = (uint32_t)(((tap / 3) * TWP + (tap % 3) + 1) * ROWB) >> 4;
-                            if (wait_b) mbar_wait(bars0 + 8 * (B_FULL + slot), pb);
-                            tc_fence_after();
-                            uint32_t bl = lo_of(b0 + slot * B_SLOT);
-#pragma unroll
-                            for (int k = 0; k < KSTEPS; ++k) {
-                                umma_bf16(d_tmem + (mm % PARTS) * N, desc(ah + roff + 2 * k), desc(bl + 2 * k), IDESC_N, mm >= PARTS ? 1u : 0u);
-                                ++mm;
-                                umma_bf16(d_tmem + (mm % PARTS) * N, desc(al + roff + 2 * k), desc(bl + 2 * k), IDESC_N, mm >= PARTS ? 1u : 0u);
-                                ++mm;
-                            }
-                            if (!p.resident) umma_commit(bars0 + 8 * (B_EMPTY + slot));
-                            if (++slot == p.nslot_b) slot = 0, pb ^= 1;
-                            if (wait_b) mbar_wait(bars0 + 8 * (B_FULL + slot), pb);
-                            tc_fence_after();
-                            bl = lo_of(b0 + slot * B_SLOT);
-#pragma unroll
-                            for (int k = 0; k < KSTEPS; ++k) {
-                                umma_bf16(d_tmem + (mm % PARTS) * N, desc(ah + roff + 2 * k), desc(bl + 2 * k), IDESC_N, mm >= PARTS ? 1u : 0u);
-                                ++mm;
-                            }
-                            if (!p.resident) umma_commit(bars0 + 8 * (B_EMPTY + slot));
-                            if (++slot == p.nslot_b) slot = 0, pb ^= 1;
+                        for (int k = 0; k < KSTEPS; ++k) {
+                            if (leader) umma_bf16(d_tmem + (mm % PARTS) * N, desc(ah + roff + 2 * k), desc(bl + 2 * k), IDESC_N, mm >= PARTS ? 1u : 0u);
+                            ++mm;
+                            if (leader) umma_bf16(d_tmem + (mm % PARTS) * N, desc(al + roff + 2 * k), desc(bl + 2 * k), IDESC_N, mm >= PARTS ? 1u : 0u);
+                            ++mm;
                         }
-                        umma_commit(bars0 + 8 * (A_EMPTY + sa));
-                        if (++sa == NSTAGE_A) sa = 0, pa ^= 1;
+                        if (!p.resident && leader) umma_commit(bars0 + 8 * (B_EMPTY + slot));
+                        if (++slot == p.nslot_b) slot = 0, pb ^= 1;
+                        if (wait_b) mbar_wait(bars0 + 8 * (B_FULL + slot), pb);
+                        tc_fence_after();
+                        bl = lo_of(b0 + slot * B_SLOT);
+#pragma unroll
+                        for (int k = 0; k < KSTEPS; ++k) {
+                            if (leader) umma_bf16(d_tmem + (mm % PARTS) * N, desc(ah + roff + 2 * k), desc(bl + 2 * k), IDESC_N, mm >= PARTS ? 1u : 0u);
+                            ++mm;
+                        }
+                        if (!p.resident && leader) umma_commit(bars0 + 8 * (B_EMPTY + slot));
+                        if (++slot == p.nslot_b) slot = 0, pb ^= 1;
                     }
-                } else {
-                    // ---------------- mixed tile: one operand slot per (tap, parity), MMAs of N = NTC
-                    uint32_t inited = 0;                 // bit (part * 4 + parity): that column range already holds a sum
-                    for (int kc = 0; kc < nchunks; ++kc) {
+                    if (leader) umma_commit(bars0 + 8 * (A_EMPTY + sa));
+                    if (++sa == NSTAGE_A) sa = 0, pa ^= 1;
+                }
+            } else {
+                // ---------------- mixed tile: one operand slot per (tap, parity), MMAs of N = NTC
+                uint32_t inited = 0;                     // bit (part * 4 + parity): that column range already holds a sum
+                for (int kc = 0; kc < nchunks; ++kc) {
 #pragma unroll 1
-                        for (int tap = 0; tap < 9; ++tap) {
-                            int slot_lo = slot + 1;
-                            uint32_t pb_lo = pb;
-                            if (slot_lo == p.nslot_b) slot_lo = 0, pb_lo ^= 1;
-                            if (wait_b) {
-                                mbar_wait(bars0 + 8 * (B_FULL + slot), pb);
-                                mbar_wait(bars0 + 8 * (B_FULL + slot_lo), pb_lo);
-                            }
-                            const uint32_t bh = lo_of(b0 + slot * B_SLOT), bl = lo_of(b0 + slot_lo * B_SLOT);
-#pragma unroll
-                            for (int q = 0; q < NPH; ++q) {
-                                mbar_wait(bars0 + 8 * (A_FULL + sa), pa);
-                                tc_fence_after();
-                                const uint32_t ah = lo_of(a0 + sa * A_STAGE), al = ah + (A_PLANE >> 4);
-                                const uint32_t boff = (uint32_t)(q * NTC * ROWB) >> 4;
-                                const uint32_t dq = d_tmem + (uint32_t)(q * NTC);
-                                auto issue = [&](uint64_t da, uint64_t db) {
-                                    const uint32_t part = mm % PARTS, bit = 1u << (part * 4 + q);
-                                    umma_bf16(dq + part * N, da, db, IDESC_Q, (inited & bit) ? 1u : 0u);
-                                    inited |= bit;
-                                    ++mm;
-                                };
-#pragma unroll
-                                for (int k = 0; k < KSTEPS; ++k) {
-                                    issue(desc(ah + 2 * k), desc(bh + boff + 2 * k));
-                                    issue(desc(al + 2 * k), desc(bh + boff + 2 * k));
-                                    issue(desc(ah + 2 * k), desc(bl + boff + 2 * k));
-                                }
-                                umma_commit(bars0 + 8 * (A_EMPTY + sa));
-                                if (++sa == NSTAGE_A) sa = 0, pa ^= 1;
-                            }
-                            if (!p.resident) {
-                                umma_commit(bars0 + 8 * (B_EMPTY + slot));
-                                umma_commit(bars0 + 8 * (B_EMPTY + slot_lo));
-                            }
-                            slot = slot_lo, pb = pb_lo;
-                            if (++slot == p.nslot_b) slot = 0, pb ^= 1;
+                    for (int tap = 0; tap < 9; ++tap) {
+                        int slot_lo = slot + 1;
+                        uint32_t pb_lo = pb;
+                        if (slot_lo == p.nslot_b) slot_lo = 0, pb_lo ^= 1;
+                        if (wait_b) {
+                            mbar_wait(bars0 + 8 * (B_FULL + slot), pb);
+                            mbar_wait(bars0 + 8 * (B_FULL + slot_lo), pb_lo);
                         }
+                        const uint32_t bh = lo_of(b0 + slot * B_SLOT), bl = lo_of(b0 + slot_lo * B_SLOT);
+#pragma unroll
+                        for (int q = 0; q < NPH; ++q) {
+                            mbar_wait(bars0 + 8 * (A_FULL + sa), pa);
+                            tc_fence_after();
+                            const uint32_t ah = lo_of(a0 + sa * A_STAGE), al = ah + (A_PLANE >> 4);
+                            const uint32_t boff = (uint32_t)(q * NTC * ROWB) >> 4;
+                            const uint32_t dq = d_tmem + (uint32_t)(q * NTC);
+                            auto issue = [&](uint64_t da, uint64_t db) {
+                                const uint32_t part = mm % PARTS, bit = 1u << (part * 4 + q);
+                                if (leader) umma_bf16(dq + part * N, da, db, IDESC_Q, (inited & bit) ? 1u : 0u);
+                                inited |= bit;
+                                ++mm;
+                            };
+#pragma unroll
+                            for (int k = 0; k < KSTEPS; ++k) {
+                                issue(desc(ah + 2 * k), desc(bh + boff + 2 * k));
+                                issue(desc(al + 2 * k), desc(bh + boff + 2 * k));
+                                issue(desc(ah + 2 * k), desc(bl + boff + 2 * k));
+                            }
+                            if (leader) umma_commit(bars0 + 8 * (A_EMPTY + sa));
+                            if (++sa == NSTAGE_A) sa = 0, pa ^= 1;
+                        }
+                        if (!p.resident && leader) {
+                            umma_commit(bars0 + 8 * (B_EMPTY + slot));
+                            umma_commit(bars0 + 8 * (B_EMPTY + slot_lo));
+                        }
+                        slot = slot_lo, pb = pb_lo;
+                        if (++slot == p.nslot_b) slot = 0, pb ^= 1;
                     }
                 }
-                umma_commit(bars0 + 8 * (ACC_FULL + acc));
-                pacc[acc] ^= 1;
-                if (NACC == 2) acc ^= 1;
-                b_ready = true;
             }
+            if (leader) umma_commit(bars0 + 8 * (ACC_FULL + acc));
+            if (acc) pacc1 ^= 1; else pacc0 ^= 1;
+            acc ^= 1;
+            b_ready = true;
             __syncwarp();
         }
     } else if (warp < 10) {
