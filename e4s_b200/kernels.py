@@ -381,7 +381,7 @@ def torgb_bwd(g: Tensor, x_pm: Tensor, wrgb: Tensor, s: Tensor, label: Optional[
 
 
 # ------------------------------------------------------------------------------ encoder conv stack
-ENCODER_CONV_ENTRY = "e4s_conv3x3_tcp_f32"
+ENCODER_CONV_ENTRY = "e4s_conv3x3_tcr_f32"
 
 
 def split_bf16(w: Tensor) -> Tensor:

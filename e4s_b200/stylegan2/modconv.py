@@ -150,7 +150,7 @@ def warn_frozen(weight: Tensor):
 DEFAULT_CONV_MODE = "auto"   # auto -> tcp (second generation) until a later generation beats it end to end
 
 
-AUTO_KERNEL = "tcp"
+AUTO_KERNEL = "tcr"
 
 
 def conv_path(prep: "PreparedConv", x_pm: Tensor) -> str:

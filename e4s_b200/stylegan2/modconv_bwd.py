@@ -22,7 +22,7 @@ def _dgrad_weights(prep):
     return prep.wd
 
 
-BWD_MODE_DEFAULT = "simt"        # "auto" once the tensor-core dgrad is verified on hardware
+BWD_MODE_DEFAULT = "auto"        # tensor-core dgrad from 16x16 up (verified against the SIMT dgrad), SIMT below
 
 
 def _dgrad_planes(prep):

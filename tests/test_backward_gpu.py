@@ -101,6 +101,7 @@ def test_generator_gradient_golden_exact_path(golden, monkeypatch):
     """d<image, R>/d(codes) for the 32x32, K=13, iid-mask case against the reference's own autograd result, with the
     forward on the exact-fp32 kernels: max-norm parity at the 1e-3 bar."""
     monkeypatch.setenv("E4S_B200_CONV", "simt")
+    monkeypatch.setenv("E4S_B200_BWD", "simt")
     assert_close(_generator_dcodes(), golden["generator/g32_k13_iid/dcodes"], REL_TOL, "dcodes (fp32 path)")
 
 
@@ -110,7 +111,8 @@ def test_generator_gradient_golden_tensor_core_path(golden, monkeypatch):
     sign of a few dozen near-zero pre-activations per layer, each moving its share of the gradient by O(1).  In
     max-norm that is ~1e-2 for this case (any non-bit-exact forward - e.g. the reference's own default TF32 convs -
     shows the same effect, larger); the direction and norm of the gradient are what the optimiser consumes."""
-    monkeypatch.setenv("E4S_B200_CONV", "tcp")
+    monkeypatch.setenv("E4S_B200_CONV", "tcr")
+    monkeypatch.setenv("E4S_B200_BWD", "tc")
     g = _generator_dcodes().double().cpu().flatten()
     ref = torch.from_numpy(golden["generator/g32_k13_iid/dcodes"]).double().flatten()
     rel_l2 = float((g - ref).norm() / ref.norm())
@@ -124,7 +126,8 @@ def test_inversion_loop_matches_oracle(monkeypatch):
     losses and the updated latent against the same loop run through the CPU oracle."""
     from e4s_b200.networks import Net3
     from e4s_b200.optimization import invert
-    monkeypatch.setenv("E4S_B200_CONV", "simt")          # strict step-by-step comparison on the exact-fp32 forward
+    monkeypatch.setenv("E4S_B200_CONV", "simt")          # strict step-by-step comparison on the exact-fp32 kernels
+    monkeypatch.setenv("E4S_B200_BWD", "simt")
     size, ncls, K = 32, 12, 13
     opts = types.SimpleNamespace(fsencoder_type="psp", remaining_layer_idx=K, num_seg_cls=ncls, out_size=size,
                                  train_G=False, start_from_latent_avg=True, learn_in_w=False)
@@ -169,7 +172,8 @@ def test_inversion_loop_matches_oracle(monkeypatch):
             assert_close(out_latent - cu(sv0), ref_latent - sv0, 5e-3, "SGD update of the texture vectors after 3 steps")
         assert ours[-1] < ours[0], (opt_name, ours)
     # and the same loop on the tensor-core forward: the loss trajectory must still track the oracle's
-    monkeypatch.setenv("E4S_B200_CONV", "tcp")
+    monkeypatch.setenv("E4S_B200_CONV", "tcr")
+    monkeypatch.setenv("E4S_B200_BWD", "tc")
     ref_latent, ref_losses = oracle_loop("adam", 1e-2)
     _, _, hist = invert(net, cu(target), cu(mask), style_vectors=cu(sv0), steps=3, lr=1e-2, opt_name="adam",
                         noise=[cu(n) for n in noise])

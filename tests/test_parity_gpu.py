@@ -387,7 +387,7 @@ def test_tcq_kernel_matches_simt(b, cin, cout, hw, up, ncls, kind):
 def test_generator_golden_tensor_core_path(golden, monkeypatch):
     """Whole generator with every eligible layer forced onto the persistent tcgen05 kernel (also at 4x4..8x8, where
     the default policy would pick the SIMT kernel), against the reference vectors."""
-    monkeypatch.setenv("E4S_B200_CONV", "tcq")
+    monkeypatch.setenv("E4S_B200_CONV", "tcr")
     for tag, size, K_, B, nc, msz, kind in [("g64_k5", 64, 5, 2, 5, 32, "blobs"), ("g256_k13", 256, 13, 1, 12, 512, "blobs")]:
         G, _ = _generator(size, K_)
         codes, mask, _, noise = O.synthetic_inputs(B, nc, size, msz, seed=size + K_, kind=kind)
