@@ -17,10 +17,11 @@
 //    precomputed (high word constant, low word = base + immediate), the tap / k loops are fully unrolled, and the
 //    resident / streamed and pure / mixed variants are separate straight-line code paths.
 //
-//  * Partial accumulators.  Source-level ncu sampling of the 32->32 layer showed every role waiting on the tensor pipe
-//    while the pipe itself was 11 % active: consecutive tcgen05.mma into the SAME TMEM columns serialise on the MMA
-//    latency (~140 cycles), which a 16-cycle N = 32 MMA cannot cover.  MMAs therefore rotate over PARTS = 256 / N
-//    independent column ranges (8 for N = 32, 4 for N = 64, 2 for N = 128); the epilogue adds the partial sums.
+//  * What bounds the small-N layers (source-level ncu sampling, profiles/): not DRAM latency (TMA staging did not help),
+//    not accumulator dependencies (rotating MMAs over independent TMEM column ranges did not help) but the single MMA
+//    warp itself - ~1400 warp instructions per tile for 54 MMAs, stalled on fixed-latency dependencies and on
+//    instruction fetch of a fully unrolled 30-KB loop.  The issue loop is therefore COMPACT: a runtime loop over taps,
+//    one lane-election per group of MMAs + commit, descriptors in uniform registers.
 //
 // K chunk: 64 channels (128-byte swizzle) when Cin % 64 == 0, else 32 channels (64-byte swizzle).
 #include <cuda.h>
@@ -187,7 +188,7 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
     constexpr int A_PLANE = A_ROWS * ROWB;
     constexpr int A_STAGE = 2 * A_PLANE;
     constexpr int B_SLOT = N * ROWB;
-    constexpr int PARTS = N >= 256 ? 1 : 256 / N;      // independent partial accumulators (see header)
+    constexpr int PARTS = 1;      // partial accumulators (rotating MMAs over 256/N column ranges) measured no gain: off
     constexpr int ACC_COLS = PARTS * N;                // 256
     constexpr int NACC = 2;
     constexpr int TMEM_COLS = 512;
@@ -303,38 +304,41 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
             const uint32_t d_tmem = tmem_u + (uint32_t)(acc * ACC_COLS);
             if (p.resident) slot = 0;
             const bool wait_b = !p.resident || !b_ready;
-            uint32_t mm = 0;                             // MMA counter: rotates over the partial accumulators
             if (!mixed) {
                 // ---------------- region-pure tile: operand staged once per chunk, taps are row shifts
+                uint32_t accum = 0;
+#pragma unroll 1
                 for (int kc = 0; kc < nchunks; ++kc) {
                     mbar_wait(bars0 + 8 * (A_FULL + sa), pa);
                     tc_fence_after();
                     const uint32_t ah = lo_of(a0 + sa * A_STAGE), al = ah + (A_PLANE >> 4);
-#pragma unroll
+                    uint32_t roff = (uint32_t)ROWB >> 4;                   // tap (0,0): row shift 1
+#pragma unroll 1
                     for (int tap = 0; tap < 9; ++tap) {
-                        const uint32_t roff = (uint32_t)(((tap / 3) * TWP + (tap % 3) + 1) * ROWB) >> 4;
                         if (wait_b) mbar_wait(bars0 + 8 * (B_FULL + slot), pb);
                         tc_fence_after();
                         uint32_t bl = lo_of(b0 + slot * B_SLOT);
+                        if (leader) {
 #pragma unroll
-                        for (int k = 0; k < KSTEPS; ++k) {
-                            if (leader) umma_bf16(d_tmem + (mm % PARTS) * N, desc(ah + roff + 2 * k), desc(bl + 2 * k), IDESC_N, mm >= PARTS ? 1u : 0u);
-                            ++mm;
-                            if (leader) umma_bf16(d_tmem + (mm % PARTS) * N, desc(al + roff + 2 * k), desc(bl + 2 * k), IDESC_N, mm >= PARTS ? 1u : 0u);
-                            ++mm;
+                            for (int k = 0; k < KSTEPS; ++k) {
+                                umma_bf16(d_tmem, desc(ah + roff + 2 * k), desc(bl + 2 * k), IDESC_N, k == 0 ? accum : 1u);
+                                umma_bf16(d_tmem, desc(al + roff + 2 * k), desc(bl + 2 * k), IDESC_N, 1u);
+                            }
+                            if (!p.resident) umma_commit(bars0 + 8 * (B_EMPTY + slot));
                         }
-                        if (!p.resident && leader) umma_commit(bars0 + 8 * (B_EMPTY + slot));
+                        accum = 1u;
                         if (++slot == p.nslot_b) slot = 0, pb ^= 1;
                         if (wait_b) mbar_wait(bars0 + 8 * (B_FULL + slot), pb);
                         tc_fence_after();
                         bl = lo_of(b0 + slot * B_SLOT);
+                        if (leader) {
 #pragma unroll
-                        for (int k = 0; k < KSTEPS; ++k) {
-                            if (leader) umma_bf16(d_tmem + (mm % PARTS) * N, desc(ah + roff + 2 * k), desc(bl + 2 * k), IDESC_N, mm >= PARTS ? 1u : 0u);
-                            ++mm;
+                            for (int k = 0; k < KSTEPS; ++k) umma_bf16(d_tmem, desc(ah + roff + 2 * k), desc(bl + 2 * k), IDESC_N, 1u);
+                            if (!p.resident) umma_commit(bars0 + 8 * (B_EMPTY + slot));
                         }
-                        if (!p.resident && leader) umma_commit(bars0 + 8 * (B_EMPTY + slot));
                         if (++slot == p.nslot_b) slot = 0, pb ^= 1;
+                        // next tap: +1 row, or to the start of the next halo row (+16 - 2) after dx = 2
+                        roff += (uint32_t)(((tap % 3) == 2 ? (TWP - 2) : 1) * ROWB) >> 4;
                     }
                     if (leader) umma_commit(bars0 + 8 * (A_EMPTY + sa));
                     if (++sa == NSTAGE_A) sa = 0, pa ^= 1;
@@ -360,18 +364,16 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                             const uint32_t ah = lo_of(a0 + sa * A_STAGE), al = ah + (A_PLANE >> 4);
                             const uint32_t boff = (uint32_t)(q * NTC * ROWB) >> 4;
                             const uint32_t dq = d_tmem + (uint32_t)(q * NTC);
-                            auto issue = [&](uint64_t da, uint64_t db) {
-                                const uint32_t part = mm % PARTS, bit = 1u << (part * 4 + q);
-                                if (leader) umma_bf16(dq + part * N, da, db, IDESC_Q, (inited & bit) ? 1u : 0u);
-                                inited |= bit;
-                                ++mm;
-                            };
+                            const uint32_t bit = 1u << q;
+                            if (leader) {
 #pragma unroll
-                            for (int k = 0; k < KSTEPS; ++k) {
-                                issue(desc(ah + 2 * k), desc(bh + boff + 2 * k));
-                                issue(desc(al + 2 * k), desc(bh + boff + 2 * k));
-                                issue(desc(ah + 2 * k), desc(bl + boff + 2 * k));
+                                for (int k = 0; k < KSTEPS; ++k) {
+                                    umma_bf16(dq, desc(ah + 2 * k), desc(bh + boff + 2 * k), IDESC_Q, (k == 0 && !(inited & bit)) ? 0u : 1u);
+                                    umma_bf16(dq, desc(al + 2 * k), desc(bh + boff + 2 * k), IDESC_Q, 1u);
+                                    umma_bf16(dq, desc(ah + 2 * k), desc(bl + boff + 2 * k), IDESC_Q, 1u);
+                                }
                             }
+                            inited |= bit;
                             if (leader) umma_commit(bars0 + 8 * (A_EMPTY + sa));
                             if (++sa == NSTAGE_A) sa = 0, pa ^= 1;
                         }

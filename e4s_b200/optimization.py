@@ -37,7 +37,7 @@ def setup_W_optimizer(W_init: torch.Tensor, opt_name: str = "adam", lr: float = 
 def invert(net, target: torch.Tensor, onehot: torch.Tensor, style_vectors: Optional[torch.Tensor] = None,
            steps: int = 200, lr: float = 1e-2, opt_name: str = "adam", l2_lambda: float = 1.0,
            extra_losses: Sequence[Tuple[float, Callable]] = (), noise: Optional[List[torch.Tensor]] = None,
-           callback: Optional[Callable] = None):
+           callback: Optional[Callable] = None, cuda_graph: bool = False):
     """Optimise the texture vectors of ONE batch of faces so that net.gen_img reproduces `target`.
 
     net: e4s_b200.networks.Net3 (eval, latent_avg set).  target [B,3,S,S]; onehot [B,ncls,Hm,Wm].
@@ -48,6 +48,8 @@ def invert(net, target: torch.Tensor, onehot: torch.Tensor, style_vectors: Optio
     if style_vectors is None:
         with torch.no_grad():
             style_vectors, _ = net.get_style_vectors(target, onehot)
+    if cuda_graph:
+        return _invert_graphed(net, target, onehot, style_vectors, steps, lr, l2_lambda, extra_losses, noise)
     opt, latent = setup_W_optimizer(style_vectors, opt_name, lr)
     history, recon = [], None
     for step in range(steps):
@@ -63,3 +65,44 @@ def invert(net, target: torch.Tensor, onehot: torch.Tensor, style_vectors: Optio
         if callback is not None:
             callback(step, loss, recon, latent)
     return latent.detach(), recon.detach(), history
+
+
+def _invert_graphed(net, target, onehot, style_vectors, steps, lr, l2_lambda, extra_losses, noise):
+    """The same loop with one optimisation step (zero_grad, forward, loss, backward, Adam) captured in a CUDA graph and
+    replayed: at one face per GPU the eager loop is bound by ~400 kernel launches per step, not by the kernels.
+    Adam only (capturable); fresh noise comes from the graph-safe CUDA generator, so every replay draws new noise."""
+    latent = style_vectors.clone().detach().requires_grad_(True)
+    opt = torch.optim.Adam([latent], lr=lr, capturable=True)
+    static_loss = torch.zeros((), device=latent.device)
+    static_recon = torch.empty_like(target)
+
+    def one_step():
+        opt.zero_grad(set_to_none=False)
+        codes = net.cal_style_codes(latent)
+        recon, _, _ = net.gen_img(None, codes, onehot, noise=noise) if noise is not None else net.gen_img(None, codes, onehot)
+        loss = l2_lambda * F.mse_loss(recon, target) if l2_lambda > 0 else recon.new_zeros(())
+        for weight, fn in extra_losses:
+            loss = loss + weight * fn(recon, target)
+        loss.backward()
+        opt.step()
+        static_loss.copy_(loss.detach())
+        static_recon.copy_(recon.detach())
+
+    history = []
+    warm = min(3, steps)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):                       # eager warm-up: weight preparation, mask validation, allocator
+        for _ in range(warm):
+            one_step()
+            history.append(static_loss.clone())
+    torch.cuda.current_stream().wait_stream(side)
+    if steps > warm:
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            one_step()
+        history.append(static_loss.clone())
+        for _ in range(steps - warm - 1):
+            graph.replay()
+            history.append(static_loss.clone())
+    return latent.detach(), static_recon, history
