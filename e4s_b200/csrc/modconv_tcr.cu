@@ -91,6 +91,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (clock64() - t0 > 8000000000ll) __trap();
     }
 }
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -399,7 +404,7 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
         const int pix0 = t / CPR;                        // 0..PPS-1
         constexpr int NSW_SHIFT = (160 + PPS - 1) / PPS; // sweeps over the 160 halo pixels (5 or 3)
         constexpr int NSW_ROWS = 128 / PPS;              // sweeps over the 128 operand rows (4 or 2)
-        int sa = 0, sx = 0;
+        int sa = 0, xstage = 0;
         uint32_t pa = 0, px = 0;
         uint32_t chunk_ctr = 0;                          // selects the s_tab buffer
         for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
@@ -421,8 +426,8 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                     const float4 t1 = sh ? __ldg(reinterpret_cast<const float4*>(sh + ch + 4)) : zero4;
                     float4 v0[NSW_SHIFT], v1[NSW_SHIFT];
                     bool inb[NSW_SHIFT];
-                    if (XS) mbar_wait(smem_u32(&bars[XS_FULL + sx]), px);
-                    const float* xs = reinterpret_cast<const float*>(xs_buf + sx * XS_STAGE);
+                    if (XS) mbar_wait(smem_u32(&bars[XS_FULL + xstage]), px);
+                    const uint32_t xs = smem_u32(xs_buf + xstage * XS_STAGE);
 #pragma unroll
                     for (int i = 0; i < NSW_SHIFT; ++i) {
                         const int hp = pix0 + PPS * i;
@@ -431,18 +436,14 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                         inb[i] = hp < 160 && gy >= 0 && gy < p.h && gx >= 0 && gx < p.w;
                         if (XS) {
                             if (hp < 160) {                       // the TMA box is already zero outside the image
-                                v0[i] = *reinterpret_cast<const float4*>(xs + hp * 32 + 8 * c8);
-                                v1[i] = *reinterpret_cast<const float4*>(xs + hp * 32 + 8 * c8 + 4);
+                                v0[i] = lds_f4(xs + (uint32_t)(hp * 128 + 32 * c8));
+                                v1[i] = lds_f4(xs + (uint32_t)(hp * 128 + 32 * c8 + 16));
                             }
                         } else if (inb[i]) {
                             const float* src = xb + ((int64_t)gy * p.w + gx) * p.cin + ch;
                             v0[i] = __ldg(reinterpret_cast<const float4*>(src));
                             v1[i] = __ldg(reinterpret_cast<const float4*>(src + 4));
                         }
-                    }
-                    if (XS) {
-                        mbar_arrive(smem_u32(&bars[XS_EMPTY + sx]));      // values are in registers: release the raw tile
-                        if (++sx == NXS) sx = 0, px ^= 1;
                     }
                     mbar_wait(smem_u32(&bars[A_EMPTY + sa]), pa ^ 1);
                     uint8_t* hi_plane = a_buf + sa * A_STAGE;
@@ -473,6 +474,14 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                     fence_proxy_async();
                     mbar_arrive(smem_u32(&bars[A_FULL + sa]));
                     if (++sa == NSTAGE_A) sa = 0, pa ^= 1;
+                    if (XS) {
+                        // Release the raw tile only AFTER the stores that consume the loaded values: an arrive issued right
+                        // behind the loads does not wait for them (no register dependence), and a load still in flight when
+                        // the next TMA write lands returns the NEXT tile's first bytes (seen on hardware: ~25 % of the work
+                        // items had the first 8 halo pixels of a chunk replaced).
+                        mbar_arrive(smem_u32(&bars[XS_EMPTY + xstage]));
+                        if (++xstage == NXS) xstage = 0, px ^= 1;
+                    }
                 }
             } else {
                 // ---- mixed tile: per (tap, parity) operand tiles, every row scaled by the style of its own output pixel's region
@@ -503,8 +512,8 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                     }
                     xform_barrier();
                     const int ch = kc * KC + 8 * c8;
-                    if (XS) mbar_wait(smem_u32(&bars[XS_FULL + sx]), px);
-                    const float* xs = reinterpret_cast<const float*>(xs_buf + sx * XS_STAGE);
+                    if (XS) mbar_wait(smem_u32(&bars[XS_FULL + xstage]), px);
+                    const uint32_t xs = smem_u32(xs_buf + xstage * XS_STAGE);
 #pragma unroll 1
                     for (int tap = 0; tap < 9; ++tap) {
                         const int dy = tap / 3, dx = tap - 3 * dy;
@@ -516,8 +525,8 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                             v0[i] = make_float4(0.f, 0.f, 0.f, 0.f), v1[i] = v0[i];
                             if (XS) {
                                 const int hp = min(((r >> 4) + dy) * 16 + (r & 15) + dx, 159);
-                                v0[i] = *reinterpret_cast<const float4*>(xs + hp * 32 + 8 * c8);
-                                v1[i] = *reinterpret_cast<const float4*>(xs + hp * 32 + 8 * c8 + 4);
+                                v0[i] = lds_f4(xs + (uint32_t)(hp * 128 + 32 * c8));
+                                v1[i] = lds_f4(xs + (uint32_t)(hp * 128 + 32 * c8 + 16));
                             } else if (gy >= 0 && gy < p.h && gx >= 0 && gx < p.w) {
                                 const float* src = xb + ((int64_t)gy * p.w + gx) * p.cin + ch;
                                 v0[i] = __ldg(reinterpret_cast<const float4*>(src));
@@ -555,8 +564,8 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                         }
                     }
                     if (XS) {
-                        mbar_arrive(smem_u32(&bars[XS_EMPTY + sx]));
-                        if (++sx == NXS) sx = 0, px ^= 1;
+                        mbar_arrive(smem_u32(&bars[XS_EMPTY + xstage]));
+                        if (++xstage == NXS) xstage = 0, px ^= 1;
                     }
                 }
             }

@@ -7,9 +7,9 @@ import traceback
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import torch
-from test_parity_gpu import _tc_case, TC_CASES, TCP_EXTRA
+from test_parity_gpu import _tc_case, TC_CASES, TCP_EXTRA, PRODUCTION_CASES
 
-CASES = TC_CASES + TCP_EXTRA + [(2, 64, 128, 30, True, 5, "blobs"), (1, 160, 256, 28, False, 12, "iid"), (2, 256, 64, 16, True, 12, "iid")]
+CASES = PRODUCTION_CASES + TC_CASES + TCP_EXTRA + [(2, 64, 128, 30, True, 5, "blobs"), (1, 160, 256, 28, False, 12, "iid"), (2, 256, 64, 16, True, 12, "iid")]
 
 for mode in ("tcr",):
     for case in CASES:
@@ -24,7 +24,10 @@ for mode in ("tcr",):
             if err > 1e-3:
                 d = (out - ref).abs().amax(dim=3)[0]            # per pixel error map of sample 0
                 rows = (d > 1e-3 * ref.abs().max()).nonzero()
-                print("   first bad pixels:", rows[:12].tolist(), flush=True)
+                print("   first bad pixels:", rows[:12].tolist(), " last:", rows[-4:].tolist(), flush=True)
+                ty = (rows[:, 0] // (16 if case[4] else 8)).unique().tolist()
+                tx = (rows[:, 1] // (28 if case[4] else 14)).unique().tolist()
+                print("   bad tile rows:", ty[:40], " bad tile cols:", tx[:40], flush=True)
         except Exception:
             traceback.print_exc()
             print(f"kernel={mode} case={case}: EXCEPTION", flush=True)

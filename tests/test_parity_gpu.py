@@ -332,6 +332,22 @@ TCP_EXTRA = [
     (1, 64, 32, 36, True, 1, "blobs"),        # up, N = 4 x 32
     (1, 96, 32, 16, True, 3, "iid"),          # 32-channel chunks x3, up, masked
     (3, 512, 512, 64, False, 12, "blobs"),    # production shape c7@64: > 148 work items, two N tiles, 12 regions
+    (1, 64, 128, 40, False, 1, "blobs"),      # encoder shape: small K with N = 128
+    (2, 32, 128, 24, False, 3, "iid"),        # small K, N = 128, masked
+]
+# production shapes of the 1024x1024 generator's top layers and of the encoder's first unit, B = 1: several work items
+# per persistent CTA (ring wrap-around of every pipeline), checked against the fp32 SIMT kernel
+PRODUCTION_CASES = [
+    (1, 64, 64, 512, False, 1, "blobs"),      # c13 @512
+    (1, 64, 32, 512, True, 1, "blobs"),       # c14 ^1024
+    (1, 32, 32, 1024, False, 1, "blobs"),     # c15 @1024
+    (1, 128, 64, 256, True, 1, "blobs"),      # c12 ^512
+    (1, 64, 128, 256, False, 1, "blobs"),     # encoder unit 0 conv1
+    (1, 128, 128, 256, False, 12, "blobs"),   # c11 @256, masked
+    (1, 256, 128, 128, True, 12, "blobs"),    # c10 ^256, masked
+    (1, 64, 64, 256, False, 12, "blobs"),     # small-K activation ring, mixed tiles
+    (1, 64, 32, 256, True, 12, "blobs"),
+    (2, 32, 32, 512, False, 5, "blobs"),
 ]
 
 
@@ -370,6 +386,16 @@ def test_tcr_kernel_matches_simt(b, cin, cout, hw, up, ncls, kind):
     out = K.modconv3x3_tcr_fwd(x, prep.w_hilo, *args)
     torch.cuda.synchronize()
     e = assert_close(out, ref, 1e-4, f"tcr vs simt {b},{cin},{cout},{hw},{up},{ncls},{kind}")
+    print(f"tcr-vs-simt rel err {e:.2e}")
+
+
+@pytest.mark.parametrize("b,cin,cout,hw,up,ncls,kind", PRODUCTION_CASES)
+def test_tcr_kernel_production_shapes(b, cin, cout, hw, up, ncls, kind):
+    K, prep, x, args = _tc_case(b, cin, cout, hw, up, ncls, kind, seed=cin + cout + hw)
+    ref = K.modconv3x3_fwd(x, prep.wt, *args)
+    out = K.modconv3x3_tcr_fwd(x, prep.w_hilo, *args)
+    torch.cuda.synchronize()
+    e = assert_close(out, ref, 1e-4, f"tcr vs simt (production shape) {b},{cin},{cout},{hw},{up},{ncls},{kind}")
     print(f"tcr-vs-simt rel err {e:.2e}")
 
 
