@@ -56,6 +56,7 @@ struct Params {
     const float* shift;
     const float* slope;
     int out_stride;
+    long long* prof;      // optional [5 roles][4] cycle counters of CTA 0 (e4s_tcr_set_profile); nullptr in production
 };
 
 // ------------------------------------------------------------------------------------ PTX helpers
@@ -95,6 +96,13 @@ __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
     return v;
+}
+// profiling variant: cycles spent waiting are added to `ctr` (bench/diagnostic builds of the launch only)
+__device__ __forceinline__ void mbar_wait_p(uint32_t bar, uint32_t parity, long long& ctr, bool on) {
+    if (!on) { mbar_wait(bar, parity); return; }
+    const long long t0 = clock64();
+    mbar_wait(bar, parity);
+    ctr += clock64() - t0;
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -222,6 +230,9 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ho = p.h * MUL, wo = p.w * MUL;
     const int nchunks = p.cin / KC;
+    const bool prof_on = p.prof != nullptr && blockIdx.x == 0;
+    long long pw[4] = {0, 0, 0, 0};                      // [0] role time, [1..3] cycles in its barrier waits
+    const long long t_start = prof_on ? clock64() : 0;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < NSTAGE_A; ++i) mbar_init(smem_u32(&bars[A_FULL + i]), NUM_XFORM), mbar_init(smem_u32(&bars[A_EMPTY + i]), 1);
@@ -254,7 +265,7 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                 for (int kc = 0; kc < nchunks; ++kc)
                     for (int tap = 0; tap < 9; ++tap)
                         for (int hl = 0; hl < 2; ++hl) {
-                            if (!p.resident) mbar_wait(smem_u32(&bars[B_EMPTY + slot]), ph ^ 1);
+                            if (!p.resident) mbar_wait_p(smem_u32(&bars[B_EMPTY + slot]), ph ^ 1, pw[1], prof_on);
                             const uint32_t full = smem_u32(&bars[B_FULL + slot]);
                             mbar_expect_tx(full, B_SLOT);
                             const uint32_t dst = smem_u32(b_buf + (size_t)slot * B_SLOT);
@@ -275,7 +286,7 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
             for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
                 const Item item = decode_item(p, it);
                 for (int kc = 0; kc < nchunks; ++kc) {
-                    mbar_wait(smem_u32(&bars[XS_EMPTY + st]), ph ^ 1);
+                    mbar_wait_p(smem_u32(&bars[XS_EMPTY + st]), ph ^ 1, pw[1], prof_on);
                     const uint32_t full = smem_u32(&bars[XS_FULL + st]);
                     mbar_expect_tx(full, XS_STAGE);
                     tma_load_4d(smem_u32(xs_buf + st * XS_STAGE), &xmap, kc * KC, item.tx * TW - 1, item.ty * TH - 1, item.b, full);
@@ -304,7 +315,7 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
             const Item item = decode_item(p, it);
             const uint32_t classes = __shfl_sync(0xffffffffu, tile_class_mask<NPH>(p, item, lane), 0);
             const bool mixed = (classes & (classes - 1)) != 0;
-            mbar_wait(bars0 + 8 * (ACC_EMPTY + acc), (acc ? pacc1 : pacc0) ^ 1);
+            mbar_wait_p(bars0 + 8 * (ACC_EMPTY + acc), (acc ? pacc1 : pacc0) ^ 1, pw[1], prof_on);
             tc_fence_after();
             const uint32_t d_tmem = tmem_u + (uint32_t)(acc * ACC_COLS);
             if (p.resident) slot = 0;
@@ -314,13 +325,13 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                 uint32_t accum = 0;
 #pragma unroll 1
                 for (int kc = 0; kc < nchunks; ++kc) {
-                    mbar_wait(bars0 + 8 * (A_FULL + sa), pa);
+                    mbar_wait_p(bars0 + 8 * (A_FULL + sa), pa, pw[2], prof_on);
                     tc_fence_after();
                     const uint32_t ah = lo_of(a0 + sa * A_STAGE), al = ah + (A_PLANE >> 4);
                     uint32_t roff = (uint32_t)ROWB >> 4;                   // tap (0,0): row shift 1
 #pragma unroll 1
                     for (int tap = 0; tap < 9; ++tap) {
-                        if (wait_b) mbar_wait(bars0 + 8 * (B_FULL + slot), pb);
+                        if (wait_b) mbar_wait_p(bars0 + 8 * (B_FULL + slot), pb, pw[3], prof_on);
                         tc_fence_after();
                         uint32_t bl = lo_of(b0 + slot * B_SLOT);
                         if (leader) {
@@ -333,7 +344,7 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                         }
                         accum = 1u;
                         if (++slot == p.nslot_b) slot = 0, pb ^= 1;
-                        if (wait_b) mbar_wait(bars0 + 8 * (B_FULL + slot), pb);
+                        if (wait_b) mbar_wait_p(bars0 + 8 * (B_FULL + slot), pb, pw[3], prof_on);
                         tc_fence_after();
                         bl = lo_of(b0 + slot * B_SLOT);
                         if (leader) {
@@ -358,13 +369,13 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                         uint32_t pb_lo = pb;
                         if (slot_lo == p.nslot_b) slot_lo = 0, pb_lo ^= 1;
                         if (wait_b) {
-                            mbar_wait(bars0 + 8 * (B_FULL + slot), pb);
-                            mbar_wait(bars0 + 8 * (B_FULL + slot_lo), pb_lo);
+                            mbar_wait_p(bars0 + 8 * (B_FULL + slot), pb, pw[3], prof_on);
+                            mbar_wait_p(bars0 + 8 * (B_FULL + slot_lo), pb_lo, pw[3], prof_on);
                         }
                         const uint32_t bh = lo_of(b0 + slot * B_SLOT), bl = lo_of(b0 + slot_lo * B_SLOT);
 #pragma unroll
                         for (int q = 0; q < NPH; ++q) {
-                            mbar_wait(bars0 + 8 * (A_FULL + sa), pa);
+                            mbar_wait_p(bars0 + 8 * (A_FULL + sa), pa, pw[2], prof_on);
                             tc_fence_after();
                             const uint32_t ah = lo_of(a0 + sa * A_STAGE), al = ah + (A_PLANE >> 4);
                             const uint32_t boff = (uint32_t)(q * NTC * ROWB) >> 4;
@@ -426,7 +437,7 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                     const float4 t1 = sh ? __ldg(reinterpret_cast<const float4*>(sh + ch + 4)) : zero4;
                     float4 v0[NSW_SHIFT], v1[NSW_SHIFT];
                     bool inb[NSW_SHIFT];
-                    if (XS) mbar_wait(smem_u32(&bars[XS_FULL + xstage]), px);
+                    if (XS) mbar_wait_p(smem_u32(&bars[XS_FULL + xstage]), px, pw[1], prof_on);
                     const uint32_t xs = smem_u32(xs_buf + xstage * XS_STAGE);
 #pragma unroll
                     for (int i = 0; i < NSW_SHIFT; ++i) {
@@ -445,7 +456,7 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                             v1[i] = __ldg(reinterpret_cast<const float4*>(src + 4));
                         }
                     }
-                    mbar_wait(smem_u32(&bars[A_EMPTY + sa]), pa ^ 1);
+                    mbar_wait_p(smem_u32(&bars[A_EMPTY + sa]), pa ^ 1, pw[2], prof_on);
                     uint8_t* hi_plane = a_buf + sa * A_STAGE;
                     uint8_t* lo_plane = hi_plane + A_PLANE;
 #pragma unroll
@@ -512,7 +523,7 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                     }
                     xform_barrier();
                     const int ch = kc * KC + 8 * c8;
-                    if (XS) mbar_wait(smem_u32(&bars[XS_FULL + xstage]), px);
+                    if (XS) mbar_wait_p(smem_u32(&bars[XS_FULL + xstage]), px, pw[1], prof_on);
                     const uint32_t xs = smem_u32(xs_buf + xstage * XS_STAGE);
 #pragma unroll 1
                     for (int tap = 0; tap < 9; ++tap) {
@@ -535,7 +546,7 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                         }
 #pragma unroll
                         for (int q = 0; q < NPH; ++q) {
-                            mbar_wait(smem_u32(&bars[A_EMPTY + sa]), pa ^ 1);
+                            mbar_wait_p(smem_u32(&bars[A_EMPTY + sa]), pa ^ 1, pw[2], prof_on);
                             uint8_t* hi_plane = a_buf + sa * A_STAGE;
                             uint8_t* lo_plane = hi_plane + A_PLANE;
 #pragma unroll
@@ -584,7 +595,7 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
             const bool strided = (NPH == 1 && p.out_stride == 2);
             const bool mine = tx < TW && iy < p.h && ix < p.w && (!strided || ((iy | ix) & 1) == 0);
             const int n0 = item.nt * NTC;
-            mbar_wait(smem_u32(&bars[ACC_FULL + acc]), pacc[acc]);
+            mbar_wait_p(smem_u32(&bars[ACC_FULL + acc]), pacc[acc], pw[1], prof_on);
             pacc[acc] ^= 1;
             tc_fence_after();
 #pragma unroll
@@ -639,6 +650,15 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
         }
     }
 
+    if (prof_on) {
+        int role = -1;
+        if (lane == 0) role = warp == 0 ? 0 : warp == 1 ? 1 : warp == 2 ? 2 : warp == 10 ? 3 : warp == 14 ? 4 : -1;
+        if (role >= 0) {
+            pw[0] = clock64() - t_start;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) p.prof[role * 4 + k] = pw[k];
+        }
+    }
     // ---- teardown
     tc_fence_before();
     __syncthreads();
@@ -678,8 +698,11 @@ static int num_sms() {
     return n;
 }
 
+static long long* g_prof = nullptr;
+
 template <int NTC, int KC, int NPH, bool XS = false>
 static int launch(const void* w_hilo, Params p, cudaStream_t st) {
+    p.prof = g_prof;
     constexpr int N = NTC * NPH, ROWB = KC * 2;
     constexpr int A_BYTES = (((NSTAGE_A * 2 * A_ROWS * ROWB) + 1023) & ~1023) + (XS ? NXS * XS_STAGE : 0);
     constexpr int B_SLOT = N * ROWB;
@@ -795,4 +818,11 @@ extern "C" int e4s_conv3x3_tcr_f32(const float* x, const void* w_hilo_bf16, cons
     tcr::Params p{x, scale, nullptr, nullptr, nullptr, nullptr, nullptr, y, batch, h, w, cin, cout, 1, 1, prelu_slope ? 2 : 0,
                   0, 0, 0, 0, 0, 0, shift, prelu_slope, out_stride};
     return tcr::dispatch(w_hilo_bf16, p, 0, (cudaStream_t)stream);
+}
+
+// Diagnostic: per-role stall attribution of CTA 0 of every following tcr launch ([5 roles][4] int64 cycle counters in
+// device memory: role time, then the cycles it spent in its barrier waits).  nullptr switches it off (the default).
+extern "C" int e4s_tcr_set_profile(long long* device_counters) {
+    tcr::g_prof = device_counters;
+    return E4S_OK;
 }

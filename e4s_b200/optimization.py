@@ -37,19 +37,21 @@ def setup_W_optimizer(W_init: torch.Tensor, opt_name: str = "adam", lr: float = 
 def invert(net, target: torch.Tensor, onehot: torch.Tensor, style_vectors: Optional[torch.Tensor] = None,
            steps: int = 200, lr: float = 1e-2, opt_name: str = "adam", l2_lambda: float = 1.0,
            extra_losses: Sequence[Tuple[float, Callable]] = (), noise: Optional[List[torch.Tensor]] = None,
-           callback: Optional[Callable] = None, cuda_graph: bool = False):
+           callback: Optional[Callable] = None, cuda_graph: bool = False, stats: Optional[dict] = None):
     """Optimise the texture vectors of ONE batch of faces so that net.gen_img reproduces `target`.
 
     net: e4s_b200.networks.Net3 (eval, latent_avg set).  target [B,3,S,S]; onehot [B,ncls,Hm,Wm].
     style_vectors: initial [B,ncls,1280] (default: the encoder's, as scripts/optimization.py:178-180).
     noise: fixed noise list, or None for fresh noise every step (the reference's behaviour, :216).
+    cuda_graph: capture one step and replay it (Adam only); stats (optional dict) then receives the device time of the
+    replayed steps alone ("replay_ms_per_step", "replayed_steps").
     Returns (latent [B,ncls,1280], final reconstruction, list of per-step loss values as 0-d tensors).
     """
     if style_vectors is None:
         with torch.no_grad():
             style_vectors, _ = net.get_style_vectors(target, onehot)
     if cuda_graph:
-        return _invert_graphed(net, target, onehot, style_vectors, steps, lr, l2_lambda, extra_losses, noise)
+        return _invert_graphed(net, target, onehot, style_vectors, steps, lr, l2_lambda, extra_losses, noise, stats)
     opt, latent = setup_W_optimizer(style_vectors, opt_name, lr)
     history, recon = [], None
     for step in range(steps):
@@ -67,7 +69,7 @@ def invert(net, target: torch.Tensor, onehot: torch.Tensor, style_vectors: Optio
     return latent.detach(), recon.detach(), history
 
 
-def _invert_graphed(net, target, onehot, style_vectors, steps, lr, l2_lambda, extra_losses, noise):
+def _invert_graphed(net, target, onehot, style_vectors, steps, lr, l2_lambda, extra_losses, noise, stats=None):
     """The same loop with one optimisation step (zero_grad, forward, loss, backward, Adam) captured in a CUDA graph and
     replayed: at one face per GPU the eager loop is bound by ~400 kernel launches per step, not by the kernels.
     Adam only (capturable); fresh noise comes from the graph-safe CUDA generator, so every replay draws new noise."""
@@ -102,7 +104,14 @@ def _invert_graphed(net, target, onehot, style_vectors, steps, lr, l2_lambda, ex
         with torch.cuda.graph(graph):
             one_step()
         history.append(static_loss.clone())
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
         for _ in range(steps - warm - 1):
             graph.replay()
             history.append(static_loss.clone())
+        e1.record()
+        if stats is not None and steps - warm - 1 > 0:
+            e1.synchronize()
+            stats["replayed_steps"] = steps - warm - 1
+            stats["replay_ms_per_step"] = e0.elapsed_time(e1) / (steps - warm - 1)
     return latent.detach(), static_recon, history

@@ -153,6 +153,9 @@ int e4s_modconv3x3_tcr_fwd(const float* x, const void* w_hilo_bf16, const float*
 int e4s_conv3x3_tcr_f32(const float* x, const void* w_hilo_bf16, const float* scale, const float* shift,
                         const float* prelu_slope, float* y, int batch, int h, int w, int cin, int cout, int out_stride,
                         void* stream);
+/* Diagnostic (no reference counterpart): per-role stall attribution of CTA 0 of every following gen-4 launch.
+ * device_counters: [5 roles][4] int64 in device memory (role time, cycles in its barrier waits); NULL = off. */
+int e4s_tcr_set_profile(long long* device_counters);
 
 /* ---- RGI encoder conv stack (src/models/encoders/helpers.py:122-144, psp_encoders.py:285-309) ------------------
  * Plain 3x3 convolution, padding 1, stride 1 or 2 (out_stride), on the persistent tensor-core kernel.

@@ -45,6 +45,7 @@ def main():
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "opbench.json"))
     ap.add_argument("--conv", default="simt,tc")
     ap.add_argument("--layers", default="all")
+    ap.add_argument("--prof", action="store_true", help="gen-4 kernel: per-role stall attribution of CTA 0 (e4s_tcr_set_profile)")
     ap.add_argument("--unmasked", action="store_true", help="time the masked layers with a single region (no class passes)")
     args = ap.parse_args()
     B = args.batch
@@ -131,6 +132,20 @@ def main():
             ms = timeit(fn, iters=3, warmup=1, flush=flush)
             total[mode] += ms
             row(f"modconv[{mode}] {name} {cin}->{cout} in{r} up{up} ncls{ncls}", ms, flops, "TFLOP/s")
+            if args.prof and mode == "tcr":
+                from e4s_b200._lib import load as lib
+                ctr = torch.zeros(20, dtype=torch.int64, device=DEV)
+                lib().e4s_tcr_set_profile(ctr.data_ptr())
+                fn()
+                torch.cuda.synchronize()
+                lib().e4s_tcr_set_profile(None)
+                c = ctr.cpu().view(5, 4).tolist()
+                names = ["weights(TMA)  wait: B_EMPTY", "mma           wait: ACC_EMPTY, A_FULL, B_FULL", "transform     wait: XS_FULL, A_EMPTY",
+                         "epilogue      wait: ACC_FULL", "x-tiles(TMA)  wait: XS_EMPTY"]
+                for rname, cc in zip(names, c):
+                    tot = max(cc[0], 1)
+                    print(f"    prof {rname:48s} total {cc[0]:>10d} cyc  waits " + " ".join(f"{100.0 * v / tot:5.1f}%" for v in cc[1:]), flush=True)
+                res["rows"][-1]["prof"] = c
         del xpm, noise
     res["conv_total_ms"] = total
     print(json.dumps({"conv_total_ms": total}))
