@@ -12,7 +12,7 @@ from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
 import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libe4s_b200.so")
+LIB_PATH = os.environ.get("E4S_B200_LIB") or os.path.join(_PKG, "libe4s_b200.so")   # env: diagnostic twin (build --profile)
 
 _ERR = {-1: "E4S_ERR_ARG (null pointer / bad size)", -2: "E4S_ERR_SHAPE (unsupported shape)",
         -3: "E4S_ERR_ALIGN (pointer not 16-byte aligned)", -4: "E4S_ERR_NOT_ONEHOT", -5: "E4S_ERR_ARCH (device is not sm_100)"}

@@ -32,12 +32,12 @@ def _newer(src_list, target):
     return any(os.path.getmtime(s) > t for s in src_list)
 
 
-def _compile(src, verbose):
-    obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
+def _compile(src, verbose, objdir=None, extra=()):
+    obj = os.path.join(objdir or OBJ, os.path.basename(src)[:-3] + ".o")
     deps = [src] + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(INCLUDE, "*.h"))
     if not _newer(deps, obj):
         return obj, ""
-    cmd = [NVCC] + ARCH + CFLAGS + ["-c", src, "-o", obj]
+    cmd = [NVCC] + ARCH + CFLAGS + list(extra) + ["-c", src, "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
@@ -67,6 +67,26 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_profile(verbose: bool = False) -> str:
+    """Diagnostic twin of the library with the gen-4 kernel's stall counters compiled in (tools/opbench.py --prof):
+    libe4s_b200_prof.so, selected with E4S_B200_LIB=<path>."""
+    build(verbose=verbose)
+    objdir = os.path.join(CSRC, "_obj_prof")
+    os.makedirs(objdir, exist_ok=True)
+    src = os.path.join(CSRC, "modconv_tcr.cu")
+    obj, _ = _compile(src, verbose, objdir, ["-DE4S_TCR_PROFILE"])
+    others = [os.path.join(OBJ, os.path.basename(s)[:-3] + ".o") for s in sorted(glob.glob(os.path.join(CSRC, "*.cu"))) if s != src]
+    lib = os.path.join(PKG, "libe4s_b200_prof.so")
+    if _newer([obj] + others, lib):
+        r = subprocess.run([NVCC] + ARCH + ["-shared", "-o", lib, obj] + others + ["-lcudart", "-lcuda"], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return lib
+
+
 if __name__ == "__main__":
+    if "--profile" in sys.argv:
+        print(build_profile(verbose="--verbose" in sys.argv))
+        sys.exit(0)
     path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
     print(path)

@@ -37,7 +37,7 @@ constexpr int A_ROWS = 168;
 constexpr int NSTAGE_A = 2;
 constexpr int NUM_THREADS = 448;              // 14 warps: 0 weights, 1 MMA, 2-9 transform, 10-13 epilogue
 constexpr int NUM_THREADS_XS = 480;           // + warp 14: producer of raw activation tiles (XS mode)
-constexpr int NXS = 4;                        // raw-tile ring depth (XS mode, 32-channel chunks: 20 KB per stage)
+constexpr int NXS = 3;                        // raw-tile ring depth (XS mode, 32-channel chunks: 20 KB per stage)
 constexpr int XS_STAGE = 160 * 32 * 4;
 constexpr int NUM_XFORM = 256, NUM_EPI = 128;
 constexpr int SMEM_BUDGET = 227 * 1024 - 2048;
@@ -97,13 +97,19 @@ __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
     return v;
 }
-// profiling variant: cycles spent waiting are added to `ctr` (bench/diagnostic builds of the launch only)
+// Stall attribution (tools/opbench.py --prof): only in the diagnostic build (-DE4S_TCR_PROFILE, libe4s_b200_prof.so) -
+// the eight counter registers cost the mixed-tile transform path ~10 % through spills.
+#ifdef E4S_TCR_PROFILE
 __device__ __forceinline__ void mbar_wait_p(uint32_t bar, uint32_t parity, long long& ctr, bool on) {
     if (!on) { mbar_wait(bar, parity); return; }
     const long long t0 = clock64();
     mbar_wait(bar, parity);
     ctr += clock64() - t0;
 }
+#define MBAR_WAIT_P(bar, parity, k) mbar_wait_p(bar, parity, pw[k], prof_on)
+#else
+#define MBAR_WAIT_P(bar, parity, k) mbar_wait(bar, parity)
+#endif
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -201,13 +207,24 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
     constexpr int A_PLANE = A_ROWS * ROWB;
     constexpr int A_STAGE = 2 * A_PLANE;
     constexpr int B_SLOT = N * ROWB;
-    constexpr int PARTS = 1;      // partial accumulators (rotating MMAs over 256/N column ranges) measured no gain: off
-    constexpr int ACC_COLS = PARTS * N;                // 256
+    // N-STACKING: an MMA of M = 128 costs ~130-150 cycles whatever its N (the A operand, 128 rows x 32 B per K step, is read
+    // from shared memory at a fixed rate; measured with the stall counters, tools/opbench.py --prof).  Where two weight
+    // planes fit in one MMA (2N <= 256) the products x_hi*w_hi and x_hi*w_lo are therefore computed by ONE instruction
+    // against B' = [w_hi ; w_lo] (the two ring slots are adjacent in shared memory) into 2N accumulator columns, and
+    // x_lo*w_hi by a second one: 2 instructions per tap and K step instead of 3, the epilogue adds the two column halves.
+    constexpr bool SP = (2 * N <= 256);               // region-pure tiles: all parities, [hi | lo]
+    // mixed tiles: per parity [hi | lo] (slot pair laid out [q][hl][NTC]).  Measured slower for up-sampling layers (the
+    // 4 x 2 x 64-column tile needs both accumulator buffers, so MMA and epilogue stop overlapping): plain convs only.
+    constexpr bool SMX = (2 * NTC <= 256) && NPH == 1;
+    constexpr bool MIX_WIDE = SMX && (2 * N > 256);   // ... which then needs both accumulator buffers (512 columns)
+    constexpr int ACC_COLS = 256;
     constexpr int NACC = 2;
     constexpr int TMEM_COLS = 512;
     constexpr uint32_t IDESC_BASE = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 4) << 24);
     constexpr uint32_t IDESC_N = IDESC_BASE | ((uint32_t)(N >> 3) << 17);         // all parities in one MMA
     constexpr uint32_t IDESC_Q = IDESC_BASE | ((uint32_t)(NTC >> 3) << 17);       // one parity
+    constexpr uint32_t IDESC_2N = IDESC_BASE | ((uint32_t)((SP ? 2 * N : N) >> 3) << 17);
+    constexpr uint32_t IDESC_2Q = IDESC_BASE | ((uint32_t)((SMX ? 2 * NTC : NTC) >> 3) << 17);
     constexpr uint32_t DESC_HI = (uint32_t)((KC == 64 ? 1024u : 512u) >> 4) | (1u << 14) | ((KC == 64 ? 2u : 4u) << 29);
     constexpr int KSTEPS = KC / 16;
     constexpr int MUL = NPH == 4 ? 2 : 1;
@@ -230,9 +247,13 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ho = p.h * MUL, wo = p.w * MUL;
     const int nchunks = p.cin / KC;
+    // resident weights of an up-sampling layer are shared by pure and mixed tiles, whose stacked layouts differ
+    const bool stack_mixed = SMX && !(p.resident && NPH == 4);
+#ifdef E4S_TCR_PROFILE
     const bool prof_on = p.prof != nullptr && blockIdx.x == 0;
     long long pw[4] = {0, 0, 0, 0};                      // [0] role time, [1..3] cycles in its barrier waits
     const long long t_start = prof_on ? clock64() : 0;
+#endif
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < NSTAGE_A; ++i) mbar_init(smem_u32(&bars[A_FULL + i]), NUM_XFORM), mbar_init(smem_u32(&bars[A_EMPTY + i]), 1);
@@ -258,26 +279,38 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
         uint32_t ph = 0;
         const int rows_lo = (NPH * 9) * p.cout;
         bool loaded_resident = false;
-        if (lane == 0) {
-            for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
-                if (p.resident && loaded_resident) break;
-                const Item item = decode_item(p, it);
+        for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
+            if (p.resident && loaded_resident) break;
+            const Item item = decode_item(p, it);
+            bool by_parity = false;                      // slot pair laid out [q][hl][NTC] (mixed tile, stacked MMAs)
+            if (NPH == 4 && stack_mixed) {
+                const uint32_t classes = tile_class_mask<NPH>(p, item, lane);
+                by_parity = (classes & (classes - 1)) != 0;
+            }
+            if (lane == 0) {
                 for (int kc = 0; kc < nchunks; ++kc)
                     for (int tap = 0; tap < 9; ++tap)
                         for (int hl = 0; hl < 2; ++hl) {
-                            if (!p.resident) mbar_wait_p(smem_u32(&bars[B_EMPTY + slot]), ph ^ 1, pw[1], prof_on);
+                            if (!p.resident) {
+                                MBAR_WAIT_P(smem_u32(&bars[B_EMPTY + slot]), ph ^ 1, 1);
+                                // the [q][hl] layout puts hi rows into both slots of the pair: both must be free
+                                if (by_parity && hl == 0) MBAR_WAIT_P(smem_u32(&bars[B_EMPTY + slot + 1]), ph ^ 1, 1);
+                            }
                             const uint32_t full = smem_u32(&bars[B_FULL + slot]);
                             mbar_expect_tx(full, B_SLOT);
-                            const uint32_t dst = smem_u32(b_buf + (size_t)slot * B_SLOT);
+                            const uint32_t pair = smem_u32(b_buf + (size_t)(slot & ~1) * B_SLOT);
 #pragma unroll
-                            for (int q = 0; q < NPH; ++q)
-                                tma_load_2d(dst + q * NTC * ROWB, &wmap, kc * KC, hl * rows_lo + (q * 9 + tap) * p.cout + item.nt * NTC, full);
+                            for (int q = 0; q < NPH; ++q) {
+                                const uint32_t dst = by_parity ? pair + (uint32_t)((q * 2 + hl) * NTC * ROWB)
+                                                               : pair + (uint32_t)(hl * B_SLOT + q * NTC * ROWB);
+                                tma_load_2d(dst, &wmap, kc * KC, hl * rows_lo + (q * 9 + tap) * p.cout + item.nt * NTC, full);
+                            }
                             if (++slot == p.nslot_b) slot = 0, ph ^= 1;
                         }
-                loaded_resident = true;
             }
+            loaded_resident = true;
+            __syncwarp();
         }
-        __syncwarp();
     } else if (warp == 14) {
         // ===================================================================== raw activation tile producer (XS mode)
         if (XS && lane == 0) {
@@ -286,7 +319,7 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
             for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
                 const Item item = decode_item(p, it);
                 for (int kc = 0; kc < nchunks; ++kc) {
-                    mbar_wait_p(smem_u32(&bars[XS_EMPTY + st]), ph ^ 1, pw[1], prof_on);
+                    MBAR_WAIT_P(smem_u32(&bars[XS_EMPTY + st]), ph ^ 1, 1);
                     const uint32_t full = smem_u32(&bars[XS_FULL + st]);
                     mbar_expect_tx(full, XS_STAGE);
                     tma_load_4d(smem_u32(xs_buf + st * XS_STAGE), &xmap, kc * KC, item.tx * TW - 1, item.ty * TH - 1, item.b, full);
@@ -315,9 +348,11 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
             const Item item = decode_item(p, it);
             const uint32_t classes = __shfl_sync(0xffffffffu, tile_class_mask<NPH>(p, item, lane), 0);
             const bool mixed = (classes & (classes - 1)) != 0;
-            mbar_wait_p(bars0 + 8 * (ACC_EMPTY + acc), (acc ? pacc1 : pacc0) ^ 1, pw[1], prof_on);
+            const bool wide = MIX_WIDE && mixed && stack_mixed;      // a stacked mixed tile of 4 x 64 columns: both buffers
+            MBAR_WAIT_P(bars0 + 8 * (ACC_EMPTY + acc), (acc ? pacc1 : pacc0) ^ 1, 1);
+            if (wide) MBAR_WAIT_P(bars0 + 8 * (ACC_EMPTY + (acc ^ 1)), (acc ? pacc0 : pacc1) ^ 1, 1);
             tc_fence_after();
-            const uint32_t d_tmem = tmem_u + (uint32_t)(acc * ACC_COLS);
+            const uint32_t d_tmem = wide ? tmem_u : tmem_u + (uint32_t)(acc * ACC_COLS);
             if (p.resident) slot = 0;
             const bool wait_b = !p.resident || !b_ready;
             if (!mixed) {
@@ -325,34 +360,58 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                 uint32_t accum = 0;
 #pragma unroll 1
                 for (int kc = 0; kc < nchunks; ++kc) {
-                    mbar_wait_p(bars0 + 8 * (A_FULL + sa), pa, pw[2], prof_on);
+                    MBAR_WAIT_P(bars0 + 8 * (A_FULL + sa), pa, 2);
                     tc_fence_after();
                     const uint32_t ah = lo_of(a0 + sa * A_STAGE), al = ah + (A_PLANE >> 4);
                     uint32_t roff = (uint32_t)ROWB >> 4;                   // tap (0,0): row shift 1
 #pragma unroll 1
                     for (int tap = 0; tap < 9; ++tap) {
-                        if (wait_b) mbar_wait_p(bars0 + 8 * (B_FULL + slot), pb, pw[3], prof_on);
-                        tc_fence_after();
-                        uint32_t bl = lo_of(b0 + slot * B_SLOT);
-                        if (leader) {
-#pragma unroll
-                            for (int k = 0; k < KSTEPS; ++k) {
-                                umma_bf16(d_tmem, desc(ah + roff + 2 * k), desc(bl + 2 * k), IDESC_N, k == 0 ? accum : 1u);
-                                umma_bf16(d_tmem, desc(al + roff + 2 * k), desc(bl + 2 * k), IDESC_N, 1u);
+                        if (SP) {
+                            // slots (slot, slot + 1) = [w_hi ; w_lo], adjacent: x_hi * [hi|lo] -> 2N columns, x_lo * hi -> first N
+                            if (wait_b) {
+                                MBAR_WAIT_P(bars0 + 8 * (B_FULL + slot), pb, 3);
+                                MBAR_WAIT_P(bars0 + 8 * (B_FULL + slot + 1), pb, 3);
                             }
-                            if (!p.resident) umma_commit(bars0 + 8 * (B_EMPTY + slot));
-                        }
-                        accum = 1u;
-                        if (++slot == p.nslot_b) slot = 0, pb ^= 1;
-                        if (wait_b) mbar_wait_p(bars0 + 8 * (B_FULL + slot), pb, pw[3], prof_on);
-                        tc_fence_after();
-                        bl = lo_of(b0 + slot * B_SLOT);
-                        if (leader) {
+                            tc_fence_after();
+                            const uint32_t bp = lo_of(b0 + slot * B_SLOT);
+                            if (leader) {
 #pragma unroll
-                            for (int k = 0; k < KSTEPS; ++k) umma_bf16(d_tmem, desc(ah + roff + 2 * k), desc(bl + 2 * k), IDESC_N, 1u);
-                            if (!p.resident) umma_commit(bars0 + 8 * (B_EMPTY + slot));
+                                for (int k = 0; k < KSTEPS; ++k) {
+                                    umma_bf16(d_tmem, desc(ah + roff + 2 * k), desc(bp + 2 * k), IDESC_2N, k == 0 ? accum : 1u);
+                                    umma_bf16(d_tmem, desc(al + roff + 2 * k), desc(bp + 2 * k), IDESC_N, 1u);
+                                }
+                                if (!p.resident) {
+                                    umma_commit(bars0 + 8 * (B_EMPTY + slot));
+                                    umma_commit(bars0 + 8 * (B_EMPTY + slot + 1));
+                                }
+                            }
+                            accum = 1u;
+                            slot += 2;
+                            if (slot >= p.nslot_b) slot = 0, pb ^= 1;
+                        } else {
+                            if (wait_b) MBAR_WAIT_P(bars0 + 8 * (B_FULL + slot), pb, 3);
+                            tc_fence_after();
+                            uint32_t bl = lo_of(b0 + slot * B_SLOT);
+                            if (leader) {
+#pragma unroll
+                                for (int k = 0; k < KSTEPS; ++k) {
+                                    umma_bf16(d_tmem, desc(ah + roff + 2 * k), desc(bl + 2 * k), IDESC_N, k == 0 ? accum : 1u);
+                                    umma_bf16(d_tmem, desc(al + roff + 2 * k), desc(bl + 2 * k), IDESC_N, 1u);
+                                }
+                                if (!p.resident) umma_commit(bars0 + 8 * (B_EMPTY + slot));
+                            }
+                            accum = 1u;
+                            if (++slot == p.nslot_b) slot = 0, pb ^= 1;
+                            if (wait_b) MBAR_WAIT_P(bars0 + 8 * (B_FULL + slot), pb, 3);
+                            tc_fence_after();
+                            bl = lo_of(b0 + slot * B_SLOT);
+                            if (leader) {
+#pragma unroll
+                                for (int k = 0; k < KSTEPS; ++k) umma_bf16(d_tmem, desc(ah + roff + 2 * k), desc(bl + 2 * k), IDESC_N, 1u);
+                                if (!p.resident) umma_commit(bars0 + 8 * (B_EMPTY + slot));
+                            }
+                            if (++slot == p.nslot_b) slot = 0, pb ^= 1;
                         }
-                        if (++slot == p.nslot_b) slot = 0, pb ^= 1;
                         // next tap: +1 row, or to the start of the next halo row (+16 - 2) after dx = 2
                         roff += (uint32_t)(((tap % 3) == 2 ? (TWP - 2) : 1) * ROWB) >> 4;
                     }
@@ -360,8 +419,8 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                     if (++sa == NSTAGE_A) sa = 0, pa ^= 1;
                 }
             } else {
-                // ---------------- mixed tile: one operand slot per (tap, parity), MMAs of N = NTC
-                uint32_t inited = 0;                     // bit (part * 4 + parity): that column range already holds a sum
+                // ---------------- mixed tile: one operand slot per (tap, parity), MMAs of N = NTC (2 NTC when stacked)
+                uint32_t inited = 0;                     // bit parity: that column range already holds a sum
                 for (int kc = 0; kc < nchunks; ++kc) {
 #pragma unroll 1
                     for (int tap = 0; tap < 9; ++tap) {
@@ -369,24 +428,37 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                         uint32_t pb_lo = pb;
                         if (slot_lo == p.nslot_b) slot_lo = 0, pb_lo ^= 1;
                         if (wait_b) {
-                            mbar_wait_p(bars0 + 8 * (B_FULL + slot), pb, pw[3], prof_on);
-                            mbar_wait_p(bars0 + 8 * (B_FULL + slot_lo), pb_lo, pw[3], prof_on);
+                            MBAR_WAIT_P(bars0 + 8 * (B_FULL + slot), pb, 3);
+                            MBAR_WAIT_P(bars0 + 8 * (B_FULL + slot_lo), pb_lo, 3);
                         }
                         const uint32_t bh = lo_of(b0 + slot * B_SLOT), bl = lo_of(b0 + slot_lo * B_SLOT);
 #pragma unroll
                         for (int q = 0; q < NPH; ++q) {
-                            mbar_wait_p(bars0 + 8 * (A_FULL + sa), pa, pw[2], prof_on);
+                            MBAR_WAIT_P(bars0 + 8 * (A_FULL + sa), pa, 2);
                             tc_fence_after();
                             const uint32_t ah = lo_of(a0 + sa * A_STAGE), al = ah + (A_PLANE >> 4);
-                            const uint32_t boff = (uint32_t)(q * NTC * ROWB) >> 4;
-                            const uint32_t dq = d_tmem + (uint32_t)(q * NTC);
                             const uint32_t bit = 1u << q;
-                            if (leader) {
+                            if (stack_mixed) {
+                                // slot pair = [q][hi | lo][NTC] rows: x_hi * [hi|lo](q) -> 2 NTC columns, x_lo * hi(q) -> first NTC
+                                const uint32_t bq = bh + ((uint32_t)(q * 2 * NTC * ROWB) >> 4);
+                                const uint32_t dq = d_tmem + (uint32_t)(q * 2 * NTC);
+                                if (leader) {
 #pragma unroll
-                                for (int k = 0; k < KSTEPS; ++k) {
-                                    umma_bf16(dq, desc(ah + 2 * k), desc(bh + boff + 2 * k), IDESC_Q, (k == 0 && !(inited & bit)) ? 0u : 1u);
-                                    umma_bf16(dq, desc(al + 2 * k), desc(bh + boff + 2 * k), IDESC_Q, 1u);
-                                    umma_bf16(dq, desc(ah + 2 * k), desc(bl + boff + 2 * k), IDESC_Q, 1u);
+                                    for (int k = 0; k < KSTEPS; ++k) {
+                                        umma_bf16(dq, desc(ah + 2 * k), desc(bq + 2 * k), IDESC_2Q, (k == 0 && !(inited & bit)) ? 0u : 1u);
+                                        umma_bf16(dq, desc(al + 2 * k), desc(bq + 2 * k), IDESC_Q, 1u);
+                                    }
+                                }
+                            } else {
+                                const uint32_t boff = (uint32_t)(q * NTC * ROWB) >> 4;
+                                const uint32_t dq = d_tmem + (uint32_t)(q * NTC);
+                                if (leader) {
+#pragma unroll
+                                    for (int k = 0; k < KSTEPS; ++k) {
+                                        umma_bf16(dq, desc(ah + 2 * k), desc(bh + boff + 2 * k), IDESC_Q, (k == 0 && !(inited & bit)) ? 0u : 1u);
+                                        umma_bf16(dq, desc(al + 2 * k), desc(bh + boff + 2 * k), IDESC_Q, 1u);
+                                        umma_bf16(dq, desc(ah + 2 * k), desc(bl + boff + 2 * k), IDESC_Q, 1u);
+                                    }
                                 }
                             }
                             inited |= bit;
@@ -405,6 +477,11 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
             if (leader) umma_commit(bars0 + 8 * (ACC_FULL + acc));
             if (acc) pacc1 ^= 1; else pacc0 ^= 1;
             acc ^= 1;
+            if (wide) {                                  // the tile used both buffers: hand both over, buffer order unchanged
+                if (leader) umma_commit(bars0 + 8 * (ACC_FULL + acc));
+                if (acc) pacc1 ^= 1; else pacc0 ^= 1;
+                acc ^= 1;
+            }
             b_ready = true;
             __syncwarp();
         }
@@ -437,7 +514,7 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                     const float4 t1 = sh ? __ldg(reinterpret_cast<const float4*>(sh + ch + 4)) : zero4;
                     float4 v0[NSW_SHIFT], v1[NSW_SHIFT];
                     bool inb[NSW_SHIFT];
-                    if (XS) mbar_wait_p(smem_u32(&bars[XS_FULL + xstage]), px, pw[1], prof_on);
+                    if (XS) MBAR_WAIT_P(smem_u32(&bars[XS_FULL + xstage]), px, 1);
                     const uint32_t xs = smem_u32(xs_buf + xstage * XS_STAGE);
 #pragma unroll
                     for (int i = 0; i < NSW_SHIFT; ++i) {
@@ -456,7 +533,7 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                             v1[i] = __ldg(reinterpret_cast<const float4*>(src + 4));
                         }
                     }
-                    mbar_wait_p(smem_u32(&bars[A_EMPTY + sa]), pa ^ 1, pw[2], prof_on);
+                    MBAR_WAIT_P(smem_u32(&bars[A_EMPTY + sa]), pa ^ 1, 2);
                     uint8_t* hi_plane = a_buf + sa * A_STAGE;
                     uint8_t* lo_plane = hi_plane + A_PLANE;
 #pragma unroll
@@ -523,7 +600,7 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                     }
                     xform_barrier();
                     const int ch = kc * KC + 8 * c8;
-                    if (XS) mbar_wait_p(smem_u32(&bars[XS_FULL + xstage]), px, pw[1], prof_on);
+                    if (XS) MBAR_WAIT_P(smem_u32(&bars[XS_FULL + xstage]), px, 1);
                     const uint32_t xs = smem_u32(xs_buf + xstage * XS_STAGE);
 #pragma unroll 1
                     for (int tap = 0; tap < 9; ++tap) {
@@ -546,7 +623,7 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                         }
 #pragma unroll
                         for (int q = 0; q < NPH; ++q) {
-                            mbar_wait_p(smem_u32(&bars[A_EMPTY + sa]), pa ^ 1, pw[2], prof_on);
+                            MBAR_WAIT_P(smem_u32(&bars[A_EMPTY + sa]), pa ^ 1, 2);
                             uint8_t* hi_plane = a_buf + sa * A_STAGE;
                             uint8_t* lo_plane = hi_plane + A_PLANE;
 #pragma unroll
@@ -595,27 +672,44 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
             const bool strided = (NPH == 1 && p.out_stride == 2);
             const bool mine = tx < TW && iy < p.h && ix < p.w && (!strided || ((iy | ix) & 1) == 0);
             const int n0 = item.nt * NTC;
-            mbar_wait_p(smem_u32(&bars[ACC_FULL + acc]), pacc[acc], pw[1], prof_on);
-            pacc[acc] ^= 1;
-            tc_fence_after();
+            const uint32_t classes = tile_class_mask<NPH>(p, item, lane);
+            const bool mixed = (classes & (classes - 1)) != 0;
+            const bool wide = MIX_WIDE && mixed && stack_mixed;
+            const int oh = strided ? (p.h >> 1) : ho, ow = strided ? (p.w >> 1) : wo;
+            // everything that does not depend on the accumulator is fetched while the MMAs of this tile still run
+            int cls[NPH];
+            float nz[NPH];
 #pragma unroll
             for (int q = 0; q < NPH; ++q) {
                 const int oy = strided ? (iy >> 1) : iy * MUL + (q >> 1), ox = strided ? (ix >> 1) : ix * MUL + (q & 1);
-                const int oh = strided ? (p.h >> 1) : ho, ow = strided ? (p.w >> 1) : wo;
-                int cls = 0;
-                if (mine && p.label) cls = min((int)p.label[((int64_t)item.b * oh + oy) * ow + ox], p.ncls - 1);
-                const float* dm = p.demod ? p.demod + ((int64_t)item.b * p.ncls + cls) * p.cout + n0 : nullptr;
-                float nz = 0.f;
-                if (mine && p.noise) nz = nw * __ldg(p.noise + ((int64_t)(p.noise_b == 1 ? 0 : item.b) * oh + oy) * ow + ox);
+                cls[q] = 0, nz[q] = 0.f;
+                if (mine && p.label) cls[q] = min((int)p.label[((int64_t)item.b * oh + oy) * ow + ox], p.ncls - 1);
+                if (mine && p.noise) nz[q] = nw * __ldg(p.noise + ((int64_t)(p.noise_b == 1 ? 0 : item.b) * oh + oy) * ow + ox);
+            }
+            MBAR_WAIT_P(smem_u32(&bars[ACC_FULL + acc]), pacc[acc], 1);
+            pacc[acc] ^= 1;
+            if (wide) {
+                MBAR_WAIT_P(smem_u32(&bars[ACC_FULL + (acc ^ 1)]), pacc[acc ^ 1], 1);
+                pacc[acc ^ 1] ^= 1;
+            }
+            tc_fence_after();
+            // accumulator columns of (parity q, channel c): stacked tiles keep the x_hi * w_lo products lo_off columns further
+            const uint32_t cbase = wide ? 0u : (uint32_t)(acc * ACC_COLS);
+            const int qstride = (mixed && stack_mixed) ? 2 * NTC : NTC;
+            const int lo_off = mixed ? (stack_mixed ? NTC : 0) : (SP ? N : 0);
+#pragma unroll
+            for (int q = 0; q < NPH; ++q) {
+                const int oy = strided ? (iy >> 1) : iy * MUL + (q >> 1), ox = strided ? (ix >> 1) : ix * MUL + (q & 1);
+                const float* dm = p.demod ? p.demod + ((int64_t)item.b * p.ncls + cls[q]) * p.cout + n0 : nullptr;
                 float* dst = p.y + (((int64_t)item.b * oh + oy) * ow + ox) * p.cout + n0;
 #pragma unroll 1
                 for (int j = 0; j < NTC / 32; ++j) {
                     uint32_t r[32];
-                    tmem_ld32(tmem_base + ((quarter * 32u) << 16) + (uint32_t)(acc * ACC_COLS + q * NTC + j * 32), r);
-#pragma unroll 1
-                    for (int part = 1; part < PARTS; ++part) {          // add the other partial accumulators
+                    const uint32_t col = tmem_base + ((quarter * 32u) << 16) + cbase + (uint32_t)(q * qstride + j * 32);
+                    tmem_ld32(col, r);
+                    if (lo_off) {
                         uint32_t r2[32];
-                        tmem_ld32(tmem_base + ((quarter * 32u) << 16) + (uint32_t)(acc * ACC_COLS + part * N + q * NTC + j * 32), r2);
+                        tmem_ld32(col + (uint32_t)lo_off, r2);
 #pragma unroll
                         for (int e = 0; e < 32; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) + __uint_as_float(r2[e]));
                     }
@@ -626,10 +720,10 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                             const float4 d = dm ? __ldg(reinterpret_cast<const float4*>(dm + co)) : make_float4(1.f, 1.f, 1.f, 1.f);
                             const float4 bv = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n0 + co)) : make_float4(0.f, 0.f, 0.f, 0.f);
                             float4 o;
-                            o.x = __uint_as_float(r[4 * g + 0]) * d.x + nz + bv.x;
-                            o.y = __uint_as_float(r[4 * g + 1]) * d.y + nz + bv.y;
-                            o.z = __uint_as_float(r[4 * g + 2]) * d.z + nz + bv.z;
-                            o.w = __uint_as_float(r[4 * g + 3]) * d.w + nz + bv.w;
+                            o.x = __uint_as_float(r[4 * g + 0]) * d.x + nz[q] + bv.x;
+                            o.y = __uint_as_float(r[4 * g + 1]) * d.y + nz[q] + bv.y;
+                            o.z = __uint_as_float(r[4 * g + 2]) * d.z + nz[q] + bv.z;
+                            o.w = __uint_as_float(r[4 * g + 3]) * d.w + nz[q] + bv.w;
                             if (p.act == 1) {
                                 const float k = 1.41421356237309515f;
                                 o.x = lrelu_scaled(o.x, 0.2f, k), o.y = lrelu_scaled(o.y, 0.2f, k);
@@ -646,10 +740,15 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
             }
             tc_fence_before();
             mbar_arrive(smem_u32(&bars[ACC_EMPTY + acc]));
-            if (NACC == 2) acc ^= 1;
+            acc ^= 1;
+            if (wide) {
+                mbar_arrive(smem_u32(&bars[ACC_EMPTY + acc]));
+                acc ^= 1;
+            }
         }
     }
 
+#ifdef E4S_TCR_PROFILE
     if (prof_on) {
         int role = -1;
         if (lane == 0) role = warp == 0 ? 0 : warp == 1 ? 1 : warp == 2 ? 2 : warp == 10 ? 3 : warp == 14 ? 4 : -1;
@@ -659,6 +758,7 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
             for (int k = 0; k < 4; ++k) p.prof[role * 4 + k] = pw[k];
         }
     }
+#endif
     // ---- teardown
     tc_fence_before();
     __syncthreads();
@@ -741,7 +841,9 @@ static int launch(const void* w_hilo, Params p, cudaStream_t st) {
     if (max_slots > 36) max_slots = 36;
     if (max_slots < 4) return E4S_ERR_SHAPE;
     p.resident = (p.n_tiles == 1 && planes <= max_slots) ? 1 : 0;
-    p.nslot_b = p.resident ? planes : (max_slots > 8 ? 8 : max_slots);
+    // streamed weights: a deep ring (TMA latency ~2000 cycles against 4 MMAs per slot pair on the small-N layers);
+    // even, so that (hi, lo) pairs never straddle the wrap
+    p.nslot_b = p.resident ? planes : (max_slots > 16 ? 16 : (max_slots & ~1));
     const size_t smem = 1024 + A_BYTES + (size_t)p.nslot_b * B_SLOT + tab_bytes + (size_t)(2 * NSTAGE_A + 4 + 2 * p.nslot_b + 2 * NXS) * 8 + 64;
     static size_t smem_set = 0;
     if (smem > smem_set) {
@@ -823,6 +925,10 @@ extern "C" int e4s_conv3x3_tcr_f32(const float* x, const void* w_hilo_bf16, cons
 // Diagnostic: per-role stall attribution of CTA 0 of every following tcr launch ([5 roles][4] int64 cycle counters in
 // device memory: role time, then the cycles it spent in its barrier waits).  nullptr switches it off (the default).
 extern "C" int e4s_tcr_set_profile(long long* device_counters) {
+#ifdef E4S_TCR_PROFILE
     tcr::g_prof = device_counters;
     return E4S_OK;
+#else
+    return device_counters ? E4S_ERR_ARG : E4S_OK;      // production build carries no counters
+#endif
 }
