@@ -35,8 +35,12 @@ namespace tcr {
 constexpr int TH = 8, TWP = 16, TW = 14;
 constexpr int A_ROWS = 168;
 constexpr int NSTAGE_A = 2;
-constexpr int NUM_THREADS = 448;              // 14 warps: 0 weights, 1 MMA, 2-9 transform, 10-13 epilogue
-constexpr int NUM_THREADS_XS = 480;           // + warp 14: producer of raw activation tiles (XS mode)
+// Warp roles: 0 weights (TMA), 1-3 MMA issue (one per split-precision product), 4-11 transform, 12-15 epilogue,
+// 16 producer of raw activation tiles (XS mode only).
+constexpr int NUM_MMA_WARPS = 3;
+constexpr int W_XFORM0 = 1 + NUM_MMA_WARPS, W_EPI0 = W_XFORM0 + 8, W_XS = W_EPI0 + 4;
+constexpr int NUM_THREADS = 32 * W_XS;        // 512
+constexpr int NUM_THREADS_XS = 32 * (W_XS + 1);
 constexpr int NXS = 3;                        // raw-tile ring depth (XS mode, 32-channel chunks: 20 KB per stage)
 constexpr int XS_STAGE = 160 * 32 * 4;
 constexpr int NUM_XFORM = 256, NUM_EPI = 128;
@@ -148,6 +152,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// zero 32 accumulator columns of this warp's 32 TMEM lanes
+__device__ __forceinline__ void tmem_zero32(uint32_t taddr) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr), "r"(0u)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo_elem, float hi_elem) {
     uint32_t r;
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
@@ -207,24 +219,18 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
     constexpr int A_PLANE = A_ROWS * ROWB;
     constexpr int A_STAGE = 2 * A_PLANE;
     constexpr int B_SLOT = N * ROWB;
-    // N-STACKING: an MMA of M = 128 costs ~130-150 cycles whatever its N (the A operand, 128 rows x 32 B per K step, is read
-    // from shared memory at a fixed rate; measured with the stall counters, tools/opbench.py --prof).  Where two weight
-    // planes fit in one MMA (2N <= 256) the products x_hi*w_hi and x_hi*w_lo are therefore computed by ONE instruction
-    // against B' = [w_hi ; w_lo] (the two ring slots are adjacent in shared memory) into 2N accumulator columns, and
-    // x_lo*w_hi by a second one: 2 instructions per tap and K step instead of 3, the epilogue adds the two column halves.
-    constexpr bool SP = (2 * N <= 256);               // region-pure tiles: all parities, [hi | lo]
-    // mixed tiles: per parity [hi | lo] (slot pair laid out [q][hl][NTC]).  Measured slower for up-sampling layers (the
-    // 4 x 2 x 64-column tile needs both accumulator buffers, so MMA and epilogue stop overlapping): plain convs only.
-    constexpr bool SMX = (2 * NTC <= 256) && NPH == 1;
-    constexpr bool MIX_WIDE = SMX && (2 * N > 256);   // ... which then needs both accumulator buffers (512 columns)
+    // MMA ISSUE: one warp issues a tcgen05.mma every ~120-190 cycles whatever its shape (tools/ubench/umma_bench.cu,
+    // profiles/r1_umma_bench_*.log), while the tensor pipe needs 16 (N = 32) ... 128 (N = 256) cycles for it; several
+    // warps issuing concurrently do overlap.  The three split-precision products x_hi*w_hi, x_lo*w_hi, x_hi*w_lo are
+    // therefore issued by three warps.  MMAs of different warps have no defined order, so none of them may be the
+    // "first" one (accumulate = 0): the epilogue warps zero an accumulator buffer after reading it (tcgen05.st) and
+    // every MMA accumulates.
     constexpr int ACC_COLS = 256;
     constexpr int NACC = 2;
     constexpr int TMEM_COLS = 512;
     constexpr uint32_t IDESC_BASE = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 4) << 24);
     constexpr uint32_t IDESC_N = IDESC_BASE | ((uint32_t)(N >> 3) << 17);         // all parities in one MMA
     constexpr uint32_t IDESC_Q = IDESC_BASE | ((uint32_t)(NTC >> 3) << 17);       // one parity
-    constexpr uint32_t IDESC_2N = IDESC_BASE | ((uint32_t)((SP ? 2 * N : N) >> 3) << 17);
-    constexpr uint32_t IDESC_2Q = IDESC_BASE | ((uint32_t)((SMX ? 2 * NTC : NTC) >> 3) << 17);
     constexpr uint32_t DESC_HI = (uint32_t)((KC == 64 ? 1024u : 512u) >> 4) | (1u << 14) | ((KC == 64 ? 2u : 4u) << 29);
     constexpr int KSTEPS = KC / 16;
     constexpr int MUL = NPH == 4 ? 2 : 1;
@@ -247,8 +253,6 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ho = p.h * MUL, wo = p.w * MUL;
     const int nchunks = p.cin / KC;
-    // resident weights of an up-sampling layer are shared by pure and mixed tiles, whose stacked layouts differ
-    const bool stack_mixed = SMX && !(p.resident && NPH == 4);
 #ifdef E4S_TCR_PROFILE
     const bool prof_on = p.prof != nullptr && blockIdx.x == 0;
     long long pw[4] = {0, 0, 0, 0};                      // [0] role time, [1..3] cycles in its barrier waits
@@ -256,14 +260,17 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
 #endif
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < NSTAGE_A; ++i) mbar_init(smem_u32(&bars[A_FULL + i]), NUM_XFORM), mbar_init(smem_u32(&bars[A_EMPTY + i]), 1);
-        for (int i = 0; i < NACC; ++i) mbar_init(smem_u32(&bars[ACC_FULL + i]), 1), mbar_init(smem_u32(&bars[ACC_EMPTY + i]), NUM_EPI);
-        for (int i = 0; i < p.nslot_b; ++i) mbar_init(smem_u32(&bars[B_FULL + i]), 1), mbar_init(smem_u32(&bars[B_EMPTY + i]), 1);
+        // every MMA warp commits to the barriers of what it read: both operand planes are read by two of them
+        // (x_hi: warps 0 and 2, w_hi: warps 0 and 1) - A stages and accumulators are released by all three, a w_hi slot
+        // (even) by two, a w_lo slot (odd) by one
+        for (int i = 0; i < NSTAGE_A; ++i) mbar_init(smem_u32(&bars[A_FULL + i]), NUM_XFORM), mbar_init(smem_u32(&bars[A_EMPTY + i]), NUM_MMA_WARPS);
+        for (int i = 0; i < NACC; ++i) mbar_init(smem_u32(&bars[ACC_FULL + i]), NUM_MMA_WARPS), mbar_init(smem_u32(&bars[ACC_EMPTY + i]), NUM_EPI);
+        for (int i = 0; i < p.nslot_b; ++i) mbar_init(smem_u32(&bars[B_FULL + i]), 1), mbar_init(smem_u32(&bars[B_EMPTY + i]), (i & 1) ? 1 : 2);
         for (int i = 0; i < NXS; ++i) mbar_init(smem_u32(&bars[XS_FULL + i]), 1), mbar_init(smem_u32(&bars[XS_EMPTY + i]), NUM_XFORM);
         fence_barrier_init();
     }
     if (warp == 0 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&wmap) : "memory");
-    if (XS && warp == 14 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
+    if (XS && warp == W_XS && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -272,6 +279,15 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (warp >= W_EPI0 && warp < W_XS) {                 // every MMA accumulates: both accumulator buffers start at zero
+        const uint32_t lanes = tmem_base + (((uint32_t)(warp & 3) * 32u) << 16);
+#pragma unroll 1
+        for (int c = 0; c < TMEM_COLS; c += 32) tmem_zero32(lanes + (uint32_t)c);
+        tmem_wait_st();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
 
     if (warp == 0) {
         // ===================================================================== weight-plane producer (TMA): one pass per tile
@@ -282,36 +298,24 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
         for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
             if (p.resident && loaded_resident) break;
             const Item item = decode_item(p, it);
-            bool by_parity = false;                      // slot pair laid out [q][hl][NTC] (mixed tile, stacked MMAs)
-            if (NPH == 4 && stack_mixed) {
-                const uint32_t classes = tile_class_mask<NPH>(p, item, lane);
-                by_parity = (classes & (classes - 1)) != 0;
-            }
             if (lane == 0) {
                 for (int kc = 0; kc < nchunks; ++kc)
                     for (int tap = 0; tap < 9; ++tap)
                         for (int hl = 0; hl < 2; ++hl) {
-                            if (!p.resident) {
-                                MBAR_WAIT_P(smem_u32(&bars[B_EMPTY + slot]), ph ^ 1, 1);
-                                // the [q][hl] layout puts hi rows into both slots of the pair: both must be free
-                                if (by_parity && hl == 0) MBAR_WAIT_P(smem_u32(&bars[B_EMPTY + slot + 1]), ph ^ 1, 1);
-                            }
+                            if (!p.resident) MBAR_WAIT_P(smem_u32(&bars[B_EMPTY + slot]), ph ^ 1, 1);
                             const uint32_t full = smem_u32(&bars[B_FULL + slot]);
                             mbar_expect_tx(full, B_SLOT);
-                            const uint32_t pair = smem_u32(b_buf + (size_t)(slot & ~1) * B_SLOT);
+                            const uint32_t dst = smem_u32(b_buf + (size_t)slot * B_SLOT);
 #pragma unroll
-                            for (int q = 0; q < NPH; ++q) {
-                                const uint32_t dst = by_parity ? pair + (uint32_t)((q * 2 + hl) * NTC * ROWB)
-                                                               : pair + (uint32_t)(hl * B_SLOT + q * NTC * ROWB);
-                                tma_load_2d(dst, &wmap, kc * KC, hl * rows_lo + (q * 9 + tap) * p.cout + item.nt * NTC, full);
-                            }
+                            for (int q = 0; q < NPH; ++q)
+                                tma_load_2d(dst + q * NTC * ROWB, &wmap, kc * KC, hl * rows_lo + (q * 9 + tap) * p.cout + item.nt * NTC, full);
                             if (++slot == p.nslot_b) slot = 0, ph ^= 1;
                         }
             }
             loaded_resident = true;
             __syncwarp();
         }
-    } else if (warp == 14) {
+    } else if (warp == W_XS) {
         // ===================================================================== raw activation tile producer (XS mode)
         if (XS && lane == 0) {
             int st = 0;
@@ -328,90 +332,52 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
             }
         }
         __syncwarp();
-    } else if (warp == 1) {
-        // ===================================================================== MMA issuer
-        // The whole warp walks the loops with warp-uniform state (barrier waits included); only the tcgen05 instructions
-        // themselves are predicated on one lane.  With the loops inside `if (lane == 0)` the compiler treats descriptors
-        // as per-thread values and spends ~30 SASS instructions (R2UR.BROADCAST, BSSY/BSYNC, ...) per MMA - measured as
-        // the bottleneck of the small-N layers (source-level ncu samples, profiles/).
+    } else if (warp <= NUM_MMA_WARPS) {
+        // ===================================================================== MMA issuers (one split-precision product each)
+        // role 0: x_hi * w_hi, role 1: x_lo * w_hi, role 2: x_hi * w_lo.  Each warp walks the loops with warp-uniform state
+        // (barrier waits included); only the tcgen05 instructions are predicated on one lane, descriptors live in uniform
+        // registers (shfl-from-lane-0 marks a value as warp-uniform for the compiler).
+        const int role = warp - 1;
+        const bool lo_w = role == 2;                     // this warp reads the w_lo slot of every (hi, lo) pair
         int sa = 0, slot = 0, acc = 0;
         uint32_t pa = 0, pb = 0, pacc0 = 0, pacc1 = 0;
         bool b_ready = false;                            // resident weights: waited for once
         const bool leader = lane == 0;
-        // shfl-from-lane-0 marks values as warp-uniform for the compiler (uniform registers feed UTCHMMA directly)
         const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
         const uint32_t bars0 = smem_u32(bars);
-        const uint32_t a0 = smem_u32(a_buf), b0 = smem_u32(b_buf);
+        const uint32_t a0 = smem_u32(a_buf) + (role == 1 ? A_PLANE : 0), b0 = smem_u32(b_buf);
         auto desc = [](uint32_t lo) -> uint64_t { return ((uint64_t)DESC_HI << 32) | lo; };
         auto lo_of = [](uint32_t addr) -> uint32_t { return (addr >> 4) | 0x10000u; };
         for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
             const Item item = decode_item(p, it);
             const uint32_t classes = __shfl_sync(0xffffffffu, tile_class_mask<NPH>(p, item, lane), 0);
             const bool mixed = (classes & (classes - 1)) != 0;
-            const bool wide = MIX_WIDE && mixed && stack_mixed;      // a stacked mixed tile of 4 x 64 columns: both buffers
             MBAR_WAIT_P(bars0 + 8 * (ACC_EMPTY + acc), (acc ? pacc1 : pacc0) ^ 1, 1);
-            if (wide) MBAR_WAIT_P(bars0 + 8 * (ACC_EMPTY + (acc ^ 1)), (acc ? pacc0 : pacc1) ^ 1, 1);
             tc_fence_after();
-            const uint32_t d_tmem = wide ? tmem_u : tmem_u + (uint32_t)(acc * ACC_COLS);
+            const uint32_t d_tmem = tmem_u + (uint32_t)(acc * ACC_COLS);
             if (p.resident) slot = 0;
             const bool wait_b = !p.resident || !b_ready;
             if (!mixed) {
                 // ---------------- region-pure tile: operand staged once per chunk, taps are row shifts
-                uint32_t accum = 0;
 #pragma unroll 1
                 for (int kc = 0; kc < nchunks; ++kc) {
                     MBAR_WAIT_P(bars0 + 8 * (A_FULL + sa), pa, 2);
                     tc_fence_after();
-                    const uint32_t ah = lo_of(a0 + sa * A_STAGE), al = ah + (A_PLANE >> 4);
+                    const uint32_t ap = lo_of(a0 + sa * A_STAGE);
                     uint32_t roff = (uint32_t)ROWB >> 4;                   // tap (0,0): row shift 1
 #pragma unroll 1
                     for (int tap = 0; tap < 9; ++tap) {
-                        if (SP) {
-                            // slots (slot, slot + 1) = [w_hi ; w_lo], adjacent: x_hi * [hi|lo] -> 2N columns, x_lo * hi -> first N
-                            if (wait_b) {
-                                MBAR_WAIT_P(bars0 + 8 * (B_FULL + slot), pb, 3);
-                                MBAR_WAIT_P(bars0 + 8 * (B_FULL + slot + 1), pb, 3);
-                            }
-                            tc_fence_after();
-                            const uint32_t bp = lo_of(b0 + slot * B_SLOT);
-                            if (leader) {
+                        const int sl = slot + (lo_w ? 1 : 0);              // pairs never straddle the ring wrap (even slot count)
+                        if (wait_b) MBAR_WAIT_P(bars0 + 8 * (B_FULL + sl), pb, 3);
+                        tc_fence_after();
+                        const uint32_t bp = lo_of(b0 + sl * B_SLOT);
+                        if (leader) {
 #pragma unroll
-                                for (int k = 0; k < KSTEPS; ++k) {
-                                    umma_bf16(d_tmem, desc(ah + roff + 2 * k), desc(bp + 2 * k), IDESC_2N, k == 0 ? accum : 1u);
-                                    umma_bf16(d_tmem, desc(al + roff + 2 * k), desc(bp + 2 * k), IDESC_N, 1u);
-                                }
-                                if (!p.resident) {
-                                    umma_commit(bars0 + 8 * (B_EMPTY + slot));
-                                    umma_commit(bars0 + 8 * (B_EMPTY + slot + 1));
-                                }
-                            }
-                            accum = 1u;
-                            slot += 2;
-                            if (slot >= p.nslot_b) slot = 0, pb ^= 1;
-                        } else {
-                            if (wait_b) MBAR_WAIT_P(bars0 + 8 * (B_FULL + slot), pb, 3);
-                            tc_fence_after();
-                            uint32_t bl = lo_of(b0 + slot * B_SLOT);
-                            if (leader) {
-#pragma unroll
-                                for (int k = 0; k < KSTEPS; ++k) {
-                                    umma_bf16(d_tmem, desc(ah + roff + 2 * k), desc(bl + 2 * k), IDESC_N, k == 0 ? accum : 1u);
-                                    umma_bf16(d_tmem, desc(al + roff + 2 * k), desc(bl + 2 * k), IDESC_N, 1u);
-                                }
-                                if (!p.resident) umma_commit(bars0 + 8 * (B_EMPTY + slot));
-                            }
-                            accum = 1u;
-                            if (++slot == p.nslot_b) slot = 0, pb ^= 1;
-                            if (wait_b) MBAR_WAIT_P(bars0 + 8 * (B_FULL + slot), pb, 3);
-                            tc_fence_after();
-                            bl = lo_of(b0 + slot * B_SLOT);
-                            if (leader) {
-#pragma unroll
-                                for (int k = 0; k < KSTEPS; ++k) umma_bf16(d_tmem, desc(ah + roff + 2 * k), desc(bl + 2 * k), IDESC_N, 1u);
-                                if (!p.resident) umma_commit(bars0 + 8 * (B_EMPTY + slot));
-                            }
-                            if (++slot == p.nslot_b) slot = 0, pb ^= 1;
+                            for (int k = 0; k < KSTEPS; ++k) umma_bf16(d_tmem, desc(ap + roff + 2 * k), desc(bp + 2 * k), IDESC_N, 1u);
+                            if (!p.resident) umma_commit(bars0 + 8 * (B_EMPTY + sl));
                         }
+                        slot += 2;
+                        if (slot >= p.nslot_b) slot = 0, pb ^= 1;
                         // next tap: +1 row, or to the start of the next halo row (+16 - 2) after dx = 2
                         roff += (uint32_t)(((tap % 3) == 2 ? (TWP - 2) : 1) * ROWB) >> 4;
                     }
@@ -419,75 +385,42 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                     if (++sa == NSTAGE_A) sa = 0, pa ^= 1;
                 }
             } else {
-                // ---------------- mixed tile: one operand slot per (tap, parity), MMAs of N = NTC (2 NTC when stacked)
-                uint32_t inited = 0;                     // bit parity: that column range already holds a sum
+                // ---------------- mixed tile: one operand stage per (tap, parity), MMAs of N = NTC
                 for (int kc = 0; kc < nchunks; ++kc) {
 #pragma unroll 1
                     for (int tap = 0; tap < 9; ++tap) {
-                        int slot_lo = slot + 1;
-                        uint32_t pb_lo = pb;
-                        if (slot_lo == p.nslot_b) slot_lo = 0, pb_lo ^= 1;
-                        if (wait_b) {
-                            MBAR_WAIT_P(bars0 + 8 * (B_FULL + slot), pb, 3);
-                            MBAR_WAIT_P(bars0 + 8 * (B_FULL + slot_lo), pb_lo, 3);
-                        }
-                        const uint32_t bh = lo_of(b0 + slot * B_SLOT), bl = lo_of(b0 + slot_lo * B_SLOT);
+                        const int sl = slot + (lo_w ? 1 : 0);
+                        if (wait_b) MBAR_WAIT_P(bars0 + 8 * (B_FULL + sl), pb, 3);
+                        const uint32_t bp = lo_of(b0 + sl * B_SLOT);
 #pragma unroll
                         for (int q = 0; q < NPH; ++q) {
                             MBAR_WAIT_P(bars0 + 8 * (A_FULL + sa), pa, 2);
                             tc_fence_after();
-                            const uint32_t ah = lo_of(a0 + sa * A_STAGE), al = ah + (A_PLANE >> 4);
-                            const uint32_t bit = 1u << q;
-                            if (stack_mixed) {
-                                // slot pair = [q][hi | lo][NTC] rows: x_hi * [hi|lo](q) -> 2 NTC columns, x_lo * hi(q) -> first NTC
-                                const uint32_t bq = bh + ((uint32_t)(q * 2 * NTC * ROWB) >> 4);
-                                const uint32_t dq = d_tmem + (uint32_t)(q * 2 * NTC);
-                                if (leader) {
+                            const uint32_t ap = lo_of(a0 + sa * A_STAGE);
+                            const uint32_t boff = (uint32_t)(q * NTC * ROWB) >> 4;
+                            const uint32_t dq = d_tmem + (uint32_t)(q * NTC);
+                            if (leader) {
 #pragma unroll
-                                    for (int k = 0; k < KSTEPS; ++k) {
-                                        umma_bf16(dq, desc(ah + 2 * k), desc(bq + 2 * k), IDESC_2Q, (k == 0 && !(inited & bit)) ? 0u : 1u);
-                                        umma_bf16(dq, desc(al + 2 * k), desc(bq + 2 * k), IDESC_Q, 1u);
-                                    }
-                                }
-                            } else {
-                                const uint32_t boff = (uint32_t)(q * NTC * ROWB) >> 4;
-                                const uint32_t dq = d_tmem + (uint32_t)(q * NTC);
-                                if (leader) {
-#pragma unroll
-                                    for (int k = 0; k < KSTEPS; ++k) {
-                                        umma_bf16(dq, desc(ah + 2 * k), desc(bh + boff + 2 * k), IDESC_Q, (k == 0 && !(inited & bit)) ? 0u : 1u);
-                                        umma_bf16(dq, desc(al + 2 * k), desc(bh + boff + 2 * k), IDESC_Q, 1u);
-                                        umma_bf16(dq, desc(ah + 2 * k), desc(bl + boff + 2 * k), IDESC_Q, 1u);
-                                    }
-                                }
+                                for (int k = 0; k < KSTEPS; ++k) umma_bf16(dq, desc(ap + 2 * k), desc(bp + boff + 2 * k), IDESC_Q, 1u);
+                                umma_commit(bars0 + 8 * (A_EMPTY + sa));
                             }
-                            inited |= bit;
-                            if (leader) umma_commit(bars0 + 8 * (A_EMPTY + sa));
                             if (++sa == NSTAGE_A) sa = 0, pa ^= 1;
                         }
-                        if (!p.resident && leader) {
-                            umma_commit(bars0 + 8 * (B_EMPTY + slot));
-                            umma_commit(bars0 + 8 * (B_EMPTY + slot_lo));
-                        }
-                        slot = slot_lo, pb = pb_lo;
-                        if (++slot == p.nslot_b) slot = 0, pb ^= 1;
+                        if (!p.resident && leader) umma_commit(bars0 + 8 * (B_EMPTY + sl));
+                        slot += 2;
+                        if (slot >= p.nslot_b) slot = 0, pb ^= 1;
                     }
                 }
             }
             if (leader) umma_commit(bars0 + 8 * (ACC_FULL + acc));
             if (acc) pacc1 ^= 1; else pacc0 ^= 1;
             acc ^= 1;
-            if (wide) {                                  // the tile used both buffers: hand both over, buffer order unchanged
-                if (leader) umma_commit(bars0 + 8 * (ACC_FULL + acc));
-                if (acc) pacc1 ^= 1; else pacc0 ^= 1;
-                acc ^= 1;
-            }
             b_ready = true;
             __syncwarp();
         }
-    } else if (warp < 10) {
+    } else if (warp < W_EPI0) {
         // ===================================================================== activation transform (A producers), 256 threads
-        const int t = threadIdx.x - 64;                  // 0..255
+        const int t = threadIdx.x - 32 * W_XFORM0;       // 0..255
         const int c8 = t % CPR;
         const int pix0 = t / CPR;                        // 0..PPS-1
         constexpr int NSW_SHIFT = (160 + PPS - 1) / PPS; // sweeps over the 160 halo pixels (5 or 3)
@@ -658,7 +591,7 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                 }
             }
         }
-    } else if (warp < 14) {
+    } else if (warp < W_XS) {
         // ===================================================================== epilogue: one pass per tile, region per (pixel, parity)
         const uint32_t quarter = (uint32_t)(warp & 3);
         const int m_row = quarter * 32 + lane;
@@ -672,9 +605,6 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
             const bool strided = (NPH == 1 && p.out_stride == 2);
             const bool mine = tx < TW && iy < p.h && ix < p.w && (!strided || ((iy | ix) & 1) == 0);
             const int n0 = item.nt * NTC;
-            const uint32_t classes = tile_class_mask<NPH>(p, item, lane);
-            const bool mixed = (classes & (classes - 1)) != 0;
-            const bool wide = MIX_WIDE && mixed && stack_mixed;
             const int oh = strided ? (p.h >> 1) : ho, ow = strided ? (p.w >> 1) : wo;
             // everything that does not depend on the accumulator is fetched while the MMAs of this tile still run
             int cls[NPH];
@@ -688,15 +618,8 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
             }
             MBAR_WAIT_P(smem_u32(&bars[ACC_FULL + acc]), pacc[acc], 1);
             pacc[acc] ^= 1;
-            if (wide) {
-                MBAR_WAIT_P(smem_u32(&bars[ACC_FULL + (acc ^ 1)]), pacc[acc ^ 1], 1);
-                pacc[acc ^ 1] ^= 1;
-            }
             tc_fence_after();
-            // accumulator columns of (parity q, channel c): stacked tiles keep the x_hi * w_lo products lo_off columns further
-            const uint32_t cbase = wide ? 0u : (uint32_t)(acc * ACC_COLS);
-            const int qstride = (mixed && stack_mixed) ? 2 * NTC : NTC;
-            const int lo_off = mixed ? (stack_mixed ? NTC : 0) : (SP ? N : 0);
+            const uint32_t cbase = (uint32_t)(acc * ACC_COLS);
 #pragma unroll
             for (int q = 0; q < NPH; ++q) {
                 const int oy = strided ? (iy >> 1) : iy * MUL + (q >> 1), ox = strided ? (ix >> 1) : ix * MUL + (q & 1);
@@ -705,14 +628,9 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
 #pragma unroll 1
                 for (int j = 0; j < NTC / 32; ++j) {
                     uint32_t r[32];
-                    const uint32_t col = tmem_base + ((quarter * 32u) << 16) + cbase + (uint32_t)(q * qstride + j * 32);
+                    const uint32_t col = tmem_base + ((quarter * 32u) << 16) + cbase + (uint32_t)(q * NTC + j * 32);
                     tmem_ld32(col, r);
-                    if (lo_off) {
-                        uint32_t r2[32];
-                        tmem_ld32(col + (uint32_t)lo_off, r2);
-#pragma unroll
-                        for (int e = 0; e < 32; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) + __uint_as_float(r2[e]));
-                    }
+                    tmem_zero32(col);                    // the next tile's MMAs only accumulate
                     if (mine) {
 #pragma unroll
                         for (int g = 0; g < 8; ++g) {
@@ -738,20 +656,17 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                     }
                 }
             }
+            tmem_wait_st();
             tc_fence_before();
             mbar_arrive(smem_u32(&bars[ACC_EMPTY + acc]));
             acc ^= 1;
-            if (wide) {
-                mbar_arrive(smem_u32(&bars[ACC_EMPTY + acc]));
-                acc ^= 1;
-            }
         }
     }
 
 #ifdef E4S_TCR_PROFILE
     if (prof_on) {
         int role = -1;
-        if (lane == 0) role = warp == 0 ? 0 : warp == 1 ? 1 : warp == 2 ? 2 : warp == 10 ? 3 : warp == 14 ? 4 : -1;
+        if (lane == 0) role = warp == 0 ? 0 : warp == 1 ? 1 : warp == W_XFORM0 ? 2 : warp == W_EPI0 ? 3 : warp == W_XS ? 4 : -1;
         if (role >= 0) {
             pw[0] = clock64() - t_start;
 #pragma unroll
