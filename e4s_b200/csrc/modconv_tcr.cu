@@ -35,12 +35,12 @@ namespace tcr {
 constexpr int TH = 8, TWP = 16, TW = 14;
 constexpr int A_ROWS = 168;
 constexpr int NSTAGE_A = 2;
-// Warp roles: 0 weights (TMA), 1-3 MMA issue (one per split-precision product), 4-11 transform, 12-15 epilogue,
-// 16 producer of raw activation tiles (XS mode only).
+// Warp roles: 0 TMA producer (weights; raw activation tiles in XS mode), 1-3 MMA issue (one per split-precision
+// product), 4-11 transform, 12-15 epilogue.  512 threads: 128 registers each.
 constexpr int NUM_MMA_WARPS = 3;
 constexpr int W_XFORM0 = 1 + NUM_MMA_WARPS, W_EPI0 = W_XFORM0 + 8, W_XS = W_EPI0 + 4;
 constexpr int NUM_THREADS = 32 * W_XS;        // 512
-constexpr int NUM_THREADS_XS = 32 * (W_XS + 1);
+constexpr int NUM_THREADS_XS = NUM_THREADS;  // XS mode: the raw-tile producer is the weights thread
 constexpr int NXS = 3;                        // raw-tile ring depth (XS mode, 32-channel chunks: 20 KB per stage)
 constexpr int XS_STAGE = 160 * 32 * 4;
 constexpr int NUM_XFORM = 256, NUM_EPI = 128;
@@ -226,6 +226,8 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
     // "first" one (accumulate = 0): the epilogue warps zero an accumulator buffer after reading it (tcgen05.st) and
     // every MMA accumulates.
     constexpr int ACC_COLS = 256;
+    // Two-region tiles of an up-sampling layer (most mixed tiles of a face mask): see the transform role.
+    constexpr bool TWO_CLASS = (NPH == 4) && (NSTAGE_A == 2);
     constexpr int NACC = 2;
     constexpr int TMEM_COLS = 512;
     constexpr uint32_t IDESC_BASE = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 4) << 24);
@@ -261,16 +263,16 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
 
     if (threadIdx.x == 0) {
         // every MMA warp commits to the barriers of what it read: both operand planes are read by two of them
-        // (x_hi: warps 0 and 2, w_hi: warps 0 and 1) - A stages and accumulators are released by all three, a w_hi slot
-        // (even) by two, a w_lo slot (odd) by one
+        // (x_hi: warps 0 and 2, w_hi: warps 0 and 1) - A stages, accumulators and (hi, lo) weight slot PAIRS (the ring unit:
+        // one TMA box, the barriers of the even slot) are released by all three
         for (int i = 0; i < NSTAGE_A; ++i) mbar_init(smem_u32(&bars[A_FULL + i]), NUM_XFORM), mbar_init(smem_u32(&bars[A_EMPTY + i]), NUM_MMA_WARPS);
         for (int i = 0; i < NACC; ++i) mbar_init(smem_u32(&bars[ACC_FULL + i]), NUM_MMA_WARPS), mbar_init(smem_u32(&bars[ACC_EMPTY + i]), NUM_EPI);
-        for (int i = 0; i < p.nslot_b; ++i) mbar_init(smem_u32(&bars[B_FULL + i]), 1), mbar_init(smem_u32(&bars[B_EMPTY + i]), (i & 1) ? 1 : 2);
+        for (int i = 0; i < p.nslot_b; ++i) mbar_init(smem_u32(&bars[B_FULL + i]), 1), mbar_init(smem_u32(&bars[B_EMPTY + i]), NUM_MMA_WARPS);
         for (int i = 0; i < NXS; ++i) mbar_init(smem_u32(&bars[XS_FULL + i]), 1), mbar_init(smem_u32(&bars[XS_EMPTY + i]), NUM_XFORM);
         fence_barrier_init();
     }
     if (warp == 0 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&wmap) : "memory");
-    if (XS && warp == W_XS && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
+    if (XS && warp == 0 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -290,45 +292,39 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
     tc_fence_after();
 
     if (warp == 0) {
-        // ===================================================================== weight-plane producer (TMA): one pass per tile
-        int slot = 0;
-        uint32_t ph = 0;
-        const int rows_lo = (NPH * 9) * p.cout;
+        // ===================================================================== TMA producer: weight planes (one pass per tile, or
+        // once when resident) and, in XS mode, the raw activation tile of every chunk.  One thread issues both in consumption
+        // order: x(chunk) precedes the weight taps of that chunk, so a full weight ring never holds back an activation tile
+        // the MMA warps are (indirectly) waiting for.
+        int slot = 0, st = 0;
+        uint32_t ph = 0, phx = 0;
         bool loaded_resident = false;
-        for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
-            if (p.resident && loaded_resident) break;
-            const Item item = decode_item(p, it);
-            if (lane == 0) {
-                for (int kc = 0; kc < nchunks; ++kc)
-                    for (int tap = 0; tap < 9; ++tap)
-                        for (int hl = 0; hl < 2; ++hl) {
-                            if (!p.resident) MBAR_WAIT_P(smem_u32(&bars[B_EMPTY + slot]), ph ^ 1, 1);
-                            const uint32_t full = smem_u32(&bars[B_FULL + slot]);
-                            mbar_expect_tx(full, B_SLOT);
-                            const uint32_t dst = smem_u32(b_buf + (size_t)slot * B_SLOT);
-#pragma unroll
-                            for (int q = 0; q < NPH; ++q)
-                                tma_load_2d(dst + q * NTC * ROWB, &wmap, kc * KC, hl * rows_lo + (q * 9 + tap) * p.cout + item.nt * NTC, full);
-                            if (++slot == p.nslot_b) slot = 0, ph ^= 1;
-                        }
-            }
-            loaded_resident = true;
-            __syncwarp();
-        }
-    } else if (warp == W_XS) {
-        // ===================================================================== raw activation tile producer (XS mode)
-        if (XS && lane == 0) {
-            int st = 0;
-            uint32_t ph = 0;
+        if (lane == 0) {
             for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
+                const bool load_w = !(p.resident && loaded_resident);
+                if (!XS && !load_w) break;
                 const Item item = decode_item(p, it);
                 for (int kc = 0; kc < nchunks; ++kc) {
-                    MBAR_WAIT_P(smem_u32(&bars[XS_EMPTY + st]), ph ^ 1, 1);
-                    const uint32_t full = smem_u32(&bars[XS_FULL + st]);
-                    mbar_expect_tx(full, XS_STAGE);
-                    tma_load_4d(smem_u32(xs_buf + st * XS_STAGE), &xmap, kc * KC, item.tx * TW - 1, item.ty * TH - 1, item.b, full);
-                    if (++st == NXS) st = 0, ph ^= 1;
+                    if (XS) {
+                        MBAR_WAIT_P(smem_u32(&bars[XS_EMPTY + st]), phx ^ 1, 2);
+                        const uint32_t full = smem_u32(&bars[XS_FULL + st]);
+                        mbar_expect_tx(full, XS_STAGE);
+                        tma_load_4d(smem_u32(xs_buf + st * XS_STAGE), &xmap, kc * KC, item.tx * TW - 1, item.ty * TH - 1, item.b, full);
+                        if (++st == NXS) st = 0, phx ^= 1;
+                    }
+                    if (load_w) {
+                        // one 4-D box per tap: [hi | lo] x parities x NTC rows x KC channels = the (hi, lo) slot pair, contiguous
+                        for (int tap = 0; tap < 9; ++tap) {
+                            if (!p.resident) MBAR_WAIT_P(smem_u32(&bars[B_EMPTY + slot]), ph ^ 1, 1);
+                            const uint32_t full = smem_u32(&bars[B_FULL + slot]);
+                            mbar_expect_tx(full, 2 * B_SLOT);
+                            tma_load_4d(smem_u32(b_buf + (size_t)slot * B_SLOT), &wmap, kc * KC, item.nt * NTC, tap, 0, full);
+                            slot += 2;
+                            if (slot >= p.nslot_b) slot = 0, ph ^= 1;
+                        }
+                    }
                 }
+                loaded_resident = true;
             }
         }
         __syncwarp();
@@ -352,12 +348,49 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
             const Item item = decode_item(p, it);
             const uint32_t classes = __shfl_sync(0xffffffffu, tile_class_mask<NPH>(p, item, lane), 0);
             const bool mixed = (classes & (classes - 1)) != 0;
+            const bool two = TWO_CLASS && __popc(classes) == 2;      // two regions: one accumulator buffer per region
             MBAR_WAIT_P(bars0 + 8 * (ACC_EMPTY + acc), (acc ? pacc1 : pacc0) ^ 1, 1);
+            if (two) MBAR_WAIT_P(bars0 + 8 * (ACC_EMPTY + (acc ^ 1)), (acc ? pacc0 : pacc1) ^ 1, 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_u + (uint32_t)(acc * ACC_COLS);
             if (p.resident) slot = 0;
             const bool wait_b = !p.resident || !b_ready;
-            if (!mixed) {
+            if (two) {
+                // ---------------- two-region tile: per chunk the two stages hold x * s_A and x * s_B; taps are row shifts
+                const uint32_t d_other = tmem_u + (uint32_t)((acc ^ 1) * ACC_COLS);
+#pragma unroll 1
+                for (int kc = 0; kc < nchunks; ++kc) {
+                    const int sb = sa ^ 1;
+                    MBAR_WAIT_P(bars0 + 8 * (A_FULL + sa), pa, 2);
+                    MBAR_WAIT_P(bars0 + 8 * (A_FULL + sb), sa == NSTAGE_A - 1 ? pa ^ 1 : pa, 2);
+                    tc_fence_after();
+                    const uint32_t apA = lo_of(a0 + sa * A_STAGE), apB = lo_of(a0 + sb * A_STAGE);
+                    uint32_t roff = (uint32_t)ROWB >> 4;
+#pragma unroll 1
+                    for (int tap = 0; tap < 9; ++tap) {
+                        if (wait_b) {
+                            MBAR_WAIT_P(bars0 + 8 * (B_FULL + slot), pb, 3);
+                            tc_fence_after();
+                        }
+                        const uint32_t bp = lo_of(b0 + (slot + (lo_w ? 1 : 0)) * B_SLOT);
+                        if (leader) {
+#pragma unroll
+                            for (int k = 0; k < KSTEPS; ++k) umma_bf16(d_tmem, desc(apA + roff + 2 * k), desc(bp + 2 * k), IDESC_N, 1u);
+#pragma unroll
+                            for (int k = 0; k < KSTEPS; ++k) umma_bf16(d_other, desc(apB + roff + 2 * k), desc(bp + 2 * k), IDESC_N, 1u);
+                            if (!p.resident) umma_commit(bars0 + 8 * (B_EMPTY + slot));
+                        }
+                        slot += 2;
+                        if (slot >= p.nslot_b) slot = 0, pb ^= 1;
+                        roff += (uint32_t)(((tap % 3) == 2 ? (TWP - 2) : 1) * ROWB) >> 4;
+                    }
+                    if (leader) {
+                        umma_commit(bars0 + 8 * (A_EMPTY + sa));
+                        umma_commit(bars0 + 8 * (A_EMPTY + sb));
+                    }
+                    pa ^= 1;                             // both stages consumed: same stage index, next phase
+                }
+            } else if (!mixed) {
                 // ---------------- region-pure tile: operand staged once per chunk, taps are row shifts
 #pragma unroll 1
                 for (int kc = 0; kc < nchunks; ++kc) {
@@ -367,14 +400,15 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                     uint32_t roff = (uint32_t)ROWB >> 4;                   // tap (0,0): row shift 1
 #pragma unroll 1
                     for (int tap = 0; tap < 9; ++tap) {
-                        const int sl = slot + (lo_w ? 1 : 0);              // pairs never straddle the ring wrap (even slot count)
-                        if (wait_b) MBAR_WAIT_P(bars0 + 8 * (B_FULL + sl), pb, 3);
-                        tc_fence_after();
-                        const uint32_t bp = lo_of(b0 + sl * B_SLOT);
+                        if (wait_b) {
+                            MBAR_WAIT_P(bars0 + 8 * (B_FULL + slot), pb, 3);
+                            tc_fence_after();
+                        }
+                        const uint32_t bp = lo_of(b0 + (slot + (lo_w ? 1 : 0)) * B_SLOT);
                         if (leader) {
 #pragma unroll
                             for (int k = 0; k < KSTEPS; ++k) umma_bf16(d_tmem, desc(ap + roff + 2 * k), desc(bp + 2 * k), IDESC_N, 1u);
-                            if (!p.resident) umma_commit(bars0 + 8 * (B_EMPTY + sl));
+                            if (!p.resident) umma_commit(bars0 + 8 * (B_EMPTY + slot));
                         }
                         slot += 2;
                         if (slot >= p.nslot_b) slot = 0, pb ^= 1;
@@ -389,9 +423,8 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                 for (int kc = 0; kc < nchunks; ++kc) {
 #pragma unroll 1
                     for (int tap = 0; tap < 9; ++tap) {
-                        const int sl = slot + (lo_w ? 1 : 0);
-                        if (wait_b) MBAR_WAIT_P(bars0 + 8 * (B_FULL + sl), pb, 3);
-                        const uint32_t bp = lo_of(b0 + sl * B_SLOT);
+                        if (wait_b) MBAR_WAIT_P(bars0 + 8 * (B_FULL + slot), pb, 3);
+                        const uint32_t bp = lo_of(b0 + (slot + (lo_w ? 1 : 0)) * B_SLOT);
 #pragma unroll
                         for (int q = 0; q < NPH; ++q) {
                             MBAR_WAIT_P(bars0 + 8 * (A_FULL + sa), pa, 2);
@@ -406,7 +439,7 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                             }
                             if (++sa == NSTAGE_A) sa = 0, pa ^= 1;
                         }
-                        if (!p.resident && leader) umma_commit(bars0 + 8 * (B_EMPTY + sl));
+                        if (!p.resident && leader) umma_commit(bars0 + 8 * (B_EMPTY + slot));
                         slot += 2;
                         if (slot >= p.nslot_b) slot = 0, pb ^= 1;
                     }
@@ -415,6 +448,11 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
             if (leader) umma_commit(bars0 + 8 * (ACC_FULL + acc));
             if (acc) pacc1 ^= 1; else pacc0 ^= 1;
             acc ^= 1;
+            if (two) {                                   // the tile used both buffers: hand both over, buffer order unchanged
+                if (leader) umma_commit(bars0 + 8 * (ACC_FULL + acc));
+                if (acc) pacc1 ^= 1; else pacc0 ^= 1;
+                acc ^= 1;
+            }
             b_ready = true;
             __syncwarp();
         }
@@ -434,17 +472,15 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
             const bool mixed = (classes & (classes - 1)) != 0;
             const float* xb = p.x + (int64_t)item.b * p.h * p.w * p.cin;
             const int y0 = item.ty * TH, x0 = item.tx * TW;
-            if (!mixed) {
-                const int cls = __ffs(classes) - 1;
-                const float* sc = p.s ? p.s + ((int64_t)item.b * p.ncls + cls) * p.cin : nullptr;
-                const float* sh = p.shift ? p.shift + ((int64_t)item.b * p.ncls + cls) * p.cin : nullptr;
+            const int nclass = TWO_CLASS && __popc(classes) == 2 ? 2 : 1;      // operand stages per chunk (uniform-style staging)
+            if (!mixed || nclass == 2) {
+                // region-pure tile: one stage per chunk scaled by the region's style.  Two-region tile of an up-sampling
+                // layer: TWO such stages per chunk (one per region, same loaded activations); the MMA warps accumulate
+                // them into the two accumulator buffers and the epilogue picks per (pixel, parity).
+                const int cls2[2] = {__ffs(classes) - 1, 31 - __clz(classes)};
                 for (int kc = 0; kc < nchunks; ++kc) {
                     const int ch = kc * KC + 8 * c8;
                     const float4 one4 = make_float4(1.f, 1.f, 1.f, 1.f), zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    const float4 s0 = sc ? __ldg(reinterpret_cast<const float4*>(sc + ch)) : one4;
-                    const float4 s1 = sc ? __ldg(reinterpret_cast<const float4*>(sc + ch + 4)) : one4;
-                    const float4 t0 = sh ? __ldg(reinterpret_cast<const float4*>(sh + ch)) : zero4;
-                    const float4 t1 = sh ? __ldg(reinterpret_cast<const float4*>(sh + ch + 4)) : zero4;
                     float4 v0[NSW_SHIFT], v1[NSW_SHIFT];
                     bool inb[NSW_SHIFT];
                     if (XS) MBAR_WAIT_P(smem_u32(&bars[XS_FULL + xstage]), px, 1);
@@ -466,6 +502,14 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                             v1[i] = __ldg(reinterpret_cast<const float4*>(src + 4));
                         }
                     }
+#pragma unroll 1
+                    for (int ci = 0; ci < nclass; ++ci) {
+                    const float* sc = p.s ? p.s + ((int64_t)item.b * p.ncls + cls2[ci]) * p.cin : nullptr;
+                    const float* sh = p.shift ? p.shift + ((int64_t)item.b * p.ncls + cls2[ci]) * p.cin : nullptr;
+                    const float4 s0 = sc ? __ldg(reinterpret_cast<const float4*>(sc + ch)) : one4;
+                    const float4 s1 = sc ? __ldg(reinterpret_cast<const float4*>(sc + ch + 4)) : one4;
+                    const float4 t0 = sh ? __ldg(reinterpret_cast<const float4*>(sh + ch)) : zero4;
+                    const float4 t1 = sh ? __ldg(reinterpret_cast<const float4*>(sh + ch + 4)) : zero4;
                     MBAR_WAIT_P(smem_u32(&bars[A_EMPTY + sa]), pa ^ 1, 2);
                     uint8_t* hi_plane = a_buf + sa * A_STAGE;
                     uint8_t* lo_plane = hi_plane + A_PLANE;
@@ -495,6 +539,7 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                     fence_proxy_async();
                     mbar_arrive(smem_u32(&bars[A_FULL + sa]));
                     if (++sa == NSTAGE_A) sa = 0, pa ^= 1;
+                    }
                     if (XS) {
                         // Release the raw tile only AFTER the stores that consume the loaded values: an arrive issued right
                         // behind the loads does not wait for them (no register dependence), and a load still in flight when
@@ -599,27 +644,51 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
         int acc = 0;
         uint32_t pacc[2] = {0, 0};
         const float nw = (p.noise && p.noise_w) ? __ldg(p.noise_w) : 0.f;
-        for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
-            const Item item = decode_item(p, it);
-            const int iy = item.ty * TH + ty, ix = item.tx * TW + tx;
-            const bool strided = (NPH == 1 && p.out_stride == 2);
-            const bool mine = tx < TW && iy < p.h && ix < p.w && (!strided || ((iy | ix) & 1) == 0);
-            const int n0 = item.nt * NTC;
-            const int oh = strided ? (p.h >> 1) : ho, ow = strided ? (p.w >> 1) : wo;
-            // everything that does not depend on the accumulator is fetched while the MMAs of this tile still run
-            int cls[NPH];
-            float nz[NPH];
+        const bool strided = (NPH == 1 && p.out_stride == 2);
+        const int oh = strided ? (p.h >> 1) : ho, ow = strided ? (p.w >> 1) : wo;
+        // Region and noise of my pixel do not depend on the accumulator, and the noise map is a streaming tensor (every
+        // read is a DRAM miss): they are fetched one work item AHEAD, so that an epilogue-bound layer does not pay a DRAM
+        // round trip per tile.
+        auto fetch = [&](int it2, int (&c)[NPH], float (&z)[NPH]) {
+#pragma unroll
+            for (int q = 0; q < NPH; ++q) c[q] = 0, z[q] = 0.f;
+            if (it2 >= p.items) return;
+            const Item i2 = decode_item(p, it2);
+            const int iy = i2.ty * TH + ty, ix = i2.tx * TW + tx;
+            if (!(tx < TW && iy < p.h && ix < p.w && (!strided || ((iy | ix) & 1) == 0))) return;
 #pragma unroll
             for (int q = 0; q < NPH; ++q) {
                 const int oy = strided ? (iy >> 1) : iy * MUL + (q >> 1), ox = strided ? (ix >> 1) : ix * MUL + (q & 1);
-                cls[q] = 0, nz[q] = 0.f;
-                if (mine && p.label) cls[q] = min((int)p.label[((int64_t)item.b * oh + oy) * ow + ox], p.ncls - 1);
-                if (mine && p.noise) nz[q] = nw * __ldg(p.noise + ((int64_t)(p.noise_b == 1 ? 0 : item.b) * oh + oy) * ow + ox);
+                if (p.label) c[q] = min((int)p.label[((int64_t)i2.b * oh + oy) * ow + ox], p.ncls - 1);
+                if (p.noise) z[q] = __ldg(p.noise + ((int64_t)(p.noise_b == 1 ? 0 : i2.b) * oh + oy) * ow + ox);
             }
+        };
+        int cls_next[NPH];
+        float nz_next[NPH];
+        fetch(blockIdx.x, cls_next, nz_next);
+        for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
+            const Item item = decode_item(p, it);
+            const int iy = item.ty * TH + ty, ix = item.tx * TW + tx;
+            const bool mine = tx < TW && iy < p.h && ix < p.w && (!strided || ((iy | ix) & 1) == 0);
+            const int n0 = item.nt * NTC;
+            int cls[NPH];
+            float nz[NPH];
+#pragma unroll
+            for (int q = 0; q < NPH; ++q) cls[q] = cls_next[q], nz[q] = nw * nz_next[q];
+            fetch(it + gridDim.x, cls_next, nz_next);
+            // two-region tile: region A (lowest index) accumulated in buffer `acc`, region B in the other one
+            uint32_t classes = 1u;
+            if (TWO_CLASS) classes = tile_class_mask<NPH>(p, item, lane);
+            const bool two = TWO_CLASS && __popc(classes) == 2;
+            const int cls_b = 31 - __clz(classes);
             MBAR_WAIT_P(smem_u32(&bars[ACC_FULL + acc]), pacc[acc], 1);
             pacc[acc] ^= 1;
+            if (two) {
+                MBAR_WAIT_P(smem_u32(&bars[ACC_FULL + (acc ^ 1)]), pacc[acc ^ 1], 1);
+                pacc[acc ^ 1] ^= 1;
+            }
             tc_fence_after();
-            const uint32_t cbase = (uint32_t)(acc * ACC_COLS);
+            const uint32_t cbase = (uint32_t)(acc * ACC_COLS), cother = (uint32_t)((acc ^ 1) * ACC_COLS);
 #pragma unroll
             for (int q = 0; q < NPH; ++q) {
                 const int oy = strided ? (iy >> 1) : iy * MUL + (q >> 1), ox = strided ? (ix >> 1) : ix * MUL + (q & 1);
@@ -628,9 +697,18 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
 #pragma unroll 1
                 for (int j = 0; j < NTC / 32; ++j) {
                     uint32_t r[32];
-                    const uint32_t col = tmem_base + ((quarter * 32u) << 16) + cbase + (uint32_t)(q * NTC + j * 32);
-                    tmem_ld32(col, r);
-                    tmem_zero32(col);                    // the next tile's MMAs only accumulate
+                    const uint32_t lanes = tmem_base + ((quarter * 32u) << 16) + (uint32_t)(q * NTC + j * 32);
+                    tmem_ld32(lanes + cbase, r);
+                    tmem_zero32(lanes + cbase);          // the next tile's MMAs only accumulate
+                    if (two) {
+                        uint32_t r2[32];
+                        tmem_ld32(lanes + cother, r2);
+                        tmem_zero32(lanes + cother);
+                        if (cls[q] == cls_b) {
+#pragma unroll
+                            for (int e = 0; e < 32; ++e) r[e] = r2[e];
+                        }
+                    }
                     if (mine) {
 #pragma unroll
                         for (int g = 0; g < 8; ++g) {
@@ -660,6 +738,10 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
             tc_fence_before();
             mbar_arrive(smem_u32(&bars[ACC_EMPTY + acc]));
             acc ^= 1;
+            if (two) {
+                mbar_arrive(smem_u32(&bars[ACC_EMPTY + acc]));
+                acc ^= 1;
+            }
         }
     }
 
@@ -724,11 +806,12 @@ static int launch(const void* w_hilo, Params p, cudaStream_t st) {
     EncodeTiledFn enc = encode_fn();
     if (!enc) return E4S_ERR_ARCH;
     CUtensorMap map;
-    cuuint64_t dims[2] = {(cuuint64_t)p.cin, (cuuint64_t)2 * NPH * 9 * p.cout};
-    cuuint64_t strides[1] = {(cuuint64_t)p.cin * 2};
-    cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)NTC};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult cr = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w_hilo), dims, strides, box, estr,
+    // weights [2][NPH][9][Cout][Cin] bf16 as a 4-D tensor (Cin, Cout, tap, hl * NPH + parity)
+    cuuint64_t dims[4] = {(cuuint64_t)p.cin, (cuuint64_t)p.cout, 9, (cuuint64_t)2 * NPH};
+    cuuint64_t strides[3] = {(cuuint64_t)p.cin * 2, (cuuint64_t)p.cout * p.cin * 2, (cuuint64_t)9 * p.cout * p.cin * 2};
+    cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)NTC, 1, (cuuint32_t)2 * NPH};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult cr = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(w_hilo), dims, strides, box, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) return 700 + (int)cr;

@@ -332,6 +332,12 @@ TCP_EXTRA = [
     (1, 64, 32, 36, True, 1, "blobs"),        # up, N = 4 x 32
     (1, 96, 32, 16, True, 3, "iid"),          # 32-channel chunks x3, up, masked
     (3, 512, 512, 64, False, 12, "blobs"),    # production shape c7@64: > 148 work items, two N tiles, 12 regions
+    (1, 128, 64, 32, True, 2, "iid"),         # every tile holds exactly two regions (two-region mode of up-sampling layers)
+    (2, 64, 64, 24, True, 2, "iid"),
+    (1, 256, 256, 32, True, 3, "blobs"),
+    (16, 512, 512, 4, False, 12, "iid"),      # the 4x4 / 8x8 layers of a 16-face batch (mostly-halo tiles)
+    (16, 512, 512, 4, True, 3, "iid"),
+    (4, 512, 512, 8, True, 12, "blobs"),
     (1, 64, 128, 40, False, 1, "blobs"),      # encoder shape: small K with N = 128
     (2, 32, 128, 24, False, 3, "iid"),        # small K, N = 128, masked
 ]
