@@ -319,10 +319,17 @@ def run_ours(args):
         e1.record()
         barrier()
         ims = e0.elapsed_time(e1) / args.inversion_steps
+        inv_launches = K.LaunchStats.launches
         if world > 1:
             tt = torch.tensor([ims], device=dev)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             ims = float(tt.item())
+        # where the step goes: per-entry CUDA-event times of 5 further steps (event overhead makes these steps slower)
+        K.LaunchStats.reset(timing=True)
+        invert(net, target, onehot1, style_vectors=sv, steps=5)
+        torch.cuda.synchronize()
+        inv_kernels = {k: {"launches_per_step": v[0] / 5, "ms_per_step": round(v[1] / 5, 3)} for k, v in K.LaunchStats.summary().items()}
+        K.LaunchStats.reset(False)
         graphed = None
         try:
             invert(net, target, onehot1, style_vectors=sv, steps=6, cuda_graph=True)          # capture warm-up
@@ -343,8 +350,8 @@ def run_ours(args):
                        "loss_last": float(ghist[-1]), "faces_per_sec_100_steps": world / (gtot * 1e-3)}
         except Exception as exc:                                  # reported, never hidden
             graphed = {"error": repr(exc)[:300]}
-        inversion = {"steps_timed": args.inversion_steps, "ms_per_step": ims, "launches_per_step": K.LaunchStats.launches / args.inversion_steps,
-                     "cuda_graph": graphed,
+        inversion = {"steps_timed": args.inversion_steps, "ms_per_step": ims, "launches_per_step": inv_launches / args.inversion_steps,
+                     "cuda_graph": graphed, "kernels": inv_kernels,
                      "faces_per_sec_100_steps": world / (ims * 100 * 1e-3), "loss_first": float(hist[0]), "loss_last": float(hist[-1]),
                      "config": f"one {size}x{size} face per GPU, {ncls} regions, Adam lr 1e-2, l2 loss, fresh noise per step"}
 

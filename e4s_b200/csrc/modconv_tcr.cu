@@ -2,28 +2,34 @@
 //
 // Contract and implicit-GEMM formulation: modconv_tc.cu's header (8x16 pixel tile with 14 valid columns, taps as
 // row-shifted descriptors over one staged halo tile, split-bf16 x3 accumulation in fp32 TMEM, weights streamed by TMA
-// or resident).  Pipeline as the second generation (modconv_tcp.cu: persistent CTAs, TMA weight ring, double-buffered
-// TMEM accumulator, parities of an up-sampling layer along N), with the two lessons of the measurements under
-// profiles/ built in:
+// or resident).  Persistent CTAs (one per SM), 16 warps in four roles connected by mbarrier rings:
 //
-//  * ONE main-loop pass per tile, whatever the number of regions in it.  Region-pure tiles use the row-shift trick
-//    (operand staged once per K chunk, scaled by the region's style).  Mixed tiles switch to ROW-CLASS staging: the
-//    transform warps materialise the operand of every (tap, parity) separately and scale each row by the style of
-//    the region of that row's own output pixel; the MMAs then run per (tap, parity) with N = NTC.  That is 9x (36x
-//    for up-sampling layers) the staging work, done by eight transform warps out of L1, and it replaces 2-5 full
-//    passes per mixed tile (second generation) - the MMA work becomes independent of the mask.
-//  * A tight MMA issue loop.  ncu showed the 32->32 layer at 8 % tensor activity with one thread spending ~10k cycles
-//    per tile building descriptors and polling barriers for 54 MMAs of 16 cycles each.  Descriptor words are now
-//    precomputed (high word constant, low word = base + immediate), the tap / k loops are fully unrolled, and the
-//    resident / streamed and pure / mixed variants are separate straight-line code paths.
+//   warp 0       TMA producer: per tap ONE 4-D box = the (w_hi, w_lo) slot pair of all parities; in XS mode (Cin <= 64)
+//                also the raw fp32 halo tile of every chunk, issued one chunk ahead of the weights it is used with
+//   warps 1-3    MMA issue, one warp per split-precision product (x_hi w_hi, x_lo w_hi, x_hi w_lo)
+//   warps 4-11   transform: fp32 activations x region style -> bf16 hi/lo operand stage (128-/64-byte swizzle)
+//   warps 12-15  epilogue: TMEM -> demodulate, noise, bias, activation -> HBM; zero the accumulator buffer
 //
-//  * What bounds the small-N layers (source-level ncu sampling, profiles/): not DRAM latency (TMA staging did not help),
-//    not accumulator dependencies (rotating MMAs over independent TMEM column ranges did not help) but the single MMA
-//    warp itself - ~1400 warp instructions per tile for 54 MMAs, stalled on fixed-latency dependencies and on
-//    instruction fetch of a fully unrolled 30-KB loop.  The issue loop is therefore COMPACT: a runtime loop over taps,
-//    one lane-election per group of MMAs + commit, descriptors in uniform registers.
+// What the measurements under profiles/ built into it:
 //
-// K chunk: 64 channels (128-byte swizzle) when Cin % 64 == 0, else 32 channels (64-byte swizzle).
+//  * ONE main-loop pass per tile whatever the mask.  Region-pure tiles stage the operand once per K chunk (scaled by the
+//    region's style) and use the row-shift trick.  Two-region tiles of an up-sampling layer (most mixed tiles of a face
+//    mask) stage it twice per chunk, once per region, accumulate the two in the two TMEM buffers with the same pure-tile
+//    MMA sequence (N = 4 x NTC, tensor-pipe bound) and let the epilogue pick per (pixel, parity).  Other mixed tiles use
+//    ROW-CLASS staging: the operand of every (tap, parity) is materialised separately, each row scaled by the style of
+//    that row's own output pixel, MMAs per (tap, parity) with N = NTC.
+//  * MMA issue is a per-warp resource.  tools/ubench/umma_bench.cu: one warp gets a tcgen05.mma out every ~120-190
+//    cycles whatever its shape, while the pipe needs 16 (N = 32) ... 128 (N = 256) cycles; two / four issuing warps
+//    overlap (80-94 / 47-56 cycles per MMA at N <= 64).  Hence three issuing warps.  MMAs of different warps have no
+//    defined order, so none may be the "first" (accumulate = 0): the epilogue zeroes a buffer after reading it
+//    (tcgen05.st) and every MMA accumulates.
+//  * A consumer that only LOADS a TMA-filled buffer and then arrives on its "empty" barrier does not wait for the loads:
+//    the raw-tile ring is released after the stores that consume the values (a parity bug found at 1024x1024 shapes).
+//  * The weight producer was issue-bound with one 2-D box per (tap, hi/lo, parity) (144 per tile on the 64->32
+//    up-sampling layer): one 4-D box per tap.  The noise map is a streaming tensor: the epilogue fetches its operands one
+//    work item ahead.
+//
+// K chunk: 64 channels (128-byte swizzle) when Cin % 64 == 0 and Cin > 64, else 32 channels (64-byte swizzle).
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <mutex>
@@ -111,8 +117,12 @@ __device__ __forceinline__ void mbar_wait_p(uint32_t bar, uint32_t parity, long 
     ctr += clock64() - t0;
 }
 #define MBAR_WAIT_P(bar, parity, k) mbar_wait_p(bar, parity, pw[k], prof_on)
+#define PROF_BEGIN() const long long prof_t0 = prof_on ? clock64() : 0
+#define PROF_END(k) do { if (prof_on) pw[k] += clock64() - prof_t0; } while (0)
 #else
 #define MBAR_WAIT_P(bar, parity, k) mbar_wait(bar, parity)
+#define PROF_BEGIN() do {} while (0)
+#define PROF_END(k) do {} while (0)
 #endif
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -182,6 +192,26 @@ __device__ __forceinline__ Item decode_item(const Params& p, int it) {
     r.b = pt / p.tiles_y;
     return r;
 }
+
+// Work items of one CTA: it = blockIdx.x, + gridDim.x, ...  The divisions of decode_item cost every role ~300 cycles per
+// item (9 % of all warp samples on the 32->32 layer): decoded once, then advanced with carries.
+struct Walk {
+    Item cur, step;
+    __device__ __forceinline__ void init(const Params& p, int first, int stride) {
+        cur = decode_item(p, first);
+        step = decode_item(p, stride);
+    }
+    __device__ __forceinline__ void advance(const Params& p) {
+        cur.tx += step.tx;
+        int carry = 0;
+        if (cur.tx >= p.tiles_x) cur.tx -= p.tiles_x, carry = 1;
+        cur.ty += step.ty + carry, carry = 0;
+        if (cur.ty >= p.tiles_y) cur.ty -= p.tiles_y, carry = 1;
+        cur.b += step.b + carry, carry = 0;
+        if (cur.b >= p.batch) cur.b -= p.batch, carry = 1;
+        cur.nt += step.nt + carry;
+    }
+};
 
 // Regions present among the valid (pixel, parity) outputs of a tile; one whole warp, every role recomputes it.
 template <int NPH>
@@ -300,17 +330,27 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
         uint32_t ph = 0, phx = 0;
         bool loaded_resident = false;
         if (lane == 0) {
+            // the activation tile runs one chunk AHEAD of the weights it is consumed with (the transform warps need a
+            // few thousand cycles to turn it into an operand stage)
+            auto issue_x = [&](const Item& i2, int kc2) {
+                MBAR_WAIT_P(smem_u32(&bars[XS_EMPTY + st]), phx ^ 1, 2);
+                const uint32_t full = smem_u32(&bars[XS_FULL + st]);
+                mbar_expect_tx(full, XS_STAGE);
+                tma_load_4d(smem_u32(xs_buf + st * XS_STAGE), &xmap, kc2 * KC, i2.tx * TW - 1, i2.ty * TH - 1, i2.b, full);
+                if (++st == NXS) st = 0, phx ^= 1;
+            };
+            Walk wk;
+            wk.init(p, blockIdx.x, gridDim.x);
+            if (XS && blockIdx.x < p.items) issue_x(wk.cur, 0);
             for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
                 const bool load_w = !(p.resident && loaded_resident);
                 if (!XS && !load_w) break;
-                const Item item = decode_item(p, it);
+                const Item item = wk.cur;
+                wk.advance(p);
                 for (int kc = 0; kc < nchunks; ++kc) {
                     if (XS) {
-                        MBAR_WAIT_P(smem_u32(&bars[XS_EMPTY + st]), phx ^ 1, 2);
-                        const uint32_t full = smem_u32(&bars[XS_FULL + st]);
-                        mbar_expect_tx(full, XS_STAGE);
-                        tma_load_4d(smem_u32(xs_buf + st * XS_STAGE), &xmap, kc * KC, item.tx * TW - 1, item.ty * TH - 1, item.b, full);
-                        if (++st == NXS) st = 0, phx ^= 1;
+                        if (kc + 1 < nchunks) issue_x(item, kc + 1);
+                        else if (it + (int)gridDim.x < p.items) issue_x(wk.cur, 0);
                     }
                     if (load_w) {
                         // one 4-D box per tap: [hi | lo] x parities x NTC rows x KC channels = the (hi, lo) slot pair, contiguous
@@ -344,8 +384,10 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
         const uint32_t a0 = smem_u32(a_buf) + (role == 1 ? A_PLANE : 0), b0 = smem_u32(b_buf);
         auto desc = [](uint32_t lo) -> uint64_t { return ((uint64_t)DESC_HI << 32) | lo; };
         auto lo_of = [](uint32_t addr) -> uint32_t { return (addr >> 4) | 0x10000u; };
-        for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
-            const Item item = decode_item(p, it);
+        Walk wk;
+        wk.init(p, blockIdx.x, gridDim.x);
+        for (int it = blockIdx.x; it < p.items; it += gridDim.x, wk.advance(p)) {
+            const Item item = wk.cur;
             const uint32_t classes = __shfl_sync(0xffffffffu, tile_class_mask<NPH>(p, item, lane), 0);
             const bool mixed = (classes & (classes - 1)) != 0;
             const bool two = TWO_CLASS && __popc(classes) == 2;      // two regions: one accumulator buffer per region
@@ -466,8 +508,10 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
         int sa = 0, xstage = 0;
         uint32_t pa = 0, px = 0;
         uint32_t chunk_ctr = 0;                          // selects the s_tab buffer
-        for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
-            const Item item = decode_item(p, it);
+        Walk wk;
+        wk.init(p, blockIdx.x, gridDim.x);
+        for (int it = blockIdx.x; it < p.items; it += gridDim.x, wk.advance(p)) {
+            const Item item = wk.cur;
             const uint32_t classes = tile_class_mask<NPH>(p, item, lane);
             const bool mixed = (classes & (classes - 1)) != 0;
             const float* xb = p.x + (int64_t)item.b * p.h * p.w * p.cin;
@@ -649,11 +693,10 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
         // Region and noise of my pixel do not depend on the accumulator, and the noise map is a streaming tensor (every
         // read is a DRAM miss): they are fetched one work item AHEAD, so that an epilogue-bound layer does not pay a DRAM
         // round trip per tile.
-        auto fetch = [&](int it2, int (&c)[NPH], float (&z)[NPH]) {
+        auto fetch = [&](bool valid, const Item& i2, int (&c)[NPH], float (&z)[NPH]) {
 #pragma unroll
             for (int q = 0; q < NPH; ++q) c[q] = 0, z[q] = 0.f;
-            if (it2 >= p.items) return;
-            const Item i2 = decode_item(p, it2);
+            if (!valid) return;
             const int iy = i2.ty * TH + ty, ix = i2.tx * TW + tx;
             if (!(tx < TW && iy < p.h && ix < p.w && (!strided || ((iy | ix) & 1) == 0))) return;
 #pragma unroll
@@ -665,9 +708,12 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
         };
         int cls_next[NPH];
         float nz_next[NPH];
-        fetch(blockIdx.x, cls_next, nz_next);
+        Walk wk;
+        wk.init(p, blockIdx.x, gridDim.x);
+        fetch(blockIdx.x < p.items, wk.cur, cls_next, nz_next);
         for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
-            const Item item = decode_item(p, it);
+            const Item item = wk.cur;
+            wk.advance(p);
             const int iy = item.ty * TH + ty, ix = item.tx * TW + tx;
             const bool mine = tx < TW && iy < p.h && ix < p.w && (!strided || ((iy | ix) & 1) == 0);
             const int n0 = item.nt * NTC;
@@ -675,7 +721,7 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
             float nz[NPH];
 #pragma unroll
             for (int q = 0; q < NPH; ++q) cls[q] = cls_next[q], nz[q] = nw * nz_next[q];
-            fetch(it + gridDim.x, cls_next, nz_next);
+            fetch(it + (int)gridDim.x < p.items, wk.cur, cls_next, nz_next);
             // two-region tile: region A (lowest index) accumulated in buffer `acc`, region B in the other one
             uint32_t classes = 1u;
             if (TWO_CLASS) classes = tile_class_mask<NPH>(p, item, lane);
@@ -696,10 +742,20 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                 float* dst = p.y + (((int64_t)item.b * oh + oy) * ow + ox) * p.cout + n0;
 #pragma unroll 1
                 for (int j = 0; j < NTC / 32; ++j) {
+                    // demodulation and bias are fetched two channel groups ahead of their use (inside a plain load -> use
+                    // -> store loop every L1 hit was exposed behind the previous store: ncu source view, 40 % of the
+                    // epilogue warps' samples on the first FFMA of a group)
+                    auto ld_dm = [&](int g) { return dm ? __ldg(reinterpret_cast<const float4*>(dm + j * 32 + 4 * g)) : make_float4(1.f, 1.f, 1.f, 1.f); };
+                    auto ld_bv = [&](int g) { return p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j * 32 + 4 * g)) : make_float4(0.f, 0.f, 0.f, 0.f); };
+                    float4 dmr[2] = {ld_dm(0), ld_dm(1)}, bvr[2] = {ld_bv(0), ld_bv(1)};
                     uint32_t r[32];
                     const uint32_t lanes = tmem_base + ((quarter * 32u) << 16) + (uint32_t)(q * NTC + j * 32);
-                    tmem_ld32(lanes + cbase, r);
-                    tmem_zero32(lanes + cbase);          // the next tile's MMAs only accumulate
+                    {
+                        PROF_BEGIN();
+                        tmem_ld32(lanes + cbase, r);
+                        tmem_zero32(lanes + cbase);      // the next tile's MMAs only accumulate
+                        PROF_END(2);
+                    }
                     if (two) {
                         uint32_t r2[32];
                         tmem_ld32(lanes + cother, r2);
@@ -713,8 +769,8 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
 #pragma unroll
                         for (int g = 0; g < 8; ++g) {
                             const int co = j * 32 + 4 * g;
-                            const float4 d = dm ? __ldg(reinterpret_cast<const float4*>(dm + co)) : make_float4(1.f, 1.f, 1.f, 1.f);
-                            const float4 bv = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n0 + co)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            const float4 d = dmr[g & 1], bv = bvr[g & 1];
+                            if (g + 2 < 8) dmr[g & 1] = ld_dm(g + 2), bvr[g & 1] = ld_bv(g + 2);
                             float4 o;
                             o.x = __uint_as_float(r[4 * g + 0]) * d.x + nz[q] + bv.x;
                             o.y = __uint_as_float(r[4 * g + 1]) * d.y + nz[q] + bv.y;
@@ -734,7 +790,11 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                     }
                 }
             }
-            tmem_wait_st();
+            {
+                PROF_BEGIN();
+                tmem_wait_st();
+                PROF_END(3);
+            }
             tc_fence_before();
             mbar_arrive(smem_u32(&bars[ACC_EMPTY + acc]));
             acc ^= 1;

@@ -292,6 +292,40 @@ def test_get_style_vectors_golden(golden):
     assert_close(vec, golden["net3/style_vectors"], REL_TOL, "get_style_vectors")
 
 
+def test_streaming_pipeline_matches_direct_calls():
+    """e4s_b200.pipeline.SynthesisPipeline (H2D / generator / D2H on three streams, two slots) returns, per ticket, what a
+    plain gen_img call on the same inputs returns (noise strengths zeroed: the generator draws fresh noise per call)."""
+    from e4s_b200.pipeline import SynthesisPipeline
+    from e4s_b200 import masks as M
+    net, _ = _net3()
+    with torch.no_grad():
+        for name, prm in net.named_parameters():
+            if name.endswith("noise.weight"):
+                prm.zero_()
+    sv, lat, _, _ = O.net3_case()
+    net.latent_avg = cu(lat)
+    pipe = SynthesisPipeline(net, ncls=12, depth=2)
+    g = torch.Generator().manual_seed(77)
+    batches, tickets = [], []
+    for i in range(5):
+        with torch.no_grad():
+            codes = net.cal_style_codes(cu(sv) + 0.1 * i).cpu().pin_memory()
+        labels = torch.randint(0, 12, (2, 1, 8, 8), generator=g, dtype=torch.uint8).repeat_interleave(16, 2).repeat_interleave(16, 3)
+        labels = labels.contiguous().pin_memory()
+        batches.append((codes, labels))
+        tickets.append(pipe.submit(codes, labels))
+        if i >= 1:                                      # consume with a lag of one batch, like a service would
+            got = pipe.result(tickets[i - 1]).clone()
+            c, l = batches[i - 1]
+            with torch.no_grad():
+                ref, _, _ = net.gen_img(None, cu(c), M.labelMap2OneHot(cu(l), 12))
+            assert_close(got, ref.cpu(), 1e-6, f"pipeline batch {i - 1}")
+    pipe.drain()
+    torch.cuda.synchronize()
+    with pytest.raises(RuntimeError):
+        pipe.result(tickets[0])                         # only `depth` results are held
+
+
 # ---------------------------------------------------------------- tensor-core (tcgen05) kernel
 def _tc_case(b, cin, cout, hw, up, ncls, kind, seed, act=True):
     from e4s_b200 import kernels as K

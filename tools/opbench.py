@@ -141,7 +141,7 @@ def main():
                 lib().e4s_tcr_set_profile(None)
                 c = ctr.cpu().view(5, 4).tolist()
                 names = ["weights(TMA)  wait: B_EMPTY", "mma           wait: ACC_EMPTY, A_FULL, B_FULL", "transform     wait: XS_FULL, A_EMPTY",
-                         "epilogue      wait: ACC_FULL", "x-tiles(TMA)  wait: XS_EMPTY"]
+                         "epilogue      wait: ACC_FULL, tmem ld+zero, wait::st", "x-tiles(TMA)  wait: XS_EMPTY"]
                 for rname, cc in zip(names, c):
                     tot = max(cc[0], 1)
                     print(f"    prof {rname:48s} total {cc[0]:>10d} cyc  waits " + " ".join(f"{100.0 * v / tot:5.1f}%" for v in cc[1:]), flush=True)
