@@ -489,3 +489,21 @@ def test_encoder_building_blocks():
     out = K.norm_residual(cu(y), cu(ys), cu(yt), 0.5, shortcut=cu(short), sc_stride=2)
     ref = 0.5 * (y * ys[:, None, None] + yt[:, None, None]) + short[:, ::2, ::2]
     assert_close(out, ref, 1e-6, "unit tail")
+
+
+def test_generator_1024_tensor_core_path_matches_exact_fp32_path(monkeypatch):
+    """BASELINE's full size (1024x1024, K=13, 12 regions, one face): every layer on the tensor-core kernel against every
+    layer on the exact-fp32 SIMT kernel (which the 32/64/256 goldens pin to the reference).  Size-independent property:
+    the two code paths share only the op sequence."""
+    g, _ = _generator(1024, 13)
+    codes, mask, _, noise = O.synthetic_inputs(1, 12, 1024, 256, seed=21)
+    noise = [cu(n) for n in noise]
+    outs = {}
+    for mode in ("simt", "auto"):
+        monkeypatch.setenv("E4S_B200_CONV", mode)
+        with torch.no_grad():
+            img, _, _ = g([cu(codes)], None, cu(mask), input_is_latent=True, noise=noise)
+        outs[mode] = img.float().cpu()
+    assert outs["auto"].shape == (1, 3, 1024, 1024)
+    e = assert_close(outs["auto"], outs["simt"], 1e-4, "1024x1024 generator, tensor-core vs exact path")
+    print(f"1024 generator tc-vs-exact rel err {e:.2e}")
