@@ -170,6 +170,11 @@ __device__ __forceinline__ void tmem_zero32(uint32_t taddr) {
         : "memory");
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void st_global_v8(float* p, const float4& a, const float4& b) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x),
+                 "f"(b.y), "f"(b.z), "f"(b.w)
+                 : "memory");
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo_elem, float hi_elem) {
     uint32_t r;
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
@@ -766,6 +771,7 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                         }
                     }
                     if (mine) {
+                        float4 keep = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                         for (int g = 0; g < 8; ++g) {
                             const int co = j * 32 + 4 * g;
@@ -785,7 +791,9 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                                 o.x = o.x > 0.f ? o.x : o.x * sl.x, o.y = o.y > 0.f ? o.y : o.y * sl.y;
                                 o.z = o.z > 0.f ? o.z : o.z * sl.z, o.w = o.w > 0.f ? o.w : o.w * sl.w;
                             }
-                            *reinterpret_cast<float4*>(dst + co) = o;
+                            // 256-bit stores (one full 32-byte sector per lane): the odd group waits for its even neighbour
+                            if (g & 1) st_global_v8(dst + co - 4, keep, o);
+                            else keep = o;
                         }
                     }
                 }
@@ -960,6 +968,7 @@ extern "C" int e4s_modconv3x3_tcr_fwd(const float* x, const void* w_hilo_bf16, c
     E4S_REQUIRE(e4s_aligned16(x) && e4s_aligned16(w_hilo_bf16) && e4s_aligned16(s) && e4s_aligned16(y) &&
                     (!demod || e4s_aligned16(demod)) && (!bias || e4s_aligned16(bias)),
                 E4S_ERR_ALIGN);
+    E4S_REQUIRE((reinterpret_cast<uintptr_t>(y) & 31) == 0, E4S_ERR_ALIGN);          // 256-bit stores
     tcr::Params p{x, s, demod, label, noise, noise_w, bias, y, batch, h, w, cin, cout, ncls, noise_b, act ? 1 : 0,
                   0, 0, 0, 0, 0, 0, nullptr, nullptr, 1};
     return tcr::dispatch(w_hilo_bf16, p, up, (cudaStream_t)stream);
@@ -975,6 +984,7 @@ extern "C" int e4s_conv3x3_tcr_f32(const float* x, const void* w_hilo_bf16, cons
     E4S_REQUIRE(e4s_aligned16(x) && e4s_aligned16(w_hilo_bf16) && e4s_aligned16(y) && (!scale || e4s_aligned16(scale)) &&
                     (!shift || e4s_aligned16(shift)) && (!prelu_slope || e4s_aligned16(prelu_slope)),
                 E4S_ERR_ALIGN);
+    E4S_REQUIRE((reinterpret_cast<uintptr_t>(y) & 31) == 0, E4S_ERR_ALIGN);          // 256-bit stores
     tcr::Params p{x, scale, nullptr, nullptr, nullptr, nullptr, nullptr, y, batch, h, w, cin, cout, 1, 1, prelu_slope ? 2 : 0,
                   0, 0, 0, 0, 0, 0, shift, prelu_slope, out_stride};
     return tcr::dispatch(w_hilo_bf16, p, 0, (cudaStream_t)stream);

@@ -1,0 +1,3 @@
+mkdir -p gpurun_out
+timeout 600 python tests/tc_probe.py > gpurun_out/probe28.log 2>&1; echo "== probe rc=$?"; grep -c "elements off 0/" gpurun_out/probe28.log; grep -v "elements off 0/" gpurun_out/probe28.log | head -20 | cut -c1-250
+timeout 900 python tools/opbench.py --conv tcr --out gpurun_out/opbench28.json > gpurun_out/opbench28.log 2>&1; echo "== opbench rc=$?"; grep "conv_total" gpurun_out/opbench28.log

@@ -24,7 +24,7 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) { asm volatile("tcgen0
 struct Result { int m, n, sw, mode, shift; float cyc; };
 
 // mode 0: A and B from shared memory; 1: A from TMEM; 2: SS with two alternating accumulators (no D dependency)
-__global__ void __launch_bounds__(128, 1) bench(Result* out, int* nout, int m_count, int mode_mask, int nissue) {
+__global__ void __launch_bounds__(256, 1) bench(Result* out, int* nout, int m_count, int mode_mask, int nissue, int same_d) {
     extern __shared__ uint8_t raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
     __shared__ uint64_t bar;
@@ -63,10 +63,10 @@ __global__ void __launch_bounds__(128, 1) bench(Result* out, int* nout, int m_co
                             long long t0 = 0, t1 = 0;
                             // warp-uniform operands (uniform registers feed UTCHMMA directly, no R2UR in the loop)
                             const uint32_t ad_lo = __shfl_sync(0xffffffffu, (uint32_t)ad, 0), bd_lo = __shfl_sync(0xffffffffu, (uint32_t)bd, 0);
-                            const uint32_t d_u = __shfl_sync(0xffffffffu, tmem + (uint32_t)(warp * 64), 0);
+                            const uint32_t d_u = __shfl_sync(0xffffffffu, tmem + (uint32_t)(same_d ? 0 : (warp & 7) * 32), 0);
                             const bool active = warp < nissue;
                             for (int rep = 0; rep < 2; ++rep) {             // first repetition warms up
-                                asm volatile("bar.sync 1, 128;" ::: "memory");
+                                asm volatile("bar.sync 1, 256;" ::: "memory");
                                 t0 = clock64();
                                 if (active) {
 #pragma unroll 1
@@ -108,14 +108,14 @@ __global__ void __launch_bounds__(128, 1) bench(Result* out, int* nout, int m_co
 }
 
 int main(int argc, char** argv) {
-    const int m_count = argc > 1 ? atoi(argv[1]) : 1, mode_mask = argc > 2 ? atoi(argv[2]) : 5, nissue = argc > 3 ? atoi(argv[3]) : 1;
+    const int m_count = argc > 1 ? atoi(argv[1]) : 1, mode_mask = argc > 2 ? atoi(argv[2]) : 5, nissue = argc > 3 ? atoi(argv[3]) : 1, same_d = argc > 4 ? atoi(argv[4]) : 0;
     Result* d_out; int* d_n;
     cudaMalloc(&d_out, sizeof(Result) * 256); cudaMalloc(&d_n, sizeof(int));
     cudaMemset(d_n, 0, sizeof(int));
     const int smem = 161 * 1024 + 1024;
     cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    bench<<<1, 128, smem>>>(d_out, d_n, m_count, mode_mask, nissue);
-    printf("issuing warps: %d (cycles are per MMA of ONE warp; all warps issue concurrently)\n", nissue);
+    bench<<<1, 256, smem>>>(d_out, d_n, m_count, mode_mask, nissue, same_d);
+    printf("issuing warps: %d, %s accumulator columns (cycles are per MMA of ONE warp; all warps issue concurrently)\n", nissue, same_d ? "the SAME" : "private");
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("CUDA error: %s\n", cudaGetErrorString(e)); return 1; }
     Result h[256]; int n = 0;
