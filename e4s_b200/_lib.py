@@ -29,6 +29,9 @@ SIGNATURES = {
     "e4s_label_to_onehot_f32": [P, P, c_int, c_int, c_int, c_int, P],
     "e4s_label_resize_nearest_u8": [P, P, c_int, c_int, c_int, c_int, c_int, P],
     "e4s_label_remap_u8": [P, P, P, c_int64, P],
+    "e4s_swap_head_mask_u8": [P, P, P, P, P, c_int64, c_int, P],
+    "e4s_mask_box_morph_u8": [P, P, c_int, c_int, c_int, c_int, c_int, P],
+    "e4s_box_morph_f32": [P, P, c_int, c_int, c_int, c_int, c_int, c_float, P],
     "e4s_region_mean_f32": [P, P, P, P, c_int, c_int, c_int, c_int, c_int, P],
     "e4s_demod_f32": [P, P, P, c_int, c_int, c_int, c_float, P],
     "e4s_modconv3x3_fwd_f32": [P] * 9 + [c_int] * 9 + [P],

@@ -33,6 +33,12 @@ __device__ __forceinline__ float4 ld_stream_f4(const float* p) {
                  : "l"(p));
     return v;
 }
+// 256-bit variant (sm_100+): one full 32-byte sector per lane and request.  p must be 32-byte aligned.
+__device__ __forceinline__ void ld_stream_f8(const float* p, float4& a, float4& b) {
+    asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                 : "l"(p));
+}
 __device__ __forceinline__ void st_stream_f4(float* p, float4 v) {
     asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
                  "f"(v.w)

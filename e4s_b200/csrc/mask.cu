@@ -68,6 +68,112 @@ __global__ void __launch_bounds__(256) label_remap_kernel(const uint8_t* __restr
         dst[i] = s_lut[src[i]];
 }
 
+// ---- face-swapping mask stage, bit-exact --------------------------------------------------
+// Shape swapping of two 12-class parsing maps: swap_head_mask_revisit_considerGlass, src/utils/swap_face_mask.py:33-83.
+// The reference applies ~15 masked assignments over whole arrays on the CPU; every pixel is independent and later
+// assignments override earlier ones, so the sequence is one decision list per pixel.
+__device__ __forceinline__ void swap_head_pixel(int s, int t, int hair_first, uint8_t& res, uint8_t& hole, uint8_t& fg) {
+    int r = 0;
+    if (t == 0) r = 99;                                       // :42 place-holder for the target's background
+    else if (t == 8 || t == 7 || t == 11) r = t;              // :43-45 neck, ear, ear rings of the target
+    if (hair_first && t == 4) r = 4;                          // :47-48
+    if (r != 99 && (s == 1 || s == 2 || s == 3 || s == 5 || s == 6 || s == 9)) r = s;   // :51-56 inner face of the source
+    if (!hair_first && t == 4) r = 4;                         // :66-67
+    if (t == 10) r = 10;                                      // :70 eye glasses of the target
+    const bool is_hole = r == 0;                              // :74-78
+    if (is_hole) r = 6;                                       // missing pixels become skin
+    if (r == 99) r = 0;                                       // :81
+    res = (uint8_t)r;
+    hole = is_hole ? 255 : 0;
+    // scripts/face_swap.py:280-284: background = {0, 11, 4}; holes count as foreground
+    fg = (uint8_t)((!(r == 0 || r == 11 || r == 4)) || is_hole);
+}
+
+__global__ void __launch_bounds__(256) swap_head_mask_kernel(const uint8_t* __restrict__ src, const uint8_t* __restrict__ tgt,
+                                                             uint8_t* __restrict__ res, uint8_t* __restrict__ hole,
+                                                             uint8_t* __restrict__ fg, int64_t n, int hair_first, int vec) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    if (vec) {                                                // 16 labels per thread and step, 128-bit accesses
+        const int64_t n16 = n >> 4;
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+            const uint4 sv = __ldg(reinterpret_cast<const uint4*>(src) + i), tv = __ldg(reinterpret_cast<const uint4*>(tgt) + i);
+            const uint32_t sw[4] = {sv.x, sv.y, sv.z, sv.w}, tw[4] = {tv.x, tv.y, tv.z, tv.w};
+            uint32_t rw[4], hw[4], fw[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                rw[k] = hw[k] = fw[k] = 0;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    uint8_t r, h, f;
+                    swap_head_pixel((sw[k] >> (8 * b)) & 255, (tw[k] >> (8 * b)) & 255, hair_first, r, h, f);
+                    rw[k] |= (uint32_t)r << (8 * b), hw[k] |= (uint32_t)h << (8 * b), fw[k] |= (uint32_t)f << (8 * b);
+                }
+            }
+            reinterpret_cast<uint4*>(res)[i] = make_uint4(rw[0], rw[1], rw[2], rw[3]);
+            reinterpret_cast<uint4*>(hole)[i] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            if (fg) reinterpret_cast<uint4*>(fg)[i] = make_uint4(fw[0], fw[1], fw[2], fw[3]);
+        }
+    }
+    const int64_t done = vec ? (n >> 4) << 4 : 0;
+    for (int64_t i = done + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint8_t r, h, f;
+        swap_head_pixel(src[i], tgt[i], hair_first, r, h, f);
+        res[i] = r, hole[i] = h;
+        if (fg) fg[i] = f;
+    }
+}
+
+// Flat (2r+1)^2 box dilation (MAXOP) / erosion of uint8 masks with the 'geodesic' border of the reference
+// (src/utils/morphology.py:83-86, 170-173: positions outside the image never win).  The reference turns the window
+// into (2r+1)^2 = 121 convolution channels and reduces over them; a box is separable, so one CTA stages a 32x64 tile
+// with its halo, reduces along rows in shared memory, then along columns.
+constexpr int MT_W = 64, MT_H = 32, MORPH_MAX_R = 16;
+template <typename T, bool MAXOP>
+__global__ void __launch_bounds__(256) box_morph_kernel(const T* __restrict__ src, T* __restrict__ dst, int h, int w,
+                                                        int radius, T neutral) {
+    __shared__ T raw[(MT_H + 2 * MORPH_MAX_R) * (MT_W + 2 * MORPH_MAX_R)];
+    __shared__ T rows[(MT_H + 2 * MORPH_MAX_R) * MT_W];
+    const int x0 = blockIdx.x * MT_W, y0 = blockIdx.y * MT_H;
+    const T* sp = src + (int64_t)blockIdx.z * h * w;
+    const int sw = MT_W + 2 * radius, sh = MT_H + 2 * radius;
+    for (int i = threadIdx.x; i < sw * sh; i += 256) {
+        const int ry = i / sw, rx = i - ry * sw;
+        const int gy = y0 - radius + ry, gx = x0 - radius + rx;
+        raw[i] = (gy >= 0 && gy < h && gx >= 0 && gx < w) ? sp[(int64_t)gy * w + gx] : neutral;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < sh * MT_W; i += 256) {
+        const int ry = i / MT_W, cx = i - ry * MT_W;
+        const T* rp = raw + ry * sw + cx;
+        T v = rp[0];
+        for (int k = 1; k <= 2 * radius; ++k) v = MAXOP ? max(v, rp[k]) : min(v, rp[k]);
+        rows[i] = v;
+    }
+    __syncthreads();
+    T* dp = dst + (int64_t)blockIdx.z * h * w;
+    for (int i = threadIdx.x; i < MT_H * MT_W; i += 256) {
+        const int cy = i / MT_W, cx = i - cy * MT_W;
+        const int gy = y0 + cy, gx = x0 + cx;
+        if (gy >= h || gx >= w) continue;
+        T v = rows[cy * MT_W + cx];
+        for (int k = 1; k <= 2 * radius; ++k) v = MAXOP ? max(v, rows[(cy + k) * MT_W + cx]) : min(v, rows[(cy + k) * MT_W + cx]);
+        dp[(int64_t)gy * w + gx] = v;
+    }
+}
+
+template <typename T>
+int launch_box_morph(const T* src, T* dst, int planes, int h, int w, int radius, int erode, T lo, T hi, cudaStream_t st) {
+    E4S_REQUIRE(src && dst && src != dst && planes > 0 && h > 0 && w > 0 && radius >= 0, E4S_ERR_ARG);
+    E4S_REQUIRE(radius <= MORPH_MAX_R && planes <= 65535, E4S_ERR_SHAPE);
+    dim3 grid((unsigned)e4s_ceil_div(w, MT_W), (unsigned)e4s_ceil_div(h, MT_H), (unsigned)planes);
+    E4S_REQUIRE(grid.y <= 65535, E4S_ERR_SHAPE);
+    if (erode)
+        box_morph_kernel<T, false><<<grid, 256, 0, st>>>(src, dst, h, w, radius, hi);
+    else
+        box_morph_kernel<T, true><<<grid, 256, 0, st>>>(src, dst, h, w, radius, lo);
+    return e4s_launch_status();
+}
+
 // Region mean: grid (channel chunks of 32, B).  Each warp walks pixels; lane = channel inside the
 // 32-channel chunk (pixel-major: the 32 lanes read 128 contiguous bytes).  Per-class partial sums
 // live in shared memory [ncls][32] per warp, reduced across warps at the end.  Area counts are
@@ -166,6 +272,27 @@ extern "C" int e4s_label_remap_u8(const uint8_t* src, uint8_t* dst, const uint8_
     E4S_REQUIRE(src && dst && lut256 && n > 0, E4S_ERR_ARG);
     label_remap_kernel<<<gs_grid(n), 256, 0, (cudaStream_t)stream>>>(src, dst, lut256, n);
     return e4s_launch_status();
+}
+
+extern "C" int e4s_swap_head_mask_u8(const uint8_t* source, const uint8_t* target, uint8_t* swapped, uint8_t* hole,
+                                     uint8_t* foreground, int64_t n, int hair_first, void* stream) {
+    E4S_REQUIRE(source && target && swapped && hole && n > 0, E4S_ERR_ARG);
+    const int vec = e4s_aligned16(source) && e4s_aligned16(target) && e4s_aligned16(swapped) && e4s_aligned16(hole) &&
+                    (!foreground || e4s_aligned16(foreground));
+    swap_head_mask_kernel<<<gs_grid(vec ? e4s_ceil_div(n, 16) : n), 256, 0, (cudaStream_t)stream>>>(
+        source, target, swapped, hole, foreground, n, hair_first ? 1 : 0, vec);
+    return e4s_launch_status();
+}
+
+extern "C" int e4s_mask_box_morph_u8(const uint8_t* src, uint8_t* dst, int planes, int h, int w, int radius, int erode,
+                                     void* stream) {
+    return launch_box_morph<uint8_t>(src, dst, planes, h, w, radius, erode, 0, 255, (cudaStream_t)stream);
+}
+
+extern "C" int e4s_box_morph_f32(const float* src, float* dst, int planes, int h, int w, int radius, int erode, float max_val,
+                                 void* stream) {
+    // the reference pads with -max_val (dilation) / +max_val (erosion): morphology.py:83-86, 170-173
+    return launch_box_morph<float>(src, dst, planes, h, w, radius, erode, -max_val, max_val, (cudaStream_t)stream);
 }
 
 extern "C" int e4s_region_mean_f32(const float* feats, const uint8_t* label, float* out, int* area, int batch, int ncls,

@@ -16,6 +16,7 @@
 // This replaces, per region per layer, the cuDNN dgrad AND wgrad the reference's autograd runs (model.py:277-316).
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -532,12 +533,37 @@ static int launch(const void* wd_hilo, Params p, cudaStream_t st) {
     return e4s_launch_status();
 }
 
+// Width of the N tile (input channels per work item).  Wide tiles re-use a staged gradient tile for more columns, but a
+// work item is a whole (pixel tile, N tile) pair with up to ncls x NPH x 9 x Cout/KC weight slots streamed through ONE
+// CTA: the 4x4 ... 32x32 layers of a single face have 1-12 pixel tiles, and at 256 columns two CTAs pulled the whole
+// 38-MB weight set through their own L2 ports while 146 SMs idled (2.2 ms per layer, profiles/r1_bwd_layers_*.log).
+// Take the widest tile that still yields work for half the SMs, else the narrowest.  E4S_B200_NTILE=32|64|128|256
+// forces a width (tests).
+static int pick_ntile(int channels, int widest, int64_t pixel_tiles) {
+    static const int cand[4] = {256, 128, 64, 32};
+    if (const char* f = getenv("E4S_B200_NTILE")) {
+        const int v = atoi(f);
+        if ((v == 32 || v == 64 || v == 128 || v == 256) && v <= widest && channels % v == 0) return v;
+    }
+    int last = 32;
+    for (int i = 0; i < 4; ++i) {
+        const int c = cand[i];
+        if (c > widest || channels % c != 0) continue;
+        last = c;
+        if (pixel_tiles * (channels / c) >= num_sms() / 2) return c;
+    }
+    return last;
+}
+
 template <int KC, int NPH>
 static int dispatch_n(const void* wd, const Params& p, cudaStream_t st) {
-    if (p.cin % 256 == 0) return launch<256, KC, NPH>(wd, p, st);
-    if (p.cin % 128 == 0) return launch<128, KC, NPH>(wd, p, st);
-    if (p.cin % 64 == 0) return launch<64, KC, NPH>(wd, p, st);
-    return launch<32, KC, NPH>(wd, p, st);
+    const int64_t pixel_tiles = e4s_ceil_div(p.w, TW) * e4s_ceil_div(p.h, TH) * p.batch;
+    switch (pick_ntile(p.cin, 256, pixel_tiles)) {
+        case 256: return launch<256, KC, NPH>(wd, p, st);
+        case 128: return launch<128, KC, NPH>(wd, p, st);
+        case 64: return launch<64, KC, NPH>(wd, p, st);
+        default: return launch<32, KC, NPH>(wd, p, st);
+    }
 }
 
 }  // namespace tcd

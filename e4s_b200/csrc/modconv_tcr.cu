@@ -32,6 +32,7 @@
 // K chunk: 64 channels (128-byte swizzle) when Cin % 64 == 0 and Cin > 64, else 32 channels (64-byte swizzle).
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -922,6 +923,22 @@ static int launch(const void* w_hilo, Params p, cudaStream_t st) {
     return e4s_launch_status();
 }
 
+static int pick_ntile(int channels, int widest, int64_t pixel_tiles) {
+    static const int cand[4] = {256, 128, 64, 32};
+    if (const char* f = getenv("E4S_B200_NTILE")) {
+        const int v = atoi(f);
+        if ((v == 32 || v == 64 || v == 128 || v == 256) && v <= widest && channels % v == 0) return v;
+    }
+    int last = 32;
+    for (int i = 0; i < 4; ++i) {
+        const int c = cand[i];
+        if (c > widest || channels % c != 0) continue;
+        last = c;
+        if (pixel_tiles * (channels / c) >= num_sms() / 2) return c;
+    }
+    return last;
+}
+
 int dispatch(const void* w_hilo_bf16, Params p, int up, cudaStream_t st) {
     const int cin = p.cin, cout = p.cout;
     if (cin <= 64) {                 // small K: HBM-bound layers -> TMA-staged activations, 32-channel chunks
@@ -933,22 +950,28 @@ int dispatch(const void* w_hilo_bf16, Params p, int up, cudaStream_t st) {
         if (cout % 64 == 0) return launch<64, 32, 4, true>(w_hilo_bf16, p, st);
         return launch<32, 32, 4, true>(w_hilo_bf16, p, st);
     }
+    // N-tile width by occupancy (same rule and override as the gradient kernel, modconv_dgrad_tc.cu:pick_ntile): the
+    // low-resolution 512-channel layers have a handful of pixel tiles, and wide N tiles left most SMs without work.
     const bool k64 = (cin % 64) == 0;
+    const int64_t pixel_tiles = e4s_ceil_div(p.w, TW) * e4s_ceil_div(p.h, TH) * p.batch;
     if (!up) {
         if (k64) {
-            if (cout % 256 == 0) {
+            int nt = pick_ntile(cout, 256, pixel_tiles);
+            if (nt == 256) {
                 const int rc = launch<256, 64, 1>(w_hilo_bf16, p, st);
                 if (rc != E4S_ERR_SHAPE) return rc;          // too many regions for the style table next to 32-KB weight slots
+                nt = 128;
             }
-            if (cout % 128 == 0) return launch<128, 64, 1>(w_hilo_bf16, p, st);
-            if (cout % 64 == 0) return launch<64, 64, 1>(w_hilo_bf16, p, st);
+            if (nt == 128) return launch<128, 64, 1>(w_hilo_bf16, p, st);
+            if (nt == 64) return launch<64, 64, 1>(w_hilo_bf16, p, st);
             return launch<32, 64, 1>(w_hilo_bf16, p, st);
         }
-        if (cout % 64 == 0) return launch<64, 32, 1>(w_hilo_bf16, p, st);
+        if (pick_ntile(cout, 64, pixel_tiles) == 64) return launch<64, 32, 1>(w_hilo_bf16, p, st);
         return launch<32, 32, 1>(w_hilo_bf16, p, st);
     }
+    const int nt = pick_ntile(cout, 64, pixel_tiles);
     if (k64) {
-        if (cout % 64 == 0) return launch<64, 64, 4>(w_hilo_bf16, p, st);
+        if (nt == 64) return launch<64, 64, 4>(w_hilo_bf16, p, st);
         return launch<32, 64, 4>(w_hilo_bf16, p, st);
     }
     return launch<32, 32, 4>(w_hilo_bf16, p, st);

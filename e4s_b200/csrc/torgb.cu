@@ -118,14 +118,21 @@ __global__ void __launch_bounds__(256) torgb_pixel_kernel(TorgbParams p) {
         const float* w0 = ws + cls * 3 * p.cin;
         const float* xp = xb + pix * p.cin;
         float a0 = b0, a1 = b1, a2 = b2;
-        for (int c = 0; c < p.cin; c += 4) {
-            const float4 v = ld_stream_f4(xp + c);
-            const float4 u0 = *reinterpret_cast<const float4*>(w0 + c);
-            const float4 u1 = *reinterpret_cast<const float4*>(w0 + p.cin + c);
-            const float4 u2 = *reinterpret_cast<const float4*>(w0 + 2 * p.cin + c);
+        // a pixel's channels are one contiguous run: 256-bit loads fetch one whole 32-byte sector per lane and request
+        // (with 128-bit loads every sector was requested twice, by two different instructions)
+#pragma unroll 4
+        for (int c = 0; c < p.cin; c += 8) {
+            float4 v, t;
+            ld_stream_f8(xp + c, v, t);
+            const float4 u0 = *reinterpret_cast<const float4*>(w0 + c), q0 = *reinterpret_cast<const float4*>(w0 + c + 4);
+            const float4 u1 = *reinterpret_cast<const float4*>(w0 + p.cin + c), q1 = *reinterpret_cast<const float4*>(w0 + p.cin + c + 4);
+            const float4 u2 = *reinterpret_cast<const float4*>(w0 + 2 * p.cin + c), q2 = *reinterpret_cast<const float4*>(w0 + 2 * p.cin + c + 4);
             a0 += v.x * u0.x + v.y * u0.y + v.z * u0.z + v.w * u0.w;
             a1 += v.x * u1.x + v.y * u1.y + v.z * u1.z + v.w * u1.w;
             a2 += v.x * u2.x + v.y * u2.y + v.z * u2.z + v.w * u2.w;
+            a0 += t.x * q0.x + t.y * q0.y + t.z * q0.z + t.w * q0.w;
+            a1 += t.x * q1.x + t.y * q1.y + t.z * q1.z + t.w * q1.w;
+            a2 += t.x * q2.x + t.y * q2.y + t.z * q2.z + t.w * q2.w;
         }
         if (p.skip) {
             const int yy = (int)(pix / p.w), xx = (int)(pix - (int64_t)yy * p.w);
@@ -181,7 +188,8 @@ extern "C" int e4s_torgb_fwd_f32(const float* x, const float* wrgb, const float*
     E4S_REQUIRE((size_t)(3 + ncls) * cin * sizeof(float) <= 200 * 1024, E4S_ERR_SHAPE);
     TorgbParams p{x, wrgb, s, label, bias, skip, fir4x4, out, batch, h, w, cin, ncls};
     cudaStream_t st = (cudaStream_t)stream;
-    if (cin <= 64 && (size_t)ncls * 3 * cin * sizeof(float) <= 40 * 1024) {
+    if (cin <= 64 && (cin % 8) == 0 && (reinterpret_cast<uintptr_t>(x) & 31) == 0 &&
+        (size_t)ncls * 3 * cin * sizeof(float) <= 40 * 1024) {
         const int64_t hw = (int64_t)h * w;
         int64_t want = e4s_ceil_div(hw, 256), cap = e4s_ceil_div((int64_t)E4S_NUM_SMS * 16, batch);
         if (cap < 1) cap = 1;

@@ -9,8 +9,10 @@
 //     staged once through shared memory with fully coalesced loads, FIR taps live in registers,
 //     every thread produces a 4x4 micro-tile from two conflict-free 128-bit shared loads per input
 //     row and writes 128-bit streaming stores;
-//   * everything else (up = 2 RGB-skip up-sampling, down = 2, odd FIR sizes): a gather kernel with
-//     the read-only path; these carry < 4 % of the op's bytes in the model.
+//   * up = 2 with the 4x4 FIR (Upsample of the RGB skip, model.py:34-53): polyphase 2x2 stencil, one 128-bit
+//     store of 4 outputs per thread;
+//   * everything else (down = 2, odd FIR sizes): a gather kernel with the read-only path; these carry < 1 % of
+//     the op's bytes in the model.
 #include "common.cuh"
 
 namespace {
@@ -54,6 +56,65 @@ __global__ void __launch_bounds__(256) upfirdn2d_gather_kernel(const float* __re
             }
         }
         y[idx] = acc;
+    }
+}
+
+// ----------------------------------------------------------- up = 2, down = 1, 4x4 FIR (Upsample of the RGB skip)
+// Polyphase form: on the zero-stuffed grid only taps of one parity per axis meet a sample, so an output is a 2x2
+// stencil of the input, not 16 guarded taps.  One thread produces 4 consecutive output columns of one row (one
+// 128-bit streaming store) from a 2 x 4 input window; the window is re-used by the neighbouring rows/threads
+// through L1, so HBM sees each input once and the kernel is bound by its output stream (4x the input bytes).
+__global__ void __launch_bounds__(256) upfirdn2d_up2_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                            const float* __restrict__ fir, UpfirdnParams p,
+                                                            int64_t total4) {
+    float kf[4][4];                       // flipped taps: kf[ky][kx] multiplies the sample under tap (ky, kx)
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) kf[a][b] = __ldg(fir + (3 - a) * 4 + (3 - b));
+    const int ow4 = p.out_w >> 2;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total4;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int q = (int)(idx % ow4);
+        int64_t t = idx / ow4;
+        const int oy = (int)(t % p.out_h);
+        const int64_t plane = t / p.out_h;
+        const float* xp = x + plane * (int64_t)p.in_h * p.in_w;
+        // rows: taps ky = py, py + 2 land on even positions my = oy - pad_y0 + ky of the zero-stuffed grid
+        const int my0 = oy - p.pad_y0, py = my0 & 1;
+        const int iy0 = (my0 + py) >> 1;                       // sample under tap py; tap py + 2 sees iy0 + 1
+        // columns: output ox = 4q + j, mx0 = ox - pad_x0; taps kx = px, px + 2; samples ix0(j), ix0(j) + 1
+        const int base = 4 * q - p.pad_x0;
+        const int c0 = (base + (base & 1)) >> 1;               // ceil(base / 2): leftmost sample any of the 4 outputs reads
+        float v[2][4];
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            const int iy = iy0 + a;
+            const bool rowok = iy >= 0 && iy < p.in_h;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int ix = c0 + c;
+                v[a][c] = (rowok && ix >= 0 && ix < p.in_w) ? __ldg(xp + (int64_t)iy * p.in_w + ix) : 0.f;
+            }
+        }
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int mx0 = base + j, px = mx0 & 1;
+            const int cj = ((mx0 + px) >> 1) - c0;             // 0..2
+            float acc = 0.f;
+#pragma unroll
+            for (int a = 0; a < 2; ++a) {
+                const float k0 = py ? (px ? kf[2 * a + 1][1] : kf[2 * a + 1][0]) : (px ? kf[2 * a][1] : kf[2 * a][0]);
+                const float k1 = py ? (px ? kf[2 * a + 1][3] : kf[2 * a + 1][2]) : (px ? kf[2 * a][3] : kf[2 * a][2]);
+                const float s0 = cj == 0 ? v[a][0] : (cj == 1 ? v[a][1] : v[a][2]);
+                const float s1 = cj == 0 ? v[a][1] : (cj == 1 ? v[a][2] : v[a][3]);
+                acc = fmaf(s0, k0, acc);
+                acc = fmaf(s1, k1, acc);
+            }
+            o[j] = acc;
+        }
+        st_stream_f4(y + (plane * p.out_h + oy) * (int64_t)p.out_w + 4 * q, make_float4(o[0], o[1], o[2], o[3]));
     }
 }
 
@@ -189,6 +250,11 @@ extern "C" int e4s_upfirdn2d_f32(const float* x, float* y, const float* fir, int
             E4S_REQUIRE(nblk < (1ll << 31), E4S_ERR_SHAPE);
             upfirdn2d_fir4_kernel<8><<<(unsigned)nblk, 256, 0, st>>>(x, y, fir, p, tx, ty);
         }
+    } else if (up_x == 2 && up_y == 2 && down_x == 1 && down_y == 1 && kh == 4 && kw == 4 && (out_w & 3) == 0 &&
+               e4s_aligned16(y)) {
+        int64_t total4 = (int64_t)planes * out_h * (out_w >> 2);
+        int64_t want = e4s_ceil_div(total4, 256), cap = (int64_t)E4S_NUM_SMS * 32;
+        upfirdn2d_up2_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(x, y, fir, p, total4);
     } else {
         int64_t total = (int64_t)planes * out_h * out_w;
         int64_t want = e4s_ceil_div(total, 256);

@@ -217,6 +217,50 @@ def label_remap(label: Tensor, lut: Tensor) -> Tensor:
     return out
 
 
+def _u8c(t: Tensor, what: str) -> Tensor:
+    _lib.require_cuda(t, what)
+    if t.dtype != torch.uint8:
+        t = t.to(torch.uint8)
+    return t.contiguous()
+
+
+def swap_head_mask(source: Tensor, target: Tensor, hair_first: bool = True):
+    """Two 12-class label maps of equal shape -> (swapped labels, hole map in {0, 255}, foreground in {0, 1}), uint8."""
+    source, target = _u8c(source, "source"), _u8c(target, "target")
+    if source.shape != target.shape:
+        raise RuntimeError(f"source {tuple(source.shape)} and target {tuple(target.shape)} label maps differ in shape")
+    res, hole, fg = torch.empty_like(target), torch.empty_like(target), torch.empty_like(target)
+    if target.numel() == 0:
+        return res, hole, fg
+    with torch.cuda.device(target.device):
+        _call("e4s_swap_head_mask_u8", _lib.load().e4s_swap_head_mask_u8, ptr(source), ptr(target), ptr(res), ptr(hole), ptr(fg),
+              target.numel(), int(bool(hair_first)), stream_ptr(), work=5.0 * target.numel())
+    return res, hole, fg
+
+
+def mask_box_morph(mask: Tensor, radius: int, erode: bool, max_val: float = 1e4) -> Tensor:
+    """uint8 or fp32 images [..., H, W] -> flat (2r+1)^2 box dilation / erosion with the geodesic border."""
+    _lib.require_cuda(mask, "mask")
+    if mask.dtype not in (torch.uint8, torch.float32):
+        mask = mask.float()
+    mask = mask.contiguous()
+    if mask.dim() < 2:
+        raise RuntimeError("mask must have at least 2 dimensions")
+    h, w = mask.shape[-2:]
+    out = torch.empty_like(mask)
+    if mask.numel() == 0:
+        return out
+    planes = mask.numel() // (h * w)
+    with torch.cuda.device(mask.device):
+        if mask.dtype == torch.uint8:
+            _call("e4s_mask_box_morph_u8", _lib.load().e4s_mask_box_morph_u8, ptr(mask), ptr(out), planes, h, w, int(radius),
+                  int(bool(erode)), stream_ptr(), work=2.0 * mask.numel())
+        else:
+            _call("e4s_box_morph_f32", _lib.load().e4s_box_morph_f32, ptr(mask), ptr(out), planes, h, w, int(radius),
+                  int(bool(erode)), float(max_val), stream_ptr(), work=8.0 * mask.numel())
+    return out
+
+
 def region_mean(feats_pm: Tensor, label: Tensor, ncls: int):
     """feats_pm: [B, H, W, C] contiguous; label: [B, H, W] uint8 -> ([B, ncls, C], area [B, ncls] int32)."""
     b, h, w, c = feats_pm.shape

@@ -79,6 +79,24 @@ int e4s_label_resize_nearest_u8(const uint8_t* src, uint8_t* dst, int batch, int
 /* Class remap through a 256-entry LUT (device pointer); the CelebAMask-HQ 19->12 conversion of
  * src/datasets/dataset.py:153-209 is one such table. */
 int e4s_label_remap_u8(const uint8_t* src, uint8_t* dst, const uint8_t* lut256, int64_t n, void* stream);
+/* Shape swapping of the face-swapping pipeline (step 4 of scripts/face_swap.py:253): replaces
+ * swap_head_mask_revisit_considerGlass, src/utils/swap_face_mask.py:33-83, a numpy routine on the host.
+ * source / target: 12-class label maps (faceParser_label_list_detailed, :27-29) of n pixels each;
+ * swapped: the recomposed label map; hole: 255 where no region claimed the pixel (filled with skin), else 0;
+ * foreground (may be NULL): 1 where the swapped label is not background / hair / ear rings or the pixel is a hole
+ * (scripts/face_swap.py:280-284), else 0.  hair_first selects :47-48 over :66-67. */
+int e4s_swap_head_mask_u8(const uint8_t* source, const uint8_t* target, uint8_t* swapped, uint8_t* hole,
+                          uint8_t* foreground, int64_t n, int hair_first, void* stream);
+/* Flat (2*radius+1)^2 box dilation (erode = 0) or erosion (erode = 1) of uint8 masks [planes, h, w] with the
+ * reference's 'geodesic' border (pixels outside the image are ignored): dilation / erosion of
+ * src/utils/morphology.py:23-197 as scripts/face_swap.py:30-48 (create_masks) calls them.  radius <= 16;
+ * src and dst must not alias. */
+int e4s_mask_box_morph_u8(const uint8_t* src, uint8_t* dst, int planes, int h, int w, int radius, int erode,
+                          void* stream);
+/* The same on fp32 images (the reference's tensors are float): out-of-image positions count as -max_val (dilation)
+ * or +max_val (erosion), exactly the padding of morphology.py:83-86, 170-173 (default max_val 1e4). */
+int e4s_box_morph_f32(const float* src, float* dst, int planes, int h, int w, int radius, int erode, float max_val,
+                      void* stream);
 /* Region mean pooling, FSEncoder_PSP.get_per_comp_styleCode, psp_encoders.py:264-283.
  * feats: pixel-major [B, H, W, C]; label: [B, H, W] uint8 (already at feature resolution);
  * out: [B, ncls, C] (zero for empty regions); area: [B, ncls] int32 scratch/outputs. */

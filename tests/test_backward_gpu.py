@@ -196,6 +196,22 @@ def test_inversion_loop_matches_oracle(monkeypatch):
     (2, 256, 256, 8, False, 12, "blobs", True),
 ])
 def test_dgrad_tc_matches_simt(b, cin, cout, hw, up, ncls, kind, act):
+    _dgrad_case(b, cin, cout, hw, up, ncls, kind, act)
+
+
+@pytest.mark.parametrize("ntile", ["32", "64", "128", "256"])
+@pytest.mark.parametrize("b,cin,cout,hw,up,ncls,kind,act", [
+    (1, 512, 512, 8, False, 12, "iid", True),
+    (1, 512, 512, 8, True, 3, "iid", True),
+    (2, 256, 128, 16, True, 4, "blobs", True),
+])
+def test_dgrad_tc_every_n_tile_width(monkeypatch, ntile, b, cin, cout, hw, up, ncls, kind, act):
+    """csrc/modconv_dgrad_tc.cu:pick_ntile (N-tile width by occupancy): every width gives the same gradients."""
+    monkeypatch.setenv("E4S_B200_NTILE", ntile)
+    _dgrad_case(b, cin, cout, hw, up, ncls, kind, act)
+
+
+def _dgrad_case(b, cin, cout, hw, up, ncls, kind, act):
     from e4s_b200 import kernels as K
     from e4s_b200.stylegan2.modconv import PreparedConv
     from e4s_b200.stylegan2 import modconv_bwd as MB

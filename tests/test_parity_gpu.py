@@ -430,6 +430,24 @@ def test_tcr_kernel_matches_simt(b, cin, cout, hw, up, ncls, kind):
     print(f"tcr-vs-simt rel err {e:.2e}")
 
 
+@pytest.mark.parametrize("ntile", ["32", "64", "128", "256"])
+@pytest.mark.parametrize("b,cin,cout,hw,up,ncls,kind", [
+    (1, 512, 512, 8, False, 12, "iid"),       # low-resolution layers of ONE face: the occupancy rule narrows the N tile
+    (1, 512, 512, 8, True, 3, "iid"),
+    (2, 256, 256, 16, False, 4, "blobs"),
+    (1, 128, 256, 32, True, 2, "iid"),
+])
+def test_tcr_kernel_every_n_tile_width(monkeypatch, ntile, b, cin, cout, hw, up, ncls, kind):
+    """csrc/modconv_tcr.cu:pick_ntile chooses the N-tile width by occupancy; every width it can choose (forced here with
+    E4S_B200_NTILE; widths a layer does not allow fall back to the automatic choice) gives the same result."""
+    monkeypatch.setenv("E4S_B200_NTILE", ntile)
+    K, prep, x, args = _tc_case(b, cin, cout, hw, up, ncls, kind, seed=cin + cout + hw)
+    ref = K.modconv3x3_fwd(x, prep.wt, *args)
+    out = K.modconv3x3_tcr_fwd(x, prep.w_hilo, *args)
+    torch.cuda.synchronize()
+    assert_close(out, ref, 1e-4, f"tcr vs simt, N tile {ntile}: {b},{cin},{cout},{hw},{up},{ncls},{kind}")
+
+
 @pytest.mark.parametrize("b,cin,cout,hw,up,ncls,kind", PRODUCTION_CASES)
 def test_tcr_kernel_production_shapes(b, cin, cout, hw, up, ncls, kind):
     K, prep, x, args = _tc_case(b, cin, cout, hw, up, ncls, kind, seed=cin + cout + hw)

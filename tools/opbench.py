@@ -46,6 +46,8 @@ def main():
     ap.add_argument("--conv", default="simt,tc")
     ap.add_argument("--layers", default="all")
     ap.add_argument("--prof", action="store_true", help="gen-4 kernel: per-role stall attribution of CTA 0 (e4s_tcr_set_profile)")
+    ap.add_argument("--only-conv", action="store_true", help="skip the HBM-bound kernels")
+    ap.add_argument("--once", action="store_true", help="one launch per layer, no warm-up (for `ncu --set full -k regex:modconv3x3`)")
     ap.add_argument("--unmasked", action="store_true", help="time the masked layers with a single region (no class passes)")
     args = ap.parse_args()
     B = args.batch
@@ -62,6 +64,13 @@ def main():
 
     # ---- upfirdn2d: the blur after the last up-sampling conv (largest call of the model) and friends
     fir = torch.tensor([1., 3., 3., 1.]); fir = (torch.outer(fir, fir) / 64 * 4).to(DEV)
+    hbm_rows(args, B, fir, flush, row)
+    conv_rows(args, B, fir, flush, row, res)
+
+
+def hbm_rows(args, B, fir, flush, row):
+    if args.only_conv:
+        return
     for c, h in [(32, 1025), (64, 513), (128, 257)]:
         x = torch.randn(B, c, h, h, device=DEV)
         ms = timeit(lambda: upfirdn2d(x, fir, pad=(1, 1)), flush=flush)
@@ -88,6 +97,9 @@ def main():
         row(f"torgb [{B},{h},{h},{cin}]", ms, 4.0 * B * h * h * (cin + 3), "GB/s")
         del xpm, skip
 
+
+
+def conv_rows(args, B, fir, flush, row, res):
     # ---- modulated convs, every 3x3 layer of the 1024 generator: (name, cin, cout, in_res, up, masked)
     layers = [("conv1@4", 512, 512, 4, 0, 1), ("c0^8", 512, 512, 4, 1, 1), ("c1@8", 512, 512, 8, 0, 1), ("c2^16", 512, 512, 8, 1, 1),
               ("c3@16", 512, 512, 16, 0, 1), ("c4^32", 512, 512, 16, 1, 1), ("c5@32", 512, 512, 32, 0, 1), ("c6^64", 512, 512, 32, 1, 1),
@@ -129,7 +141,7 @@ def main():
                 fn = lambda f=f: f(xpm, prep.w_hilo, s, dm, label, noise, nw, bias, bool(up), True)
             else:
                 fn = lambda: K.modconv3x3_fwd(xpm, prep.wt, s, dm, label, noise, nw, bias, bool(up), True)
-            ms = timeit(fn, iters=3, warmup=1, flush=flush)
+            ms = timeit(fn, iters=1, warmup=0, flush=flush) if args.once else timeit(fn, iters=3, warmup=1, flush=flush)
             total[mode] += ms
             row(f"modconv[{mode}] {name} {cin}->{cout} in{r} up{up} ncls{ncls}", ms, flops, "TFLOP/s")
             if args.prof and mode == "tcr":
