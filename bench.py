@@ -35,6 +35,11 @@ import torch
 
 METRIC = "1024x1024 faces/sec (mask-guided StyleGAN2 synthesis, 12 regions, K=13)"
 ALGO_GFLOP_PER_FACE = {1024: 148.1, 512: 118.8, 256: 89.5}   # 3x3 modulated convs, SURVEY.md section 8d
+# dram__bytes_read.sum + dram__bytes_write.sum per modulated-conv launch, mean over the 17 launches of one step of the default
+# workload (1024x1024, 16 faces, 12-region face masks), from the ncu --set full capture profiles/r1_ncu_tcr_17_layers.md
+# (15.67 GB per step against 14.90 GB algorithmic: input + output once in fp32, weights once)
+NCU_CONV_DRAM_BYTES_PER_LAUNCH = 921.9e6
+NCU_CONV_TENSOR_PIPE_PCT = 48.3                               # time-weighted sm__pipe_tensor_cycles_active, same capture
 
 
 def parse_args():
@@ -51,6 +56,9 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--gather", action="store_true",
                     help="N>1: also all-gather every rank's images inside the timed step (the path itself has no exchange step)")
+    ap.add_argument("--faceswap-pairs", type=int, default=8,
+                    help="also time steps 3-5 of scripts/face_swap.py (encoder, shape/texture swap, generator, blending masks) on "
+                         "this many (driven, target) pairs per GPU (BASELINE configs[3]: 64 pairs over 8 GPUs); 0 disables")
     ap.add_argument("--inversion-steps", type=int, default=20,
                     help="also time this many steps of the texture-vector optimisation (scripts/optimization.py:209-232, "
                          "l2 loss) on one face per GPU; 0 disables")
@@ -337,6 +345,7 @@ def run_ours(args):
     else:
         peak_tf, peak_src, hbm_gbs = 1590.0, "fallback (B200_PROFILING.md)", 6650.0
     roofline, kernels = None, {}
+    default_workload = (size, B, ncls, args.mask) == (1024, 16, 12, "faces")
     for name, (n, kms, work) in summary.items():
         kernels[name] = {"launches": n, "ms": round(kms, 3), "share": round(kms / ms, 4)}
     conv_names = [n for n in summary if n.startswith("e4s_modconv3x3")]
@@ -347,7 +356,10 @@ def run_ours(args):
         top = max(conv_names, key=lambda k: summary[k][1])
         ach = flops / (kms * 1e-3) / 1e12
         roofline = {"kernel": f"modulated 3x3 convolutions (all 17 StyledConv layers; dominant entry point {top})",
-                    "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
+                    "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+                    "traffic": NCU_CONV_DRAM_BYTES_PER_LAUNCH if default_workload else None,
+                    "traffic_source": "ncu --set full, mean of the 17 launches of one step (profiles/r1_ncu_tcr_17_layers.md)" if default_workload else None,
+                    "tensor_pipe_active_pct_ncu": NCU_CONV_TENSOR_PIPE_PCT if default_workload else None,
                     "peak_source": peak_src, "algorithmic_gflop_per_face": flops / 1e9 / (B * args.steps), "launches": n,
                     "avg_launch_ms": kms / n, "share_of_step": kms / ms,
                     "note": "achieved = ALGORITHMIC fp32 FLOPs / event time; the kernel issues 3 bf16 MMAs per algorithmic MAC "
@@ -410,6 +422,38 @@ def run_ours(args):
                      "faces_per_sec_100_steps": world / (ims * 100 * 1e-3), "loss_first": float(hist[0]), "loss_last": float(hist[-1]),
                      "config": f"one {size}x{size} face per GPU, {ncls} regions, Adam lr 1e-2, l2 loss, fresh noise per step"}
 
+    # ---- BASELINE configs[3]: face swapping, steps 3-5 of scripts/face_swap.py on (driven, target) pairs, sharded like faces
+    faceswap = None
+    if args.faceswap_pairs > 0:
+        from e4s_b200.face_swap import swap_faces
+        P = args.faceswap_pairs
+        g3 = torch.Generator().manual_seed(400 + rank)
+        driven, target = torch.randn(P, 3, size, size, generator=g3).to(dev), torch.randn(P, 3, size, size, generator=g3).to(dev)
+        labs = face_label_maps(2 * P, ncls, args.mask, seed=500 + rank)[:, 0].to(dev)
+        d_lab, t_lab = labs[0::2].contiguous(), labs[1::2].contiguous()        # source / target example masks, alternating
+        fs_steps = max(3, args.steps // 2)
+        for _ in range(2):
+            swap_faces(net, driven, target, d_lab, t_lab)
+        barrier()
+        K.LaunchStats.reset(False)
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(fs_steps):
+            res = swap_faces(net, driven, target, d_lab, t_lab)
+        f1.record()
+        barrier()
+        fms = f0.elapsed_time(f1) / fs_steps
+        fs_launches = K.LaunchStats.launches / fs_steps
+        if world > 1:
+            tf = torch.tensor([fms], device=dev)
+            dist.all_reduce(tf, op=dist.ReduceOp.MAX)
+            fms = float(tf.item())
+        faceswap = {"pairs_per_gpu": P, "steps_timed": fs_steps, "ms_per_step": fms, "pairs_per_sec": P * world / (fms * 1e-3),
+                    "launches_per_step": fs_launches,
+                    "config": f"{size}x{size} driven + target faces and their {ncls}-class parsing maps resident in HBM -> RGI encoder on "
+                              f"both, shape swap, texture swap, MLPs, generator, blending masks (e4s_b200.face_swap.swap_faces)"}
+        del driven, target, res
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         pick_cpu_threads(ncls)                                        # also warms the thread pool / allocator
@@ -429,7 +473,7 @@ def run_ours(args):
                            "parallelism": (f"dp{world}: faces sharded across ranks, weights replicated, no data-path collective"
                                            + (" + NCCL all-gather of the final images" if args.gather else "")) if world > 1 else "single GPU"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-                "kernels": kernels, "hbm_peak_gbs": hbm_gbs, "inversion": inversion}
+                "kernels": kernels, "hbm_peak_gbs": hbm_gbs, "inversion": inversion, "faceswap": faceswap}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -16,6 +16,7 @@
 // This replaces, per region per layer, the cuDNN dgrad AND wgrad the reference's autograd runs (model.py:277-316).
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cstdio>
 #include <cstdlib>
 #include <mutex>
 
@@ -43,6 +44,8 @@ struct Params {
     float* gs;             // [B, ncls, Cin] (atomic accumulate) or NULL
     int batch, h, w, cin, cout, ncls, act;
     int tiles_x, tiles_y, n_tiles, items, nslot_b;
+    int gsplit, hsplit;    // a (pixel tile, N tile) pair is cut into gsplit x hsplit work items: region passes g, g + gsplit, ...
+                           // and NPH / hsplit parity planes each; > 1 -> partial sums meet in gx by red.global.add
 };
 
 // ------------------------------------------------------------------------------------ PTX helpers
@@ -133,14 +136,22 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo_elem, float hi_elem) {
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
     return r;
 }
+__device__ __forceinline__ void red_add_f4(float* p, const float4& v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 __device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 
 
 struct Item {
-    int b, ty, tx, nt;
+    int b, ty, tx, nt, g, hq;
 };
 __device__ __forceinline__ Item decode_item(const Params& p, int it) {
     Item r;
+    const int nsub = p.gsplit * p.hsplit;
+    const int sub = it % nsub;
+    it /= nsub;
+    r.g = sub % p.gsplit;
+    r.hq = sub / p.gsplit;
     const int ptiles = p.tiles_x * p.tiles_y * p.batch;
     r.nt = it / ptiles;
     int pt = it - r.nt * ptiles;
@@ -168,7 +179,15 @@ __device__ __forceinline__ uint32_t halo_class_mask(const Params& p, const Item&
             if (NPH == 4) m |= (1u << min((int)lp[1], p.ncls - 1)) | (1u << min((int)lp[wo], p.ncls - 1)) | (1u << min((int)lp[wo + 1], p.ncls - 1));
         }
     }
-    return __reduce_or_sync(0xffffffffu, m);
+    m = __reduce_or_sync(0xffffffffu, m);
+    if (p.gsplit > 1) {                       // this work item's share of the region passes: every gsplit-th present region
+        uint32_t mine = 0;
+        int k = 0;
+        for (uint32_t cm = m; cm; cm &= cm - 1, ++k)
+            if (k % p.gsplit == it.g) mine |= cm & (0u - cm);
+        m = mine;
+    }
+    return m;
 }
 
 // NTI = input channels (N of the MMA) per work item; KC = output channels per K chunk; NPH = parity planes.
@@ -234,8 +253,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) modconv3x3_dgrad_tc_kernel(con
             const Item item = decode_item(p, it);
             const int npass = __popc(halo_class_mask<NPH>(p, item, lane));
             if (lane == 0) {
+                const int q0 = item.hq * (NPH / p.hsplit), q1 = q0 + NPH / p.hsplit;
                 for (int pass = 0; pass < npass; ++pass)
-                    for (int q = 0; q < NPH; ++q)
+                    for (int q = q0; q < q1; ++q)
                         for (int kc = 0; kc < nchunks; ++kc)
                             for (int tap = 0; tap < 9; ++tap)
                                 for (int hl = 0; hl < 2; ++hl) {
@@ -266,7 +286,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) modconv3x3_dgrad_tc_kernel(con
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_u + (uint32_t)(acc * N);
 #pragma unroll 1
-                for (int kk = 0; kk < NPH * nchunks; ++kk) {
+                for (int kk = 0; kk < (NPH / p.hsplit) * nchunks; ++kk) {
                     mbar_wait(bars0 + 8 * (A_FULL + sa), pa);
                     tc_fence_after();
                     const uint32_t ap = a0 + sa * A_STAGE;
@@ -315,7 +335,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) modconv3x3_dgrad_tc_kernel(con
             for (uint32_t cm = classes; cm; cm &= cm - 1) {
                 const int cls = __ffs(cm) - 1;
                 const float* dmc = p.demod ? p.demod + ((int64_t)item.b * p.ncls + cls) * p.cout : nullptr;
-                for (int q = 0; q < NPH; ++q) {
+                for (int q = item.hq * (NPH / p.hsplit); q < (item.hq + 1) * (NPH / p.hsplit); ++q) {
                     const int py = q >> 1, px = q & 1;
                     for (int kc = 0; kc < nchunks; ++kc) {
                         const int ch = kc * KC + 8 * c8;
@@ -398,6 +418,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) modconv3x3_dgrad_tc_kernel(con
             const bool mine = tx < TW && qy < p.h && qx < p.w;
             const int n0 = item.nt * NTI;
             const int64_t pix = ((int64_t)item.b * p.h + qy) * p.w + qx;
+            const bool partial = p.gsplit * p.hsplit > 1;       // several work items add into the same gx rows (zeroed by the host side)
             bool first = true;
             for (uint32_t cm = classes; cm; cm &= cm - 1) {
                 const int cls = __ffs(cm) - 1;
@@ -417,6 +438,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) modconv3x3_dgrad_tc_kernel(con
                             const float4 sv = __ldg(reinterpret_cast<const float4*>(sc + j * 32 + 4 * g));
                             float4 o = make_float4(__uint_as_float(r[4 * g]) * sv.x, __uint_as_float(r[4 * g + 1]) * sv.y,
                                                    __uint_as_float(r[4 * g + 2]) * sv.z, __uint_as_float(r[4 * g + 3]) * sv.w);
+                            if (partial) {
+                                red_add_f4(dst + 4 * g, o);
+                                continue;
+                            }
                             if (!first) {
                                 const float4 old = *reinterpret_cast<const float4*>(dst + 4 * g);
                                 o.x += old.x, o.y += old.y, o.z += old.z, o.w += old.w;
@@ -496,6 +521,30 @@ static int num_sms() {
     return n;
 }
 
+// One (pixel tile, N tile) pair is a serial chain of (regions in the tile) x NPH x Cout/KC x 9 weight slots with 4 MMAs
+// each, whatever the N width - MMA issue, not bandwidth, sets its length (~150 cycles per MMA and issuing warp).  The
+// 4x4 ... 32x32 layers of ONE face have 1-12 pixel tiles with every region in each: 2 CTAs ran 12 x 4 x 8 x 9 slots
+// back to back (2.2 ms per layer, profiles/r1_bwd_layers_wide_ntile.log).  When the pairs cannot fill the SMs, cut the
+// chain: region passes first (up to ncls ways), then parity planes; the partial sums meet in gx through vector
+// red.global.add (gx zeroed first) and in gs through the atomics the kernel uses anyway.
+// E4S_B200_DGRAD_SPLIT="G,H" forces a split (tests).
+static void choose_split(int64_t pairs, int ncls, int nph, int& gsplit, int& hsplit) {
+    gsplit = hsplit = 1;
+    if (const char* f = getenv("E4S_B200_DGRAD_SPLIT")) {
+        int g = 0, h = 0;
+        if (sscanf(f, "%d,%d", &g, &h) == 2 && g >= 1 && (h == 1 || h == 2 || h == 4)) {
+            gsplit = g < ncls ? g : ncls, hsplit = h < nph ? h : nph;
+            return;
+        }
+    }
+    const int sms = num_sms();
+    if (pairs >= 2 * sms) return;
+    // aim at ~4 work items per SM: the chains differ in length (regions per tile) and CTAs take items round-robin
+    const int64_t g = e4s_ceil_div(4 * sms, pairs);
+    gsplit = (int)(g < ncls ? g : ncls);
+    while (hsplit < nph && pairs * gsplit * hsplit < sms) hsplit *= 2;
+}
+
 template <int NTI, int KC, int NPH>
 static int launch(const void* wd_hilo, Params p, cudaStream_t st) {
     constexpr int ROWB = KC * 2;
@@ -515,9 +564,14 @@ static int launch(const void* wd_hilo, Params p, cudaStream_t st) {
     p.tiles_x = (int)e4s_ceil_div(p.w, TW);
     p.tiles_y = (int)e4s_ceil_div(p.h, TH);
     p.n_tiles = p.cin / NTI;
-    const int64_t items = (int64_t)p.tiles_x * p.tiles_y * p.batch * p.n_tiles;
+    const int64_t pairs = (int64_t)p.tiles_x * p.tiles_y * p.batch * p.n_tiles;
+    choose_split(pairs, p.label ? p.ncls : 1, NPH, p.gsplit, p.hsplit);
+    const int64_t items = pairs * p.gsplit * p.hsplit;
     if (items >= (1ll << 31)) return E4S_ERR_SHAPE;
     p.items = (int)items;
+    if (p.gsplit * p.hsplit > 1 && p.gx &&
+        cudaMemsetAsync(p.gx, 0, (size_t)p.batch * p.h * p.w * p.cin * sizeof(float), st) != cudaSuccess)
+        return (int)cudaGetLastError();
     int max_slots = (SMEM_BUDGET - A_BYTES - 1024) / B_SLOT;
     if (max_slots < 2) return E4S_ERR_SHAPE;
     p.nslot_b = max_slots > 8 ? 8 : (max_slots & ~1);      // even: (hi, lo) slot pairs never straddle the ring wrap
@@ -539,7 +593,7 @@ static int launch(const void* wd_hilo, Params p, cudaStream_t st) {
 // 38-MB weight set through their own L2 ports while 146 SMs idled (2.2 ms per layer, profiles/r1_bwd_layers_*.log).
 // Take the widest tile that still yields work for half the SMs, else the narrowest.  E4S_B200_NTILE=32|64|128|256
 // forces a width (tests).
-static int pick_ntile(int channels, int widest, int64_t pixel_tiles) {
+static int pick_ntile(int channels, int widest, int64_t pixel_tiles, int max_split = 1) {
     static const int cand[4] = {256, 128, 64, 32};
     if (const char* f = getenv("E4S_B200_NTILE")) {
         const int v = atoi(f);
@@ -550,7 +604,7 @@ static int pick_ntile(int channels, int widest, int64_t pixel_tiles) {
         const int c = cand[i];
         if (c > widest || channels % c != 0) continue;
         last = c;
-        if (pixel_tiles * (channels / c) >= num_sms() / 2) return c;
+        if (pixel_tiles * (channels / c) * max_split >= num_sms() / 2) return c;
     }
     return last;
 }
@@ -558,7 +612,7 @@ static int pick_ntile(int channels, int widest, int64_t pixel_tiles) {
 template <int KC, int NPH>
 static int dispatch_n(const void* wd, const Params& p, cudaStream_t st) {
     const int64_t pixel_tiles = e4s_ceil_div(p.w, TW) * e4s_ceil_div(p.h, TH) * p.batch;
-    switch (pick_ntile(p.cin, 256, pixel_tiles)) {
+    switch (pick_ntile(p.cin, 256, pixel_tiles, (p.label ? p.ncls : 1) * NPH)) {
         case 256: return launch<256, KC, NPH>(wd, p, st);
         case 128: return launch<128, KC, NPH>(wd, p, st);
         case 64: return launch<64, KC, NPH>(wd, p, st);
@@ -577,7 +631,7 @@ extern "C" int e4s_modconv3x3_bwd_tc(const float* gy, const float* y, const floa
     E4S_REQUIRE(batch > 0 && h > 0 && w > 0 && cin > 0 && cout > 0 && ncls > 0 && ncls <= 32, E4S_ERR_ARG);
     E4S_REQUIRE((cin % 32) == 0 && (cout % 32) == 0, E4S_ERR_SHAPE);
     E4S_REQUIRE(label || ncls == 1, E4S_ERR_ARG);
-    tcd::Params p{gy, y, x, s, demod, label, gx, gs, batch, h, w, cin, cout, ncls, act, 0, 0, 0, 0, 0};
+    tcd::Params p{gy, y, x, s, demod, label, gx, gs, batch, h, w, cin, cout, ncls, act, 0, 0, 0, 0, 0, 1, 1};
     cudaStream_t st = (cudaStream_t)stream;
     const bool k64 = (cout % 64) == 0;
     if (!up) return k64 ? tcd::dispatch_n<64, 1>(wd_hilo_bf16, p, st) : tcd::dispatch_n<32, 1>(wd_hilo_bf16, p, st);

@@ -118,16 +118,17 @@ def create_masks(mask, outer_dilation=0, operation="dilation"):
 
 
 def swap_comp_style_vector(style_vectors1, style_vectors2, comp_indices=(), belowFace_interpolation=False):
-    """scripts/face_swap.py:117-146 without the two host synchronisations of its `if torch.sum(...) == 0` tests: the
-    empty-region decisions are taken on the device with `torch.where`."""
+    """scripts/face_swap.py:117-146 for a BATCH of faces and without the two host synchronisations of its
+    `if torch.sum(...) == 0` tests: the empty-region decisions (no ear / no teeth region in the source) are taken per
+    sample on the device with `torch.where`.  For one face ([1, ncls, C], the reference's case) the result is identical."""
     assert comp_indices is not None
     out = style_vectors1.clone()
     idx = list(comp_indices)
     if idx:
         out[:, idx, :] = style_vectors2[:, idx, :]
-    no_ear = (style_vectors2[:, 7, :].sum() == 0)
+    no_ear = style_vectors2[:, 7, :].sum(dim=-1, keepdim=True) == 0
     out[:, 7, :] = torch.where(no_ear, (style_vectors1[:, 7, :] + style_vectors2[:, 7, :]) / 2, out[:, 7, :])
-    no_teeth = (style_vectors2[:, 9, :].sum() == 0)
+    no_teeth = style_vectors2[:, 9, :].sum(dim=-1, keepdim=True) == 0
     out[:, 9, :] = torch.where(no_teeth, style_vectors1[:, 9, :], out[:, 9, :])
     if belowFace_interpolation:
         out[:, 8, :] = (style_vectors1[:, 8, :] + style_vectors2[:, 8, :]) / 2

@@ -211,6 +211,21 @@ def test_dgrad_tc_every_n_tile_width(monkeypatch, ntile, b, cin, cout, hw, up, n
     _dgrad_case(b, cin, cout, hw, up, ncls, kind, act)
 
 
+@pytest.mark.parametrize("split", ["1,1", "3,1", "2,2", "12,4", "5,4"])
+@pytest.mark.parametrize("b,cin,cout,hw,up,ncls,kind,act", [
+    (1, 512, 512, 4, False, 12, "iid", True),
+    (1, 512, 512, 8, True, 12, "iid", True),
+    (2, 128, 64, 20, True, 5, "blobs", True),        # tiles with fewer regions than the split: some work items are empty
+    (1, 64, 64, 24, False, 1, "blobs", False),       # single region: the region split degenerates, the parity split does not apply
+    (1, 64, 32, 24, True, 1, "blobs", True),         # single region, up-sampling: parity split only
+])
+def test_dgrad_tc_split_work_items(monkeypatch, split, b, cin, cout, hw, up, ncls, kind, act):
+    """csrc/modconv_dgrad_tc.cu:choose_split cuts a tile's chain of region passes / parity planes into several work items
+    whose partial sums meet in gx (red.global.add) and gs (atomics): every split gives the same gradients."""
+    monkeypatch.setenv("E4S_B200_DGRAD_SPLIT", split)
+    _dgrad_case(b, cin, cout, hw, up, ncls, kind, act)
+
+
 def _dgrad_case(b, cin, cout, hw, up, ncls, kind, act):
     from e4s_b200 import kernels as K
     from e4s_b200.stylegan2.modconv import PreparedConv

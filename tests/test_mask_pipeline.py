@@ -196,3 +196,48 @@ def test_swapped_mask_drives_the_generator(golden):
     onehot = labelMap2OneHot(res[None, None], 12)
     pyr = LabelPyramid.from_mask(onehot)
     assert torch.equal(pyr.at(*res.shape), res[None])
+
+
+@pytest.mark.gpu
+def test_swap_faces_pipeline_matches_oracle_composition(golden):
+    """e4s_b200.face_swap.swap_faces (steps 3-5 + blending masks of scripts/face_swap.py, batched on the device) against
+    the same steps composed on the CPU from the oracle's restatements: encoder -> shape swap -> texture swap -> MLPs ->
+    generator.  Labels / masks bit-exact, images within the fp32 bar."""
+    import types
+    from conftest import REL_TOL, assert_close
+    from oracle import e4s_oracle as O
+    from e4s_b200.face_swap import swap_faces
+    from e4s_b200.networks import Net3
+    opts = types.SimpleNamespace(fsencoder_type="psp", remaining_layer_idx=13, num_seg_cls=12, out_size=64,
+                                 train_G=False, start_from_latent_avg=True, learn_in_w=False)
+    net = Net3(opts).eval()
+    st = O.synthetic_state({k: tuple(v.shape) for k, v in net.state_dict().items()}, salt=5)
+    net.load_state_dict(st)
+    net = net.cuda()
+    g = torch.Generator().manual_seed(21)
+    lat = 0.1 * torch.randn(18, 512, generator=g)
+    net.latent_avg = lat.cuda()
+    rnd = synthetic_label_maps(31, 2, 128, 128)
+    d_lab, t_lab = torch.from_numpy(rnd[:1].copy()), torch.from_numpy(rnd[1:].copy())
+    d_lab[(d_lab == 7) | (d_lab == 9)] = 6                  # a source without ears and teeth: both special cases of the texture swap
+    driven, target = torch.randn(1, 3, 256, 256, generator=g), torch.randn(1, 3, 256, 256, generator=g)
+    _, _, _, noise = O.synthetic_inputs(1, 12, 64, 128, seed=9)
+    out = swap_faces(net, driven.cuda(), target.cuda(), d_lab.cuda(), t_lab.cuda(), noise=[n.cuda() for n in noise])
+    # ---- the same on the CPU
+    d_vec, _ = O.get_style_vectors(st, driven, O.label_to_onehot(d_lab[:, None].long(), 12))
+    t_vec, _ = O.get_style_vectors(st, target, O.label_to_onehot(t_lab[:, None].long(), 12))
+    res, hole = MO.swap_head_mask(d_lab[0].numpy(), t_lab[0].numpy())
+    comp = sorted(set(range(12)) - {0, 4, 11, 10})
+    vec = torch.from_numpy(MO.swap_comp_style_vector(t_vec.numpy(), d_vec.numpy(), comp))
+    assert float(d_vec[:, 9].abs().sum()) == 0.0 and float(d_vec[:, 7].abs().sum()) == 0.0     # both branches are taken
+    codes = O.cal_style_codes(st, vec, lat, 13)
+    gst = {k[2:]: v for k, v in st.items() if k.startswith("G.")}
+    ref_img, _ = O.generator_forward(gst, codes, O.label_to_onehot(torch.from_numpy(res)[None, None].long(), 12), noise, 64, 13)
+    fg = MO.foreground_mask(res, hole)
+    _, border, full = MO.create_masks(fg, 5, "dilation")
+    assert np.array_equal(out.swapped_label[0].cpu().numpy(), res) and np.array_equal(out.hole_map[0].cpu().numpy(), hole)
+    assert np.array_equal(out.content_mask[0, 0].cpu().numpy(), fg.astype(np.float32))
+    assert np.array_equal(out.border_mask[0, 0].cpu().numpy(), border.astype(np.float32))
+    assert np.array_equal(out.full_mask[0, 0].cpu().numpy(), full.astype(np.float32))
+    assert_close(out.style_vectors, vec, REL_TOL, "swapped texture vectors")
+    assert_close(out.image, ref_img, REL_TOL, "swapped face")

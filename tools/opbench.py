@@ -47,6 +47,7 @@ def main():
     ap.add_argument("--layers", default="all")
     ap.add_argument("--prof", action="store_true", help="gen-4 kernel: per-role stall attribution of CTA 0 (e4s_tcr_set_profile)")
     ap.add_argument("--only-conv", action="store_true", help="skip the HBM-bound kernels")
+    ap.add_argument("--only-hbm", action="store_true", help="skip the modulated convolutions")
     ap.add_argument("--once", action="store_true", help="one launch per layer, no warm-up (for `ncu --set full -k regex:modconv3x3`)")
     ap.add_argument("--unmasked", action="store_true", help="time the masked layers with a single region (no class passes)")
     args = ap.parse_args()
@@ -100,6 +101,10 @@ def hbm_rows(args, B, fir, flush, row):
 
 
 def conv_rows(args, B, fir, flush, row, res):
+    if args.only_hbm:
+        os.makedirs(os.path.dirname(args.out), exist_ok=True)
+        json.dump(res, open(args.out, "w"), indent=1)
+        return
     # ---- modulated convs, every 3x3 layer of the 1024 generator: (name, cin, cout, in_res, up, masked)
     layers = [("conv1@4", 512, 512, 4, 0, 1), ("c0^8", 512, 512, 4, 1, 1), ("c1@8", 512, 512, 8, 0, 1), ("c2^16", 512, 512, 8, 1, 1),
               ("c3@16", 512, 512, 16, 0, 1), ("c4^32", 512, 512, 16, 1, 1), ("c5@32", 512, 512, 32, 0, 1), ("c6^64", 512, 512, 32, 1, 1),
