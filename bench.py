@@ -425,34 +425,37 @@ def run_ours(args):
     # ---- BASELINE configs[3]: face swapping, steps 3-5 of scripts/face_swap.py on (driven, target) pairs, sharded like faces
     faceswap = None
     if args.faceswap_pairs > 0:
-        from e4s_b200.face_swap import swap_faces
-        P = args.faceswap_pairs
-        g3 = torch.Generator().manual_seed(400 + rank)
-        driven, target = torch.randn(P, 3, size, size, generator=g3).to(dev), torch.randn(P, 3, size, size, generator=g3).to(dev)
-        labs = face_label_maps(2 * P, ncls, args.mask, seed=500 + rank)[:, 0].to(dev)
-        d_lab, t_lab = labs[0::2].contiguous(), labs[1::2].contiguous()        # source / target example masks, alternating
-        fs_steps = max(3, args.steps // 2)
-        for _ in range(2):
-            swap_faces(net, driven, target, d_lab, t_lab)
-        barrier()
-        K.LaunchStats.reset(False)
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record()
-        for _ in range(fs_steps):
-            res = swap_faces(net, driven, target, d_lab, t_lab)
-        f1.record()
-        barrier()
-        fms = f0.elapsed_time(f1) / fs_steps
-        fs_launches = K.LaunchStats.launches / fs_steps
-        if world > 1:
-            tf = torch.tensor([fms], device=dev)
-            dist.all_reduce(tf, op=dist.ReduceOp.MAX)
-            fms = float(tf.item())
-        faceswap = {"pairs_per_gpu": P, "steps_timed": fs_steps, "ms_per_step": fms, "pairs_per_sec": P * world / (fms * 1e-3),
-                    "launches_per_step": fs_launches,
-                    "config": f"{size}x{size} driven + target faces and their {ncls}-class parsing maps resident in HBM -> RGI encoder on "
-                              f"both, shape swap, texture swap, MLPs, generator, blending masks (e4s_b200.face_swap.swap_faces)"}
-        del driven, target, res
+        try:
+            from e4s_b200.face_swap import swap_faces
+            P = args.faceswap_pairs
+            g3 = torch.Generator().manual_seed(400 + rank)
+            driven, target = torch.randn(P, 3, size, size, generator=g3).to(dev), torch.randn(P, 3, size, size, generator=g3).to(dev)
+            labs = face_label_maps(2 * P, ncls, args.mask, seed=500 + rank)[:, 0].to(dev)
+            d_lab, t_lab = labs[0::2].contiguous(), labs[1::2].contiguous()        # source / target example masks, alternating
+            fs_steps = max(3, args.steps // 2)
+            for _ in range(2):
+                swap_faces(net, driven, target, d_lab, t_lab)
+            barrier()
+            K.LaunchStats.reset(False)
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for _ in range(fs_steps):
+                res = swap_faces(net, driven, target, d_lab, t_lab)
+            f1.record()
+            barrier()
+            fms = f0.elapsed_time(f1) / fs_steps
+            fs_launches = K.LaunchStats.launches / fs_steps
+            if world > 1:
+                tf = torch.tensor([fms], device=dev)
+                dist.all_reduce(tf, op=dist.ReduceOp.MAX)
+                fms = float(tf.item())
+            faceswap = {"pairs_per_gpu": P, "steps_timed": fs_steps, "ms_per_step": fms, "pairs_per_sec": P * world / (fms * 1e-3),
+                        "launches_per_step": fs_launches,
+                        "config": f"{size}x{size} driven + target faces and their {ncls}-class parsing maps resident in HBM -> RGI encoder on "
+                                  f"both, shape swap, texture swap, MLPs, generator, blending masks (e4s_b200.face_swap.swap_faces)"}
+            del driven, target, res
+        except Exception as exc:                                      # reported, never hidden; the headline metric stands on its own
+            faceswap = {"error": repr(exc)[:300]}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -971,7 +971,10 @@ int dispatch(const void* w_hilo_bf16, Params p, int up, cudaStream_t st) {
     }
     const int nt = pick_ntile(cout, 64, pixel_tiles);
     if (k64) {
-        if (nt == 64) return launch<64, 64, 4>(w_hilo_bf16, p, st);
+        if (nt == 64) {
+            const int rc = launch<64, 64, 4>(w_hilo_bf16, p, st);
+            if (rc != E4S_ERR_SHAPE) return rc;              // > 19 regions: the style table does not fit next to 32-KB weight slots
+        }
         return launch<32, 64, 4>(w_hilo_bf16, p, st);
     }
     return launch<32, 32, 4>(w_hilo_bf16, p, st);

@@ -245,6 +245,21 @@ def test_generator_golden(golden, tag, size, K, B, nc, msz, kind):
     print(f"{tag}: image max-rel err {e:.2e}")
 
 
+@pytest.mark.parametrize("path", ["auto", "simt"])
+@pytest.mark.parametrize("size,B,nc,kind", [(64, 2, 19, "blobs"), (64, 1, 19, "iid"), (32, 1, 32, "iid"), (32, 3, 1, "blobs")])
+def test_generator_region_count_sweep_vs_oracle(monkeypatch, path, size, B, nc, kind):
+    """12 regions is the default, 19 (the raw parser label count) the sweep point; 32 is the most
+    the kernels' region bit masks hold and 1 the degenerate case.  Tensor-core and exact-fp32 paths against the CPU oracle."""
+    monkeypatch.setenv("E4S_B200_CONV", path)
+    G, st = _generator(size, 13)
+    codes, mask, _, noise = O.synthetic_inputs(B, nc, size, 2 * size, seed=size + nc, kind=kind)
+    with torch.no_grad():
+        img, _, feats = G([cu(codes)], None, cu(mask), input_is_latent=True, noise=[cu(n) for n in noise])
+        ref_img, ref_feats = O.generator_forward(st, codes, mask, noise, size, 13)
+    assert_close(img, ref_img, REL_TOL, f"{nc} regions, image")
+    assert_close(feats, ref_feats, REL_TOL, f"{nc} regions, feats")
+
+
 def test_generator_api_surface():
     G, _ = _generator(32, 13)
     assert G.n_latent == 8 and G.num_layers == 7 and len(G.convs) == 6 and len(G.to_rgbs) == 3
