@@ -59,6 +59,12 @@ def parse_args():
     ap.add_argument("--faceswap-pairs", type=int, default=8,
                     help="also time steps 3-5 of scripts/face_swap.py (encoder, shape/texture swap, generator, blending masks) on "
                          "this many (driven, target) pairs per GPU (BASELINE configs[3]: 64 pairs over 8 GPUs); 0 disables")
+    ap.add_argument("--gpen-batch", type=int, default=16,
+                    help="also time GPEN-BFR-512's FullGenerator (stage 2 of scripts/face_swap.py:208; e4s_b200.gpen) on this many "
+                         "512x512 faces per GPU; 0 disables")
+    ap.add_argument("--inversion-batch", type=int, default=8,
+                    help="also run one complete 100-step inversion of this many faces AT ONCE per GPU (independent faces, one "
+                         "optimiser over [B, ncls, 1280]); 0 disables")
     ap.add_argument("--inversion-steps", type=int, default=20,
                     help="also time this many steps of the texture-vector optimisation (scripts/optimization.py:209-232, "
                          "l2 loss) on one face per GPU; 0 disables")
@@ -417,7 +423,35 @@ def run_ours(args):
                        "loss_last": float(ghist[-1]), "faces_per_sec_100_steps": world / (gtot * 1e-3)}
         except Exception as exc:                                  # reported, never hidden
             graphed = {"error": repr(exc)[:300]}
-        inversion = {"steps_timed": args.inversion_steps, "ms_per_step": ims, "launches_per_step": inv_launches / args.inversion_steps,
+        batched = None
+        if args.inversion_batch > 1:
+            # independent faces optimised side by side: the low-resolution layers of one face cannot fill the GPU
+            try:
+                nb = args.inversion_batch
+                onehot_b = onehot_dev[:nb].contiguous() if onehot_dev.shape[0] >= nb else onehot_dev[:1].expand(nb, -1, -1, -1).contiguous()
+                svb = 0.5 * torch.randn(nb, ncls, 1280, generator=g2).to(dev)
+                with torch.no_grad():
+                    target_b, _, _ = net.gen_img(None, net.cal_style_codes(0.5 * torch.randn(nb, ncls, 1280, generator=g2).to(dev)), onehot_b)
+                invert(net, target_b, onehot_b, style_vectors=svb, steps=6, cuda_graph=True)                   # capture warm-up
+                barrier()
+                b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                b0.record()
+                bstats = {}
+                _, _, bhist = invert(net, target_b, onehot_b, style_vectors=svb, steps=100, cuda_graph=True, stats=bstats)
+                b1.record()
+                barrier()
+                btot = b0.elapsed_time(b1)
+                if world > 1:
+                    tb = torch.tensor([btot], device=dev)
+                    dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+                    btot = float(tb.item())
+                batched = {"faces_per_gpu": nb, "ms_total_100_steps": btot, "ms_per_replayed_step": bstats.get("replay_ms_per_step"),
+                           "loss_first": float(bhist[0]), "loss_last": float(bhist[-1]),
+                           "faces_per_sec_100_steps": nb * world / (btot * 1e-3)}
+                del target_b, svb, onehot_b
+            except Exception as exc:                              # reported, never hidden
+                batched = {"error": repr(exc)[:300]}
+        inversion = {"steps_timed": args.inversion_steps, "ms_per_step": ims, "batched": batched, "launches_per_step": inv_launches / args.inversion_steps,
                      "cuda_graph": graphed, "kernels": inv_kernels,
                      "faces_per_sec_100_steps": world / (ims * 100 * 1e-3), "loss_first": float(hist[0]), "loss_last": float(hist[-1]),
                      "config": f"one {size}x{size} face per GPU, {ncls} regions, Adam lr 1e-2, l2 loss, fresh noise per step"}
@@ -457,6 +491,42 @@ def run_ours(args):
         except Exception as exc:                                      # reported, never hidden; the headline metric stands on its own
             faceswap = {"error": repr(exc)[:300]}
 
+    # ---- GPEN's generator on the same kernels (512x512 restoration, stage 2 of every swap)
+    gpen = None
+    if args.gpen_batch > 0:
+        try:
+            from e4s_b200.gpen.gpen_model import FullGenerator
+            from oracle import gpen_oracle as GO                       # synthetic_state only: stand-in for the checkpoint
+            gm = FullGenerator(512, 512, 8, channel_multiplier=2, narrow=1).eval()
+            gm.load_state_dict(GO.synthetic_state(512, salt=512))
+            gm = gm.to(dev)
+            gx = torch.randn(args.gpen_batch, 3, 512, 512, generator=torch.Generator().manual_seed(600 + rank)).to(dev)
+            g_steps = max(3, args.steps // 2)
+            with torch.no_grad():
+                for _ in range(3):
+                    gm(gx)
+                barrier()
+                K.LaunchStats.reset(False)
+                p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                p0.record()
+                for _ in range(g_steps):
+                    gm(gx)
+                p1.record()
+                barrier()
+            gms = p0.elapsed_time(p1) / g_steps
+            g_launches = K.LaunchStats.launches / g_steps
+            if world > 1:
+                tg2 = torch.tensor([gms], device=dev)
+                dist.all_reduce(tg2, op=dist.ReduceOp.MAX)
+                gms = float(tg2.item())
+            gpen = {"faces_per_gpu": args.gpen_batch, "steps_timed": g_steps, "ms_per_step": gms,
+                    "faces_per_sec": args.gpen_batch * world / (gms * 1e-3), "launches_per_step": g_launches,
+                    "config": "GPEN-BFR-512 FullGenerator (size 512, 8 mapping layers, channel multiplier 2, concatenated encoder maps), "
+                              "512x512 inputs resident in HBM, random-init weights"}
+            del gm, gx
+        except Exception as exc:                                      # reported, never hidden
+            gpen = {"error": repr(exc)[:300]}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         pick_cpu_threads(ncls)                                        # also warms the thread pool / allocator
@@ -476,7 +546,7 @@ def run_ours(args):
                            "parallelism": (f"dp{world}: faces sharded across ranks, weights replicated, no data-path collective"
                                            + (" + NCCL all-gather of the final images" if args.gather else "")) if world > 1 else "single GPU"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-                "kernels": kernels, "hbm_peak_gbs": hbm_gbs, "inversion": inversion, "faceswap": faceswap}
+                "kernels": kernels, "hbm_peak_gbs": hbm_gbs, "inversion": inversion, "faceswap": faceswap, "gpen": gpen}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
