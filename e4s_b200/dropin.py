@@ -9,9 +9,14 @@ After `install()`, these reference module names resolve to the mirrors in this p
     src.models.encoders.psp_encoders   -> e4s_b200.encoders.psp_encoders   (FSEncoder_PSP)
     src.models.encoders.helpers        -> e4s_b200.encoders.helpers
     src.models.networks                -> e4s_b200.networks                (Net3, LocalMLP)
+    src.pretrained.gpen.face_model.gpen_model -> e4s_b200.gpen.gpen_model  (FullGenerator, Generator, ...; inference classes)
+    src.utils.swap_face_mask           -> e4s_b200.masks                   (swap_head_mask_revisit_considerGlass on the GPU)
     src.utils.torch_utils.labelMap2OneHot is left alone (it already runs on the GPU); e4s_b200.masks has the kernel.
 
-Everything else of the reference tree (scripts, options, datasets, criteria, pretrained/*) keeps importing from
+(`src.utils.morphology` is NOT overlaid: e4s_b200.masks.dilation / erosion implement the flat-box case the swap pipeline
+uses, not the module's whole grey-scale API; import them explicitly, INTEGRATION.md.)
+
+Everything else of the reference tree (scripts, options, datasets, criteria, the other pretrained/* nets) keeps importing from
 the reference checkout, which must be on sys.path as usual.
 """
 import importlib
@@ -27,11 +32,14 @@ _MAP = {
     "src.models.encoders.psp_encoders": "e4s_b200.encoders.psp_encoders",
     "src.models.encoders.helpers": "e4s_b200.encoders.helpers",
     "src.models.networks": "e4s_b200.networks",
+    "src.pretrained.gpen.face_model.gpen_model": "e4s_b200.gpen.gpen_model",
+    "src.utils.swap_face_mask": "e4s_b200.masks",
 }
 
 
 def install() -> None:
-    for parent in ("src", "src.models", "src.models.stylegan2", "src.models.encoders"):
+    for parent in ("src", "src.models", "src.models.stylegan2", "src.models.encoders", "src.utils", "src.pretrained",
+                   "src.pretrained.gpen", "src.pretrained.gpen.face_model"):
         if parent not in sys.modules:
             try:
                 importlib.import_module(parent)          # the reference checkout, if it is on sys.path

@@ -213,7 +213,11 @@ int e4s_modconv3x3_bwd_f32(const float* gy, const float* y, const float* x, cons
                            const float* demod, const uint8_t* label, float* gx, float* gs, int batch, int h, int w,
                            int cin, int cout, int ncls, int up, int act, void* stream);
 /* Tensor-core (tcgen05) implementation of e4s_modconv3x3_bwd_f32 for cin % 32 == 0 and cout % 32 == 0.
- * wd_hilo_bf16: [2 (hi, lo)][nphase][9][Cin][Cout] = forward weights with taps flipped, K-major over Cout. */
+ * wd_hilo_bf16: [2 (hi, lo)][nphase][9][Cin][Cout] = forward weights with taps flipped, K-major over Cout.
+ * When a launch has too few (pixel tile, channel tile) pairs to occupy the GPU, a pair's region passes / parity planes
+ * are spread over several CTAs whose partial sums meet in gx by red.global.add: gx is then zeroed first by a memset
+ * enqueued on `stream` (no allocation, no synchronisation), and the summation order - hence the last bits of gx -
+ * may differ between runs. */
 int e4s_modconv3x3_bwd_tc(const float* gy, const float* y, const float* x, const void* wd_hilo_bf16, const float* s,
                           const float* demod, const uint8_t* label, float* gx, float* gs, int batch, int h, int w,
                           int cin, int cout, int ncls, int up, int act, void* stream);

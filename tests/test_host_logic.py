@@ -93,3 +93,27 @@ def test_bench_reference_arm_emits_contract_line():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["value"] == line["value"]
     assert line["e2e"] == {"value": line["value"], "unit": "faces/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert line["steps"] == 1 and line["n_gpus"] == 1 and line["gpu_launches"] == 0
+
+
+def test_dropin_overlay_resolves_reference_import_paths():
+    """e4s_b200.dropin.install() points the reference's module names at this package (run in a subprocess: it edits
+    sys.modules).  Works without the reference checkout on sys.path - the GPU box has none."""
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "import e4s_b200.dropin as d; d.install()\n"
+        "from src.models.networks import Net3\n"
+        "from src.models.stylegan2.model import Generator, StyledConv\n"
+        "from src.models.stylegan2.op import upfirdn2d, fused_leaky_relu, FusedLeakyReLU, conv2d_gradfix\n"
+        "from src.models.encoders.psp_encoders import FSEncoder_PSP\n"
+        "from src.pretrained.gpen.face_model.gpen_model import FullGenerator\n"
+        "from src.utils.swap_face_mask import swap_head_mask_revisit_considerGlass\n"
+        "import e4s_b200.networks, e4s_b200.gpen.gpen_model, e4s_b200.masks\n"
+        "assert Net3 is e4s_b200.networks.Net3 and FullGenerator is e4s_b200.gpen.gpen_model.FullGenerator\n"
+        "assert swap_head_mask_revisit_considerGlass is e4s_b200.masks.swap_head_mask_revisit_considerGlass\n"
+        "print('ok')\n") % ROOT
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=os.path.dirname(ROOT))
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
