@@ -33,7 +33,7 @@ if ROOT not in sys.path:
 import numpy as np
 import torch
 
-METRIC = "1024x1024 faces/sec (mask-guided StyleGAN2 synthesis, 12 regions, K=13)"
+METRIC = "{size}x{size} faces/sec (mask-guided StyleGAN2 synthesis, {ncls} regions, K=13)"
 ALGO_GFLOP_PER_FACE = {1024: 148.1, 512: 118.8, 256: 89.5}   # 3x3 modulated convs, SURVEY.md section 8d
 # dram__bytes_read.sum + dram__bytes_write.sum per modulated-conv launch, mean over the 17 launches of one step of the default
 # workload (1024x1024, 16 faces, 12-region face masks), from the ncu --set full capture profiles/r1_ncu_tcr_17_layers.md
@@ -245,14 +245,14 @@ def run_reference(args):
     val = 1.0 / sec
     cores = torch.get_num_threads()
     sample = f"{args.steps} steps x one full {args.size}x{args.size} face (B=1, {args.ncls} regions, K=13), fp32, torch CPU"
-    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "faces/s", "n_gpus": args.gpus, "steps": args.steps,
+    line = {"impl": "reference", "metric": METRIC.format(size=args.size, ncls=args.ncls), "value": val, "unit": "faces/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": max(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.size}x{args.size} synthesis, CPU reference path, 1 face per step", "ncls": args.ncls},
             "cpu_baseline": {"value": val, "unit": "faces/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "faces/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------ our arm
@@ -537,7 +537,7 @@ def run_ours(args):
                          f"oracle (fp32, torch CPU; thread count = fastest of 8/16/32/64/all on a 64x64 probe)"}
 
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": "faces/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        line = {"metric": METRIC.format(size=args.size, ncls=args.ncls), "value": value, "unit": "faces/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": f"{size}x{size} synthesis, batch {B} per GPU, {ncls} regions, K=13 (BASELINE configs[1])",
@@ -547,13 +547,30 @@ def run_ours(args):
                                            + (" + NCCL all-gather of the final images" if args.gather else "")) if world > 1 else "single GPU"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
                 "kernels": kernels, "hbm_peak_gbs": hbm_gbs, "inversion": inversion, "faceswap": faceswap, "gpen": gpen}
-        print(json.dumps(line), flush=True)
+        emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
+_OUT_FD = None
+
+
+def emit(text: str) -> None:
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner to stdout when
+    NCCL_DEBUG is set, as it is on the GPU boxes), so main() points file descriptor 1 at stderr for the whole run and the
+    result line goes to the process's original stdout."""
+    if _OUT_FD is None:
+        print(text, flush=True)
+    else:
+        os.write(_OUT_FD, (text + "\n").encode())
+
+
 def main():
+    global _OUT_FD
     args = parse_args()
+    sys.stdout.flush()
+    _OUT_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
