@@ -562,7 +562,9 @@ def emit(text: str) -> None:
     if _OUT_FD is None:
         print(text, flush=True)
     else:
-        os.write(_OUT_FD, (text + "\n").encode())
+        data = (text + "\n").encode()
+        while data:
+            data = data[os.write(_OUT_FD, data):]
 
 
 def main():
