@@ -88,11 +88,11 @@ def face_label_maps(batch: int, ncls: int, kind: str, seed: int) -> torch.Tensor
 
 def build_net(size: int, ncls: int, device):
     from e4s_b200.networks import Net3
-    from oracle import e4s_oracle as O      # synthetic_state only: a stand-in for the checkpoint that cannot be downloaded
+    from e4s_b200.synthetic import synthetic_state      # seeded stand-in for the checkpoint that cannot be downloaded
     opts = types.SimpleNamespace(fsencoder_type="psp", remaining_layer_idx=13, num_seg_cls=ncls, out_size=size,
                                  train_G=False, start_from_latent_avg=True, learn_in_w=False)
     net = Net3(opts).eval()
-    state = O.synthetic_state({k: tuple(v.shape) for k, v in net.state_dict().items()}, salt=size)
+    state = synthetic_state({k: tuple(v.shape) for k, v in net.state_dict().items()}, salt=size)
     net.load_state_dict(state)
     net = net.to(device)
     net.latent_avg = torch.zeros(18, 512, device=device)
@@ -496,9 +496,9 @@ def run_ours(args):
     if args.gpen_batch > 0:
         try:
             from e4s_b200.gpen.gpen_model import FullGenerator
-            from oracle import gpen_oracle as GO                       # synthetic_state only: stand-in for the checkpoint
+            from e4s_b200.synthetic import load_synthetic
             gm = FullGenerator(512, 512, 8, channel_multiplier=2, narrow=1).eval()
-            gm.load_state_dict(GO.synthetic_state(512, salt=512))
+            load_synthetic(gm, salt=512, parameters_only=True)         # the blur / up-sampling FIR buffers keep their registered values
             gm = gm.to(dev)
             gx = torch.randn(args.gpen_batch, 3, 512, 512, generator=torch.Generator().manual_seed(600 + rank)).to(dev)
             g_steps = max(3, args.steps // 2)

@@ -117,3 +117,24 @@ def test_dropin_overlay_resolves_reference_import_paths():
         "print('ok')\n") % ROOT
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=os.path.dirname(ROOT))
     assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
+
+
+def test_package_synthetic_state_equals_the_oracles():
+    """bench.py builds its random-init models with e4s_b200.synthetic (the product package may not import the oracle); the
+    golden vectors were generated with the oracle's copy of the recipe.  The two are bit-identical, and loading parameters
+    only leaves GPEN's registered FIR buffers equal to what the oracle's GPEN state holds."""
+    from e4s_b200.synthetic import synthetic_state, load_synthetic
+    from oracle import gpen_oracle as GO
+    from e4s_b200.gpen.gpen_model import FullGenerator
+    shapes = dict(O.generator_param_shapes(64))
+    shapes.update(O.mlp_param_shapes(12))
+    shapes.update(O.encoder_param_shapes())
+    a, b = synthetic_state(shapes, salt=64), O.synthetic_state(shapes, salt=64)
+    assert a.keys() == b.keys() and all(torch.equal(a[k], b[k]) for k in a)
+    m = FullGenerator(64, 512, 8)
+    load_synthetic(m, salt=64, parameters_only=True)
+    ref = GO.synthetic_state(64, salt=64)
+    got = m.state_dict()
+    assert got.keys() == ref.keys()
+    for k in ref:
+        assert torch.allclose(got[k], ref[k], rtol=0, atol=1e-7), k
