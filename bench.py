@@ -531,7 +531,9 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         pick_cpu_threads(ncls)                                        # also warms the thread pool / allocator
         dt, _, _ = cpu_reference_face(size, ncls)
+        dt256 = min(cpu_reference_face(256, ncls)[0] for _ in range(2)) if size != 256 else dt      # BASELINE configs[0]'s size
         cpu = {"value": 1.0 / dt, "unit": "faces/s", "cores": torch.get_num_threads(), "kind": "port",
+               "value_256x256": 1.0 / dt256,
                "host_logical_cpus": os.cpu_count(),
                "sample": f"one full {size}x{size} face (B=1, {ncls} regions, K=13) through the reference-structured CPU "
                          f"oracle (fp32, torch CPU; thread count = fastest of 8/16/32/64/all on a 64x64 probe)"}
