@@ -138,3 +138,43 @@ def test_package_synthetic_state_equals_the_oracles():
     assert got.keys() == ref.keys()
     for k in ref:
         assert torch.allclose(got[k], ref[k], rtol=0, atol=1e-7), k
+
+
+def test_up2_polyphase_index_math():
+    """The index arithmetic of csrc/upfirdn2d.cu:upfirdn2d_up2_kernel (parity of the taps that meet a sample, the 2x4 input
+    window of four consecutive outputs, arithmetic shifts on negative positions) restated in Python against the oracle's
+    zero-stuff / pad / convolve definition, for asymmetric FIRs and pads."""
+    import numpy as np
+
+    def emulate(x, fir, pad0, pad1):
+        planes, h, w = x.shape
+        oh, ow = h * 2 + pad0 + pad1 - 3, w * 2 + pad0 + pad1 - 3
+        kf = fir[::-1, ::-1]
+        y = np.zeros((planes, oh, ow), np.float32)
+        for oy in range(oh):
+            my0 = oy - pad0
+            py = my0 & 1
+            iy0 = (my0 + py) >> 1
+            for q in range(ow // 4):
+                base = 4 * q - pad0
+                c0 = (base + (base & 1)) >> 1
+                v = np.zeros((planes, 2, 4), np.float32)
+                for a in range(2):
+                    for c in range(4):
+                        if 0 <= iy0 + a < h and 0 <= c0 + c < w:
+                            v[:, a, c] = x[:, iy0 + a, c0 + c]
+                for j in range(4):
+                    mx0 = base + j
+                    px = mx0 & 1
+                    cj = ((mx0 + px) >> 1) - c0
+                    assert 0 <= cj <= 2
+                    y[:, oy, 4 * q + j] = sum(v[:, a, cj] * kf[2 * a + py][px] + v[:, a, cj + 1] * kf[2 * a + py][px + 2] for a in range(2))
+        return y
+
+    rng = np.random.default_rng(0)
+    for h, w, p0, p1 in [(8, 8, 2, 1), (6, 10, 1, 2), (7, 8, 2, 1), (5, 6, 3, 4), (4, 4, 0, 3)]:
+        assert (w * 2 + p0 + p1 - 3) % 4 == 0
+        x = rng.standard_normal((3, h, w)).astype(np.float32)
+        fir = rng.standard_normal((4, 4)).astype(np.float32)
+        ref = O.upfirdn2d(torch.from_numpy(x)[None], torch.from_numpy(fir), up=2, down=1, pad=(p0, p1))[0].numpy()
+        assert np.abs(emulate(x, fir, p0, p1) - ref).max() < 1e-5, (h, w, p0, p1)
