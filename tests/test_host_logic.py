@@ -178,3 +178,19 @@ def test_up2_polyphase_index_math():
         fir = rng.standard_normal((4, 4)).astype(np.float32)
         ref = O.upfirdn2d(torch.from_numpy(x)[None], torch.from_numpy(fir), up=2, down=1, pad=(p0, p1))[0].numpy()
         assert np.abs(emulate(x, fir, p0, p1) - ref).max() < 1e-5, (h, w, p0, p1)
+
+
+def test_proposed_upsampling_dataflow_spec():
+    """tools/ubench/upconv_dataflow.py - the executable specification of the round-2 kernel design: one
+    tap-free GEMM per 8x16 pixel patch, then horizontal and vertical combination of the per-tap products - equals
+    conv_transpose2d + blur; each output parity combines exactly six (neighbour, tap) products per axis."""
+    import importlib.util
+    import os
+    import numpy as np
+    from conftest import ROOT
+    spec = importlib.util.spec_from_file_location("upconv_dataflow", os.path.join(ROOT, "tools", "ubench", "upconv_dataflow.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.self_check(seed=3) < 1e-12
+    c = mod.axis_coefficients(np.array([1.0, 3.0, 3.0, 1.0]) / 4.0)
+    assert [(c[p] != 0).sum() for p in range(2)] == [6, 6]
