@@ -637,3 +637,17 @@ extern "C" int e4s_modconv3x3_bwd_tc(const float* gy, const float* y, const floa
     if (!up) return k64 ? tcd::dispatch_n<64, 1>(wd_hilo_bf16, p, st) : tcd::dispatch_n<32, 1>(wd_hilo_bf16, p, st);
     return k64 ? tcd::dispatch_n<64, 4>(wd_hilo_bf16, p, st) : tcd::dispatch_n<32, 4>(wd_hilo_bf16, p, st);
 }
+
+// Host-only: the work list e4s_modconv3x3_bwd_tc would build for this shape (N-tile width, region-pass and parity-plane
+// split).  ncls = number of regions the label map can hold (1 without a label map).  No launch, no device access beyond
+// the SM count (148 when no device is present) - lets the host-side heuristics be tested without a GPU.
+extern "C" int e4s_modconv3x3_bwd_tc_plan(int batch, int h, int w, int cin, int ncls, int up, int* ntile, int* gsplit, int* hsplit) {
+    E4S_REQUIRE(ntile && gsplit && hsplit && batch > 0 && h > 0 && w > 0 && cin > 0 && ncls > 0 && ncls <= 32, E4S_ERR_ARG);
+    E4S_REQUIRE((cin % 32) == 0, E4S_ERR_SHAPE);
+    const int nph = up ? 4 : 1;
+    const int64_t tiles = e4s_ceil_div(w, tcd::TW) * e4s_ceil_div(h, tcd::TH) * batch;
+    *ntile = tcd::pick_ntile(cin, 256, tiles, ncls * nph);
+    tcd::choose_split(tiles * (cin / *ntile), ncls, nph, *gsplit, *hsplit);
+    return E4S_OK;
+}
+

@@ -221,6 +221,10 @@ int e4s_modconv3x3_bwd_f32(const float* gy, const float* y, const float* x, cons
 int e4s_modconv3x3_bwd_tc(const float* gy, const float* y, const float* x, const void* wd_hilo_bf16, const float* s,
                           const float* demod, const uint8_t* label, float* gx, float* gs, int batch, int h, int w,
                           int cin, int cout, int ncls, int up, int act, void* stream);
+/* Host-only: the work list e4s_modconv3x3_bwd_tc builds for a shape - N-tile width (input channels per work item) and the
+ * split of a tile's region passes (gsplit) and parity planes (hsplit) over work items.  ncls: regions of the label map
+ * (1 without one).  No launch; testable without a GPU. */
+int e4s_modconv3x3_bwd_tc_plan(int batch, int h, int w, int cin, int ncls, int up, int* ntile, int* gsplit, int* hsplit);
 /* gdu[b,c,o] += sum over pixels of region c of act'(y)*gy * (act^-1(y) - noise_w*noise - bias): the per-region
  * reduction behind d(loss)/d(demod).  gdu [B, ncls, Cout] is accumulated atomically (caller zeroes it). */
 int e4s_class_reduce_f32(const float* gy, const float* y, const uint8_t* label, const float* noise,
