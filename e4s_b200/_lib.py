@@ -35,14 +35,9 @@ SIGNATURES = {
     "e4s_region_mean_f32": [P, P, P, P, c_int, c_int, c_int, c_int, c_int, P],
     "e4s_demod_f32": [P, P, P, c_int, c_int, c_int, c_float, P],
     "e4s_modconv3x3_fwd_f32": [P] * 9 + [c_int] * 9 + [P],
-    "e4s_modconv3x3_tc_fwd": [P] * 9 + [c_int] * 10 + [P],
-    "e4s_modconv3x3_tcp_fwd": [P] * 9 + [c_int] * 9 + [P],
-    "e4s_modconv3x3_tcq_fwd": [P] * 9 + [c_int] * 9 + [P],
-    "e4s_conv3x3_tcq_f32": [P] * 6 + [c_int] * 6 + [P],
     "e4s_modconv3x3_tcr_fwd": [P] * 9 + [c_int] * 9 + [P],
     "e4s_conv3x3_tcr_f32": [P] * 6 + [c_int] * 6 + [P],
     "e4s_tcr_set_profile": [P],
-    "e4s_conv3x3_tcp_f32": [P] * 6 + [c_int] * 6 + [P],
     "e4s_instnorm_affine_f32": [P] * 4 + [c_int] * 4 + [c_float, P],
     "e4s_norm_residual_f32": [P, P, P, c_float, P, P, P, c_int, P, P] + [c_int] * 4 + [P],
     "e4s_modconv3x3_bwd_f32": [P] * 9 + [c_int] * 8 + [P],

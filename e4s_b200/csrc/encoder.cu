@@ -1,5 +1,5 @@
 // Elementwise / reduction kernels of the RGI encoder's conv stack (src/models/encoders/helpers.py:122-144,
-// psp_encoders.py:285-309) around the tensor-core convolution (e4s_conv3x3_tcp_f32):
+// psp_encoders.py:285-309) around the tensor-core convolution (e4s_conv3x3_tcr_f32):
 //   * InstanceNorm statistics per (sample, channel) -> an affine (scale, shift) that the NEXT convolution folds onto
 //     its operand while staging it (no normalised tensor is ever written);
 //   * the unit tail  out = 0.5 * IN(conv2) + shortcut  in one pass.  The 0.5 is the SE gate: SEModule

@@ -232,11 +232,8 @@ int launch_dgrad(const DgradParams& p0, cudaStream_t st) {
     if (nblk >= (1ll << 31)) return E4S_ERR_SHAPE;
     dim3 grid((unsigned)nblk, (unsigned)e4s_ceil_div(p.cin, ICT));
     size_t smem = sizeof(float) * (KC * (TH + 2) * (TW + 4) + KC * 9 * ICT + PG * ICT);
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(modconv3x3_dgrad_kernel<ICG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr = true;
-    }
+    static E4sSmemOptIn optin;
+    if (const int rc = e4s_smem_optin(optin, modconv3x3_dgrad_kernel<ICG>, smem)) return rc;
     modconv3x3_dgrad_kernel<ICG><<<grid, 256, smem, st>>>(p);
     return e4s_launch_status();
 }
@@ -381,11 +378,8 @@ extern "C" int e4s_torgb_bwd_f32(const float* g, const float* x, const float* wr
     E4S_REQUIRE(label || ncls == 1, E4S_ERR_ARG);
     size_t smem = sizeof(float) * (size_t)(3 + 2 * ncls) * cin;
     E4S_REQUIRE(smem <= 200 * 1024, E4S_ERR_SHAPE);
-    static size_t smem_set = 0;
-    if (smem > 48 * 1024 && smem > smem_set) {
-        cudaFuncSetAttribute(torgb_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        smem_set = smem;
-    }
+    static E4sSmemOptIn optin;
+    if (const int rc = e4s_smem_optin(optin, torgb_bwd_kernel, smem)) return rc;
     TorgbBwdParams p{g, x, wrgb, s, label, gx, gs, batch, h, w, cin, ncls};
     int64_t items = (int64_t)h * w * (cin / 4);
     int64_t want = e4s_ceil_div(items, 256 * 8);

@@ -511,15 +511,7 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
-static int num_sms() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = E4S_NUM_SMS;
-    }
-    return n;
-}
+static int num_sms() { return e4s_num_sms(); }
 
 // One (pixel tile, N tile) pair is a serial chain of (regions in the tile) x NPH x Cout/KC x 9 weight slots with 4 MMAs
 // each, whatever the N width - MMA issue, not bandwidth, sets its length (~150 cycles per MMA and issuing warp).  The
@@ -576,12 +568,8 @@ static int launch(const void* wd_hilo, Params p, cudaStream_t st) {
     if (max_slots < 2) return E4S_ERR_SHAPE;
     p.nslot_b = max_slots > 8 ? 8 : (max_slots & ~1);      // even: (hi, lo) slot pairs never straddle the ring wrap
     const size_t smem = 1024 + A_BYTES + (size_t)p.nslot_b * B_SLOT + (size_t)(2 * NSTAGE_A + 4 + 2 * p.nslot_b) * 8 + 64;
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
-        if (cudaFuncSetAttribute(modconv3x3_dgrad_tc_kernel<NTI, KC, NPH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-            return (int)cudaGetLastError();
-        smem_set = smem;
-    }
+    static E4sSmemOptIn optin;
+    if (const int rc = e4s_smem_optin(optin, modconv3x3_dgrad_tc_kernel<NTI, KC, NPH>, smem)) return rc;
     const int grid = p.items < num_sms() ? p.items : num_sms();
     modconv3x3_dgrad_tc_kernel<NTI, KC, NPH><<<grid, NUM_THREADS, smem, st>>>(map, p);
     return e4s_launch_status();

@@ -247,11 +247,8 @@ int launch_modconv(const ModconvParams& p0, cudaStream_t st) {
     if (nblk >= (1ll << 31)) return E4S_ERR_SHAPE;
     dim3 grid((unsigned)nblk, (unsigned)e4s_ceil_div(p.cout, OCT));
     size_t smem = sizeof(float) * (KC * (TH + 2) * (TW + 4) + KC * 9 * OCT + MAXCLS * KC);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(modconv3x3_simt_kernel<OCG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_set = true;
-    }
+    static E4sSmemOptIn optin;
+    if (const int rc = e4s_smem_optin(optin, modconv3x3_simt_kernel<OCG>, smem)) return rc;
     modconv3x3_simt_kernel<OCG><<<grid, 256, smem, st>>>(p);
     return e4s_launch_status();
 }

@@ -854,15 +854,7 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
-static int num_sms() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = E4S_NUM_SMS;
-    }
-    return n;
-}
+static int num_sms() { return e4s_num_sms(); }
 
 static long long* g_prof = nullptr;
 
@@ -912,12 +904,8 @@ static int launch(const void* w_hilo, Params p, cudaStream_t st) {
     // even, so that (hi, lo) pairs never straddle the wrap
     p.nslot_b = p.resident ? planes : (max_slots > 16 ? 16 : (max_slots & ~1));
     const size_t smem = 1024 + A_BYTES + (size_t)p.nslot_b * B_SLOT + tab_bytes + (size_t)(2 * NSTAGE_A + 4 + 2 * p.nslot_b + 2 * NXS) * 8 + 64;
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
-        if (cudaFuncSetAttribute(modconv3x3_tcr_kernel<NTC, KC, NPH, XS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-            return (int)cudaGetLastError();
-        smem_set = smem;
-    }
+    static E4sSmemOptIn optin;
+    if (const int rc = e4s_smem_optin(optin, modconv3x3_tcr_kernel<NTC, KC, NPH, XS>, smem)) return rc;
     const int grid = p.items < num_sms() ? p.items : num_sms();
     modconv3x3_tcr_kernel<NTC, KC, NPH, XS><<<grid, XS ? NUM_THREADS_XS : NUM_THREADS, smem, st>>>(map, xmap, p);
     return e4s_launch_status();

@@ -161,11 +161,8 @@ __global__ void __launch_bounds__(256) torgb_pixel_kernel(TorgbParams p) {
 template <int LPP>
 int launch_torgb(const TorgbParams& p, cudaStream_t st) {
     size_t smem = sizeof(float) * (size_t)(3 + p.ncls) * p.cin;
-    static size_t smem_set = 0;
-    if (smem > 48 * 1024 && smem > smem_set) {
-        cudaFuncSetAttribute(torgb_kernel<LPP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        smem_set = smem;
-    }
+    static E4sSmemOptIn optin;
+    if (const int rc = e4s_smem_optin(optin, torgb_kernel<LPP>, smem)) return rc;
     int64_t hw = (int64_t)p.h * p.w;
     int64_t want = e4s_ceil_div(hw, 8 * (32 / LPP));
     int64_t cap = e4s_ceil_div((int64_t)E4S_NUM_SMS * 8, p.batch);   // ~8 CTAs per SM over the batch

@@ -5,7 +5,7 @@ reference's, so E4S checkpoints load.  ``forward`` does not run those torch modu
 on the e4s_b200 kernels -
 
 * every 3x3 convolution (and the 1x1 stride-2 shortcut convolutions, as centre-tap 3x3 kernels) on the persistent
-  tcgen05 kernel ``e4s_conv3x3_tcp_f32`` (split-bf16 x3, fp32 accumulate), stride 2 taken by keeping the even pixels;
+  tcgen05 kernel ``e4s_conv3x3_tcr_f32`` (split-bf16 x3, fp32 accumulate), stride 2 taken by keeping the even pixels;
 * InstanceNorm as per-(sample, channel) statistics (``e4s_instnorm_affine_f32``) folded onto the operand of the
   following convolution, PReLU in the convolution epilogue;
 * the unit tail ``0.5 * IN(conv2) + shortcut`` in one pass (``e4s_norm_residual_f32``); 0.5 is the SE gate - the
@@ -71,12 +71,12 @@ class FSEncoder_PSP(nn.Module):
         conv1, prelu, conv2 = unit.res_layer[1], unit.res_layer[2], unit.res_layer[3]
         stride = conv2.stride[0]
         sx, tx = K.instnorm_affine(x)                                                     # res_layer[0]
-        r = K.conv3x3_tcp(x, self._prepared(f"{idx}.c1", conv1.weight), sx, tx, prelu.weight)   # conv + PReLU
-        r = K.conv3x3_tcp(r, self._prepared(f"{idx}.c2", conv2.weight), out_stride=stride)
+        r = K.conv3x3_tc(x, self._prepared(f"{idx}.c1", conv1.weight), sx, tx, prelu.weight)   # conv + PReLU
+        r = K.conv3x3_tc(r, self._prepared(f"{idx}.c2", conv2.weight), out_stride=stride)
         s2, t2 = K.instnorm_affine(r)                                                     # res_layer[4]
         if isinstance(unit.shortcut_layer, nn.MaxPool2d):                                 # MaxPool2d(1, stride) == subsample
             return K.norm_residual(r, s2, t2, 0.5, shortcut=x, sc_stride=stride)
-        sc = K.conv3x3_tcp(x, self._prepared(f"{idx}.sc", unit.shortcut_layer[0].weight), out_stride=stride)
+        sc = K.conv3x3_tc(x, self._prepared(f"{idx}.sc", unit.shortcut_layer[0].weight), out_stride=stride)
         ss, ts = K.instnorm_affine(sc)
         return K.norm_residual(r, s2, t2, 0.5, shortcut=sc, sc_scale=ss, sc_shift=ts, sc_stride=1)
 
@@ -92,7 +92,7 @@ class FSEncoder_PSP(nn.Module):
         xp = x.new_zeros((b, h, w, 32), dtype=torch.float32)             # 3 -> 32 channels (one 64-byte K chunk)
         xp[..., :c] = x.permute(0, 2, 3, 1)
         conv0, prelu0 = self.input_layer[0], self.input_layer[2]
-        y = K.conv3x3_tcp(xp, self._prepared("in", conv0.weight, pad_cin_to=32))
+        y = K.conv3x3_tc(xp, self._prepared("in", conv0.weight, pad_cin_to=32))
         s0, t0 = K.instnorm_affine(y)
         x = K.norm_residual(y, s0, t0, 1.0, prelu=prelu0.weight)         # PReLU(IN(conv))
         taps = {}

@@ -220,14 +220,14 @@ class ConvLayer(nn.Sequential):
                 raise NotImplementedError("down-sampling ConvLayer: 3x3 kernels on even-sized inputs")
             blur = mods[0]
             z = upfirdn2d(input, blur.kernel, pad=(blur.pad[0] + 1, blur.pad[1]))              # [B, C, H+2, W+2]
-            y = K.conv3x3_tcp(K.to_pixel_major(z), planes, out_stride=2)[:, 1:, 1:, :].contiguous()
+            y = K.conv3x3_tc(K.to_pixel_major(z), planes, out_stride=2)[:, 1:, 1:, :].contiguous()
         else:
             x_pm = K.to_pixel_major(input)
             if cin < 32:                                                                        # RGB input: one 32-channel K chunk
                 xp = x_pm.new_zeros(x_pm.shape[:3] + (32,))
                 xp[..., :cin] = x_pm
                 x_pm = xp
-            y = K.conv3x3_tcp(x_pm, planes)
+            y = K.conv3x3_tc(x_pm, planes)
         y = _as_nchw_view(y)
         if conv.bias is not None:
             y = y + conv.bias.view(1, -1, 1, 1)

@@ -301,47 +301,12 @@ def modconv3x3_fwd(x_pm: Tensor, wt: Tensor, s: Tensor, dm: Optional[Tensor], la
 
 
 def tc_eligible(cin: int, cout: int) -> bool:
-    """Shapes the first-generation tcgen05 kernel takes: 64-channel K chunks, N tile of 32/64/128 output channels."""
-    return cin % 64 == 0 and cout % 32 == 0 and (cout <= 128 and cout in (32, 64, 128) or cout % 128 == 0)
-
-
-def tcp_eligible(cin: int, cout: int) -> bool:
-    """Shapes the persistent tcgen05 kernel takes (K chunks of 64 or 32 channels, N tiles of 32..256 channels)."""
+    """Shapes the tcgen05 kernel takes (K chunks of 64 or 32 channels, N tiles of 32..256 channels)."""
     return cin % 32 == 0 and cout % 32 == 0
 
 
 def modconv3x3_tcr_fwd(x_pm: Tensor, w_hilo: Tensor, s: Tensor, dm: Optional[Tensor], label: Optional[Tensor],
                        noise: Optional[Tensor], noise_w: Optional[Tensor], bias: Optional[Tensor], up: bool, act: bool) -> Tensor:
-    """Fourth-generation tensor-core path (one pass per tile on any mask, tight MMA issue loop)."""
-    return modconv3x3_tcp_fwd(x_pm, w_hilo, s, dm, label, noise, noise_w, bias, up, act, entry="e4s_modconv3x3_tcr_fwd")
-
-
-def modconv3x3_tcq_fwd(x_pm: Tensor, w_hilo: Tensor, s: Tensor, dm: Optional[Tensor], label: Optional[Tensor],
-                       noise: Optional[Tensor], noise_w: Optional[Tensor], bias: Optional[Tensor], up: bool, act: bool) -> Tensor:
-    """Third-generation tensor-core path (TMA-staged activations, single pass on mixed-region tiles)."""
-    return modconv3x3_tcp_fwd(x_pm, w_hilo, s, dm, label, noise, noise_w, bias, up, act, entry="e4s_modconv3x3_tcq_fwd")
-
-
-def modconv3x3_tcp_fwd(x_pm: Tensor, w_hilo: Tensor, s: Tensor, dm: Optional[Tensor], label: Optional[Tensor],
-                       noise: Optional[Tensor], noise_w: Optional[Tensor], bias: Optional[Tensor], up: bool, act: bool,
-                       entry: str = "e4s_modconv3x3_tcp_fwd") -> Tensor:
-    """Persistent tensor-core path; w_hilo: bf16 [2, nphase, 9, Cout, Cin].  Same contract as modconv3x3_fwd."""
-    b, h, w, cin = x_pm.shape
-    cout = w_hilo.shape[3]
-    ncls = s.shape[1]
-    m = 2 if up else 1
-    y = torch.empty((b, h * m, w * m, cout), device=x_pm.device, dtype=torch.float32)
-    nb = noise.shape[0] if noise is not None else 1
-    with torch.cuda.device(x_pm.device):
-        _call(entry, getattr(_lib.load(), entry), ptr(x_pm), ptr(w_hilo), ptr(s), ptr(dm), ptr(label),
-              ptr(noise), ptr(noise_w), ptr(bias), ptr(y), b, h, w, cin, cout, ncls, int(up), nb, int(act), stream_ptr(),
-              work=2.0 * 9 * cin * cout * b * h * w)
-    return y
-
-
-def modconv3x3_tc_fwd(x_pm: Tensor, w_hilo: Tensor, s: Tensor, dm: Optional[Tensor], label: Optional[Tensor],
-                      noise: Optional[Tensor], noise_w: Optional[Tensor], bias: Optional[Tensor], up: bool, act: bool,
-                      shift_mode: int = 1) -> Tensor:
     """Tensor-core path; w_hilo: bf16 [2, nphase, 9, Cout, Cin].  Same contract as modconv3x3_fwd."""
     b, h, w, cin = x_pm.shape
     cout = w_hilo.shape[3]
@@ -350,9 +315,9 @@ def modconv3x3_tc_fwd(x_pm: Tensor, w_hilo: Tensor, s: Tensor, dm: Optional[Tens
     y = torch.empty((b, h * m, w * m, cout), device=x_pm.device, dtype=torch.float32)
     nb = noise.shape[0] if noise is not None else 1
     with torch.cuda.device(x_pm.device):
-        _call("e4s_modconv3x3_tc_fwd", _lib.load().e4s_modconv3x3_tc_fwd, ptr(x_pm), ptr(w_hilo), ptr(s), ptr(dm), ptr(label),
-              ptr(noise), ptr(noise_w), ptr(bias), ptr(y), b, h, w, cin, cout, ncls, int(up), nb, int(act), int(shift_mode),
-              stream_ptr(), work=2.0 * 9 * cin * cout * b * h * w)
+        _call("e4s_modconv3x3_tcr_fwd", _lib.load().e4s_modconv3x3_tcr_fwd, ptr(x_pm), ptr(w_hilo), ptr(s), ptr(dm), ptr(label),
+              ptr(noise), ptr(noise_w), ptr(bias), ptr(y), b, h, w, cin, cout, ncls, int(up), nb, int(act), stream_ptr(),
+              work=2.0 * 9 * cin * cout * b * h * w)
     return y
 
 
@@ -425,9 +390,6 @@ def torgb_bwd(g: Tensor, x_pm: Tensor, wrgb: Tensor, s: Tensor, label: Optional[
 
 
 # ------------------------------------------------------------------------------ encoder conv stack
-ENCODER_CONV_ENTRY = "e4s_conv3x3_tcr_f32"
-
-
 def split_bf16(w: Tensor) -> Tensor:
     """fp32 -> stacked (hi, lo) bf16 planes with hi + lo == w to ~2^-17 relative."""
     hi = w.to(torch.bfloat16)
@@ -435,17 +397,14 @@ def split_bf16(w: Tensor) -> Tensor:
     return torch.stack([hi, lo]).contiguous()
 
 
-def conv3x3_tcp(x_pm: Tensor, w_hilo: Tensor, scale: Optional[Tensor] = None, shift: Optional[Tensor] = None,
-                prelu: Optional[Tensor] = None, out_stride: int = 1) -> Tensor:
+def conv3x3_tc(x_pm: Tensor, w_hilo: Tensor, scale: Optional[Tensor] = None, shift: Optional[Tensor] = None,
+               prelu: Optional[Tensor] = None, out_stride: int = 1) -> Tensor:
     """x_pm [B,H,W,Cin]; w_hilo bf16 [2,1,9,Cout,Cin]; scale/shift [B,Cin]; prelu [Cout] -> [B,H/s,W/s,Cout]."""
-    import os
-    entry = {"tcp": "e4s_conv3x3_tcp_f32", "tcq": "e4s_conv3x3_tcq_f32", "tcr": "e4s_conv3x3_tcr_f32"}.get(
-        os.environ.get("E4S_B200_CONV", "auto"), ENCODER_CONV_ENTRY)
     b, h, w, cin = x_pm.shape
     cout = w_hilo.shape[3]
     y = torch.empty((b, h // out_stride, w // out_stride, cout), device=x_pm.device, dtype=torch.float32)
     with torch.cuda.device(x_pm.device):
-        _call(entry, getattr(_lib.load(), entry), ptr(x_pm), ptr(w_hilo), ptr(scale), ptr(shift), ptr(prelu),
+        _call("e4s_conv3x3_tcr_f32", _lib.load().e4s_conv3x3_tcr_f32, ptr(x_pm), ptr(w_hilo), ptr(scale), ptr(shift), ptr(prelu),
               ptr(y), b, h, w, cin, cout, out_stride, stream_ptr(), work=2.0 * 9 * cin * cout * b * h * w)
     return y
 

@@ -51,6 +51,10 @@ def invert(net, target: torch.Tensor, onehot: torch.Tensor, style_vectors: Optio
         with torch.no_grad():
             style_vectors, _ = net.get_style_vectors(target, onehot)
     if cuda_graph:
+        if opt_name != "adam":
+            raise ValueError(f"cuda_graph=True supports opt_name='adam' only (capturable optimiser), got {opt_name!r}")
+        if callback is not None:
+            raise ValueError("cuda_graph=True replays a captured step: a per-step Python callback cannot run inside it")
         return _invert_graphed(net, target, onehot, style_vectors, steps, lr, l2_lambda, extra_losses, noise, stats)
     opt, latent = setup_W_optimizer(style_vectors, opt_name, lr)
     history, recon = [], None
@@ -101,17 +105,16 @@ def _invert_graphed(net, target, onehot, style_vectors, steps, lr, l2_lambda, ex
     torch.cuda.current_stream().wait_stream(side)
     if steps > warm:
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
+        with torch.cuda.graph(graph):                   # capture records the step, it does not run it
             one_step()
-        history.append(static_loss.clone())
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(steps - warm - 1):
+        for _ in range(steps - warm):                   # `warm` eager steps + these replays = `steps` updates
             graph.replay()
             history.append(static_loss.clone())
         e1.record()
-        if stats is not None and steps - warm - 1 > 0:
+        if stats is not None:
             e1.synchronize()
-            stats["replayed_steps"] = steps - warm - 1
-            stats["replay_ms_per_step"] = e0.elapsed_time(e1) / (steps - warm - 1)
+            stats["replayed_steps"] = steps - warm
+            stats["replay_ms_per_step"] = e0.elapsed_time(e1) / (steps - warm)
     return latent.detach(), static_recon, history

@@ -125,7 +125,7 @@ class PreparedConv:
                 # -> [nphase, tap, Cin, Cout]
                 self.wt = wk.permute(0, 3, 4, 2, 1).reshape(wk.shape[0], 9, cin, cout).contiguous()
                 self.wrgb = None
-                if K.tcp_eligible(cin, cout):
+                if K.tc_eligible(cin, cout):
                     wk_k = wk.permute(0, 3, 4, 1, 2).reshape(wk.shape[0], 9, cout, cin)     # K-major rows [.., Cout, Cin]
                     hi = wk_k.to(torch.bfloat16)
                     lo = (wk_k - hi.float()).to(torch.bfloat16)
@@ -147,25 +147,14 @@ def warn_frozen(weight: Tensor):
         _warned_weight_grad = True
 
 
-DEFAULT_CONV_MODE = "auto"   # auto -> tcp (second generation) until a later generation beats it end to end
-
-
-AUTO_KERNEL = "tcr"
-
-
 def conv_path(prep: "PreparedConv", x_pm: Tensor) -> str:
-    """Kernel choice for one layer: 'tcq' / 'tcp' / 'tc' (third / second / first generation tcgen05 kernels) or 'simt'
-    (exact fp32).  E4S_B200_CONV=auto|tcr|tcq|tcp|tc|simt.  auto: the fourth-generation tensor-core kernel for every layer whose
-    channel counts are multiples of 32 (even a single mostly-halo 4x4 tile per CTA beats the SIMT kernel's latency)."""
-    mode = os.environ.get("E4S_B200_CONV", DEFAULT_CONV_MODE)
+    """Kernel choice for one layer: 'tcr' (the tcgen05 kernel) or 'simt' (exact fp32).  E4S_B200_CONV=auto|tcr|simt.
+    auto: the tensor-core kernel for every layer whose channel counts are multiples of 32 (even a single mostly-halo 4x4
+    tile per CTA beats the SIMT kernel's latency)."""
+    mode = os.environ.get("E4S_B200_CONV", "auto")
     if prep.w_hilo is None or mode == "simt":
         return "simt"
-    cout, cin = prep.w_hilo.shape[3], prep.w_hilo.shape[4]
-    if mode == "tc":
-        return "tc" if K.tc_eligible(cin, cout) else "simt"
-    if mode in ("tcp", "tcq", "tcr"):
-        return mode
-    return AUTO_KERNEL
+    return "tcr"
 
 
 # ================================================================================== autograd
@@ -178,12 +167,6 @@ class StyledConvFn(Function):
         path = conv_path(prep, x_pm)
         if path == "tcr":
             y = K.modconv3x3_tcr_fwd(x_pm, prep.w_hilo, s.contiguous(), dm, label, noise, noise_w, bias, up, act)
-        elif path == "tcq":
-            y = K.modconv3x3_tcq_fwd(x_pm, prep.w_hilo, s.contiguous(), dm, label, noise, noise_w, bias, up, act)
-        elif path == "tcp":
-            y = K.modconv3x3_tcp_fwd(x_pm, prep.w_hilo, s.contiguous(), dm, label, noise, noise_w, bias, up, act)
-        elif path == "tc":
-            y = K.modconv3x3_tc_fwd(x_pm, prep.w_hilo, s.contiguous(), dm, label, noise, noise_w, bias, up, act)
         else:
             y = K.modconv3x3_fwd(x_pm, prep.wt, s.contiguous(), dm, label, noise, noise_w, bias, up, act)
         ctx.set_materialize_grads(False)

@@ -130,47 +130,15 @@ int e4s_modconv3x3_fwd_f32(const float* x, const float* wt, const float* s, cons
                            float* y, int batch, int h, int w, int cin, int cout, int ncls, int up, int noise_b,
                            int act, void* stream);
 
-/* Tensor-core (tcgen05 / TMEM / TMA) implementation of the same contract as e4s_modconv3x3_fwd_f32, for
- * cin % 64 == 0 and cout in {32, 64, 128, 256, 384, 512, ...}.  Weights arrive pre-split into bf16 planes
- * w_hilo_bf16 = [2 (hi, lo)][nphase][9][Cout][Cin] with w = hi + lo to ~2^-17 relative (prepared once);
- * activations are split on the fly, three bf16 MMAs per tap accumulate in fp32 (error ~1e-5 relative to fp32).
- * shift_mode selects how tap-shifted operand descriptors encode their swizzle phase: 1 = start address only (the
- * swizzle is a function of absolute shared-memory address bits - verified on B200), 0 = also set the descriptor's
- * base_offset field (wrong on B200; kept as a self-test knob).  Callers pass 1. */
-int e4s_modconv3x3_tc_fwd(const float* x, const void* w_hilo_bf16, const float* s, const float* demod,
-                          const uint8_t* label, const float* noise, const float* noise_w, const float* bias,
-                          float* y, int batch, int h, int w, int cin, int cout, int ncls, int up, int noise_b,
-                          int act, int shift_mode, void* stream);
-
-/* Persistent, fully pipelined tcgen05 implementation (csrc/modconv_tcp.cu): same contract and weight format as
- * e4s_modconv3x3_tc_fwd; additionally takes cin % 32 == 0 (64-byte-swizzle K chunks) and puts the four output
- * parities of an up-sampling layer along the MMA's N dimension.  This is the kernel the synthesis network uses. */
-int e4s_modconv3x3_tcp_fwd(const float* x, const void* w_hilo_bf16, const float* s, const float* demod,
-                           const uint8_t* label, const float* noise, const float* noise_w, const float* bias,
-                           float* y, int batch, int h, int w, int cin, int cout, int ncls, int up, int noise_b,
-                           int act, void* stream);
-
-/* Third-generation tcgen05 implementation (csrc/modconv_tcq.cu): raw activation tiles streamed by 4-D TMA through a
- * shared-memory ring, 32-channel K chunks everywhere, and ONE main-loop pass for tiles that mix regions (row-class
- * operand staging).  Same contract and weight format; this is the kernel the synthesis network uses by default. */
-int e4s_modconv3x3_tcq_fwd(const float* x, const void* w_hilo_bf16, const float* s, const float* demod,
-                           const uint8_t* label, const float* noise, const float* noise_w, const float* bias,
-                           float* y, int batch, int h, int w, int cin, int cout, int ncls, int up, int noise_b,
-                           int act, void* stream);
-/* e4s_conv3x3_tcp_f32 on the third-generation kernel. */
-int e4s_conv3x3_tcq_f32(const float* x, const void* w_hilo_bf16, const float* scale, const float* shift,
-                        const float* prelu_slope, float* y, int batch, int h, int w, int cin, int cout, int out_stride,
-                        void* stream);
-
-/* Fourth-generation tcgen05 implementation (csrc/modconv_tcr.cu): one main-loop pass per tile whatever the number of
- * regions in it (row-class operand staging on mixed tiles), tight MMA issue loop.  Same contract and weight format. */
+/* Tensor-core (tcgen05 / TMEM / TMA) implementation of the same contract as e4s_modconv3x3_fwd_f32 for cin % 32 == 0 and
+ * cout % 32 == 0 (csrc/modconv_tcr.cu).  Weights arrive pre-split into bf16 planes
+ * w_hilo_bf16 = [2 (hi, lo)][nphase][9][Cout][Cin] with w = hi + lo to ~2^-17 relative (prepared once); activations
+ * are split on the fly, three bf16 MMAs per tap accumulate in fp32 TMEM (error ~1e-5 relative to fp32).  Persistent
+ * CTAs, one main-loop pass per tile whatever the number of regions in it. */
 int e4s_modconv3x3_tcr_fwd(const float* x, const void* w_hilo_bf16, const float* s, const float* demod,
                            const uint8_t* label, const float* noise, const float* noise_w, const float* bias,
                            float* y, int batch, int h, int w, int cin, int cout, int ncls, int up, int noise_b,
                            int act, void* stream);
-int e4s_conv3x3_tcr_f32(const float* x, const void* w_hilo_bf16, const float* scale, const float* shift,
-                        const float* prelu_slope, float* y, int batch, int h, int w, int cin, int cout, int out_stride,
-                        void* stream);
 /* Diagnostic (no reference counterpart): per-role stall attribution of CTA 0 of every following gen-4 launch.
  * device_counters: [5 roles][4] int64 in device memory (role time, cycles in its barrier waits); NULL = off. */
 int e4s_tcr_set_profile(long long* device_counters);
@@ -180,7 +148,7 @@ int e4s_tcr_set_profile(long long* device_counters);
  * x: pixel-major [B, H, W, Cin]; w_hilo_bf16: [2][1][9][Cout][Cin]; scale/shift: optional per-(sample, channel)
  * affine [B, Cin] applied to in-image pixels while staging (InstanceNorm folded onto the operand; zero padding
  * stays zero); prelu_slope: optional [Cout] PReLU epilogue; y: [B, H/out_stride, W/out_stride, Cout]. */
-int e4s_conv3x3_tcp_f32(const float* x, const void* w_hilo_bf16, const float* scale, const float* shift,
+int e4s_conv3x3_tcr_f32(const float* x, const void* w_hilo_bf16, const float* scale, const float* shift,
                         const float* prelu_slope, float* y, int batch, int h, int w, int cin, int cout, int out_stride,
                         void* stream);
 /* InstanceNorm2d statistics (biased variance, eps) of a pixel-major tensor as an affine: scale = rstd,

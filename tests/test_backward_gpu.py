@@ -181,6 +181,44 @@ def test_inversion_loop_matches_oracle(monkeypatch):
         assert abs(a - b) <= 5e-3 * abs(b), ([float(h) for h in hist], ref_losses)
 
 
+def test_graphed_inversion_equals_eager():
+    """invert(cuda_graph=True) makes exactly `steps` optimiser updates and follows the eager loop (same fixed noise): the
+    capture itself does not execute a step (round-1 review: the graphed path ran one update short and logged a stale loss)."""
+    from e4s_b200.networks import Net3
+    from e4s_b200.optimization import invert
+    size, ncls, K = 32, 12, 13
+    opts = types.SimpleNamespace(fsencoder_type="psp", remaining_layer_idx=K, num_seg_cls=ncls, out_size=size,
+                                 train_G=False, start_from_latent_avg=True, learn_in_w=False)
+    net = Net3(opts).eval()
+    st = O.synthetic_state({k: tuple(v.shape) for k, v in net.state_dict().items()}, salt=5)
+    net.load_state_dict(st)
+    for p in net.parameters():
+        p.requires_grad = False
+    net = net.to(DEV)
+    net.latent_avg = cu(0.1 * torch.randn(18, 512, generator=torch.Generator().manual_seed(77)))
+    g = torch.Generator().manual_seed(8)
+    sv0 = cu(0.5 * torch.randn(1, ncls, 1280, generator=g))
+    _, mask, _, noise = O.synthetic_inputs(1, ncls, size, 64, seed=12)
+    noise = [cu(n) for n in noise]
+    with torch.no_grad():
+        target, _, _ = net.gen_img(None, net.cal_style_codes(cu(0.5 * torch.randn(1, ncls, 1280, generator=g))), cu(mask), noise=noise)
+    steps = 7
+    lat_e, _, hist_e = invert(net, target, cu(mask), style_vectors=sv0, steps=steps, noise=noise)
+    lat_g, _, hist_g = invert(net, target, cu(mask), style_vectors=sv0, steps=steps, noise=noise, cuda_graph=True)
+    assert len(hist_e) == len(hist_g) == steps
+    he, hg = [float(h) for h in hist_e], [float(h) for h in hist_g]
+    for a, b in zip(hg, he):
+        assert abs(a - b) <= 2e-3 * abs(b), (hg, he)
+    assert len(set(hg)) == steps, hg                          # no duplicated (stale) entry
+    # same number of Adam updates: the latent moved as far as the eager one (Adam's first steps are ~lr per coordinate)
+    de, dg = (lat_e - sv0).abs().mean(), (lat_g - sv0).abs().mean()
+    assert abs(float(dg) - float(de)) <= 0.05 * float(de), (float(dg), float(de))
+    with pytest.raises(ValueError):
+        invert(net, target, cu(mask), style_vectors=sv0, steps=2, opt_name="sgd", cuda_graph=True)
+    with pytest.raises(ValueError):
+        invert(net, target, cu(mask), style_vectors=sv0, steps=2, callback=lambda *a: None, cuda_graph=True)
+
+
 # ------------------------------------------------------------------ tensor-core dgrad vs the fp32 SIMT dgrad
 @pytest.mark.parametrize("b,cin,cout,hw,up,ncls,kind,act", [
     (1, 64, 64, 16, False, 1, "blobs", True),

@@ -407,29 +407,6 @@ PRODUCTION_CASES = [
 ]
 
 
-@pytest.mark.parametrize("b,cin,cout,hw,up,ncls,kind", TC_CASES)
-def test_tc_kernel_matches_simt(b, cin, cout, hw, up, ncls, kind):
-    """The first-generation tcgen05 implicit-GEMM kernel against the exact-fp32 SIMT kernel of the same library
-    (which the tests above pin to the reference vectors).  Split-bf16 x3 keeps the error ~1e-5."""
-    K, prep, x, args = _tc_case(b, cin, cout, hw, up, ncls, kind, seed=cin + cout + hw)
-    ref = K.modconv3x3_fwd(x, prep.wt, *args)
-    out = K.modconv3x3_tc_fwd(x, prep.w_hilo, *args)
-    torch.cuda.synchronize()
-    e = assert_close(out, ref, 1e-4, f"tc vs simt {b},{cin},{cout},{hw},{up},{ncls},{kind}")
-    print(f"tc-vs-simt rel err {e:.2e}")
-
-
-@pytest.mark.parametrize("b,cin,cout,hw,up,ncls,kind", TC_CASES + TCP_EXTRA)
-def test_tcp_kernel_matches_simt(b, cin, cout, hw, up, ncls, kind):
-    """The persistent tcgen05 kernel (the one the generator uses) against the exact-fp32 SIMT kernel."""
-    K, prep, x, args = _tc_case(b, cin, cout, hw, up, ncls, kind, seed=cin + cout + hw)
-    ref = K.modconv3x3_fwd(x, prep.wt, *args)
-    out = K.modconv3x3_tcp_fwd(x, prep.w_hilo, *args)
-    torch.cuda.synchronize()
-    e = assert_close(out, ref, 1e-4, f"tcp vs simt {b},{cin},{cout},{hw},{up},{ncls},{kind}")
-    print(f"tcp-vs-simt rel err {e:.2e}")
-
-
 @pytest.mark.parametrize("b,cin,cout,hw,up,ncls,kind", TC_CASES + TCP_EXTRA + [
     (2, 64, 128, 30, True, 5, "blobs"),       # up-sampling with region borders: row-class pass + fix-up passes
     (1, 160, 256, 28, False, 12, "iid"),      # every row its own region: pure row-class mode, 5 K chunks
@@ -473,17 +450,6 @@ def test_tcr_kernel_production_shapes(b, cin, cout, hw, up, ncls, kind):
     print(f"tcr-vs-simt rel err {e:.2e}")
 
 
-@pytest.mark.parametrize("b,cin,cout,hw,up,ncls,kind", TC_CASES + TCP_EXTRA)
-def test_tcq_kernel_matches_simt(b, cin, cout, hw, up, ncls, kind):
-    """The third-generation tcgen05 kernel (TMA-staged activations, single pass on mixed tiles) vs the fp32 SIMT kernel."""
-    K, prep, x, args = _tc_case(b, cin, cout, hw, up, ncls, kind, seed=cin + cout + hw)
-    ref = K.modconv3x3_fwd(x, prep.wt, *args)
-    out = K.modconv3x3_tcq_fwd(x, prep.w_hilo, *args)
-    torch.cuda.synchronize()
-    e = assert_close(out, ref, 1e-4, f"tcq vs simt {b},{cin},{cout},{hw},{up},{ncls},{kind}")
-    print(f"tcq-vs-simt rel err {e:.2e}")
-
-
 def test_generator_golden_tensor_core_path(golden, monkeypatch):
     """Whole generator with every eligible layer forced onto the persistent tcgen05 kernel (also at 4x4..8x8, where
     the default policy would pick the SIMT kernel), against the reference vectors."""
@@ -513,7 +479,7 @@ def test_encoder_building_blocks():
     assert_close(sc, torch.rsqrt(var + 1e-5), 1e-5, "instnorm scale")
     assert_close(sh, -mean * torch.rsqrt(var + 1e-5), 1e-4, "instnorm shift")
     for stride in (1, 2):
-        y = K.conv3x3_tcp(xpm, planes, sc, sh, cu(slope), out_stride=stride)
+        y = K.conv3x3_tc(xpm, planes, sc, sh, cu(slope), out_stride=stride)
         ref = F.prelu(F.conv2d(F.instance_norm(x, eps=1e-5), w, stride=stride, padding=1), slope)
         assert_close(y.permute(0, 3, 1, 2), ref, 1e-4, f"IN->conv->PReLU stride {stride}")
     y = torch.randn(2, 12, 10, 96, generator=g)

@@ -27,7 +27,7 @@ def run(mode):
         b, c, h, w = x.shape
         xp = x.new_zeros((b, h, w, 32))
         xp[..., :c] = x.permute(0, 2, 3, 1)
-        y = K.conv3x3_tcp(xp, enc._prepared("in", enc.input_layer[0].weight, pad_cin_to=32))
+        y = K.conv3x3_tc(xp, enc._prepared("in", enc.input_layer[0].weight, pad_cin_to=32))
         outs.append(("conv0", y))
         s0, t0 = K.instnorm_affine(y)
         cur = K.norm_residual(y, s0, t0, 1.0, prelu=enc.input_layer[2].weight)
@@ -35,15 +35,15 @@ def run(mode):
         unit = enc.body[0]
         conv1, prelu, conv2 = unit.res_layer[1], unit.res_layer[2], unit.res_layer[3]
         sx, tx = K.instnorm_affine(cur)
-        r1 = K.conv3x3_tcp(cur, enc._prepared("0.c1", conv1.weight), sx, tx, prelu.weight)
+        r1 = K.conv3x3_tc(cur, enc._prepared("0.c1", conv1.weight), sx, tx, prelu.weight)
         outs.append(("u0.conv1 IN+PReLU 64->128", r1))
-        r1n = K.conv3x3_tcp(cur, enc._prepared("0.c1", conv1.weight))
+        r1n = K.conv3x3_tc(cur, enc._prepared("0.c1", conv1.weight))
         outs.append(("u0.conv1 plain 64->128", r1n))
-        r2 = K.conv3x3_tcp(r1n, enc._prepared("0.c2", conv2.weight), out_stride=2)
+        r2 = K.conv3x3_tc(r1n, enc._prepared("0.c2", conv2.weight), out_stride=2)
         outs.append(("u0.conv2 128->128 s2", r2))
-        r2b = K.conv3x3_tcp(r1n, enc._prepared("0.c2", conv2.weight), out_stride=1)
+        r2b = K.conv3x3_tc(r1n, enc._prepared("0.c2", conv2.weight), out_stride=1)
         outs.append(("u0.conv2 128->128 s1", r2b))
-        sc = K.conv3x3_tcp(cur, enc._prepared("0.sc", unit.shortcut_layer[0].weight), out_stride=2)
+        sc = K.conv3x3_tc(cur, enc._prepared("0.sc", unit.shortcut_layer[0].weight), out_stride=2)
         outs.append(("u0.shortcut 64->128 s2", sc))
         for i, unit in enumerate(enc.body):
             cur = enc._unit(i, unit, cur)

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Per-kernel micro-benchmarks on one B200 (CUDA events, L2 flushed between iterations).
 
-    python tools/opbench.py [--batch 16] [--out gpurun_out/opbench.json] [--conv simt,tc]
+    python tools/opbench.py [--batch 16] [--out gpurun_out/opbench.json] [--conv simt,tcr]
 
 Reports achieved GB/s (HBM-bound kernels, algorithmic bytes) or TFLOP/s (modulated convs, algorithmic FLOPs)
 against MEASURED_PEAKS.json.  Layer shapes are the 1024x1024 generator's.
@@ -43,7 +43,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "opbench.json"))
-    ap.add_argument("--conv", default="simt,tc")
+    ap.add_argument("--conv", default="tcr", help="comma list of simt,tcr")
     ap.add_argument("--layers", default="all")
     ap.add_argument("--prof", action="store_true", help="gen-4 kernel: per-role stall attribution of CTA 0 (e4s_tcr_set_profile)")
     ap.add_argument("--only-conv", action="store_true", help="skip the HBM-bound kernels")
@@ -135,15 +135,10 @@ def conv_rows(args, B, fir, flush, row, res):
         dm = K.demod(s, prep.wsq)
         flops = 2.0 * 9 * cin * cout * B * r * r
         for mode in args.conv.split(","):
-            if mode == "tc":
-                if prep.w_hilo is None or not K.tc_eligible(cin, cout):
-                    continue
-                fn = lambda: K.modconv3x3_tc_fwd(xpm, prep.w_hilo, s, dm, label, noise, nw, bias, bool(up), True)
-            elif mode in ("tcp", "tcq", "tcr"):
+            if mode == "tcr":
                 if prep.w_hilo is None:
                     continue
-                f = {"tcp": K.modconv3x3_tcp_fwd, "tcq": K.modconv3x3_tcq_fwd, "tcr": K.modconv3x3_tcr_fwd}[mode]
-                fn = lambda f=f: f(xpm, prep.w_hilo, s, dm, label, noise, nw, bias, bool(up), True)
+                fn = lambda: K.modconv3x3_tcr_fwd(xpm, prep.w_hilo, s, dm, label, noise, nw, bias, bool(up), True)
             else:
                 fn = lambda: K.modconv3x3_fwd(xpm, prep.wt, s, dm, label, noise, nw, bias, bool(up), True)
             ms = timeit(fn, iters=1, warmup=0, flush=flush) if args.once else timeit(fn, iters=3, warmup=1, flush=flush)
