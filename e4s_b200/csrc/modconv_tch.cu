@@ -1,0 +1,556 @@
+// Up-sampling StyledConv in the H-FORM on tcgen05 tensor cores (sm_100a): conv_transpose2d(stride 2) + 4x4 blur
+// (reference src/models/stylegan2/model.py:287-300) + region selection + noise / bias / activation in one kernel, at HALF
+// the multiply-accumulates of the polyphase form of modconv_tcr.cu.
+//
+// Formulation (executable specification: tools/ubench/hform_dataflow.py, checked against conv_transpose2d + upfirdn2d).
+// The blur is separable.  Its VERTICAL half is folded into the weights on the host, its HORIZONTAL half runs in the
+// epilogue:
+//
+//     T[py, kx][m, n'] = sum_dy V[py, kx][dy] . (s_c * x)[m + dy - 1, n']        V[py, kx][dy] = sum_ky Ay[py][dy, ky] W[ky, kx]
+//     out[2m + py, 2n + px] = sum_{dx, kx} Ax[px][dx, kx] T[py, kx][m, n + dx - 1]
+//
+// i.e. an implicit GEMM with M = 128 input pixels (the 8x16 patch of modconv_tcr.cu: patch column 0 is image column
+// x0 - 1), N = 6 x NTC accumulator columns (the six (py, kx) groups of NTC output channels) and K = 3 row taps x Cin -
+// 18 tap-MACs per input pixel against 36 in the polyphase form - followed by a six-term combination per output parity of
+// the pixel's own accumulators with those of its left / right neighbours (lane -1 / +1 of the same warp: two warp
+// shuffles per term that crosses a pixel).  Row taps are pure row shifts of one staged halo tile by 16 operand rows, the
+// same trick (and the same operand staging code) as the 3x3 kernel's taps with dx = 0.
+//
+// Regions: the style is that of the OUTPUT pixel's region (the reference masks after the blur, model.py:389-397), and an
+// accumulator row feeds output pixels of three columns, so rows cannot be scaled by "their" region.  A tile is processed
+// in PASSES of up to two regions, one accumulator buffer per region (x * s_A and x * s_B staged side by side, the same
+// weight slots multiplied into both); the epilogue combines within one region's buffer and each output pixel takes the
+// result of its own region.  One region: one pass, double-buffered across tiles.  k regions: ceil(k / 2) passes.
+//
+// Roles (persistent CTAs, 16 warps), barriers, split-bf16 x3 accumulation, zeroing of read accumulators by the epilogue:
+// as in modconv_tcr.cu.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cstdlib>
+#include <mutex>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace tch {
+using namespace tcx;
+
+constexpr int TH = 8, TW = 14;
+constexpr int A_ROWS = 168;                     // 160 halo pixels + the leading row of the 3x3 kernel's layout
+constexpr int NSTAGE_A = 2;
+constexpr int NUM_MMA_WARPS = 3;
+constexpr int W_XFORM0 = 1 + NUM_MMA_WARPS, W_EPI0 = W_XFORM0 + 8, W_END = W_EPI0 + 4;
+constexpr int NUM_THREADS = 32 * W_END;         // 512
+constexpr int NUM_XFORM = 256, NUM_EPI = 128;
+constexpr int SMEM_BUDGET = 227 * 1024 - 2048;
+constexpr int NG = 6;                           // (py, kx) accumulator column groups
+constexpr int ACC_COLS = 256, NACC = 2, TMEM_COLS = 512;
+
+struct Params {
+    const float* x;
+    const float* s;
+    const float* demod;
+    const uint8_t* label;
+    const float* noise;
+    const float* noise_w;
+    const float* bias;
+    float* y;
+    float f0, f1, f2, f3;                       // flipped horizontal FIR taps
+    int batch, h, w, cin, cout, ncls, noise_b, act;
+    int tiles_x, tiles_y, n_tiles, items, nslot_b;
+};
+
+struct Item {
+    int b, ty, tx, nt;
+};
+__device__ __forceinline__ Item decode_item(const Params& p, int it) {
+    Item r;
+    const int ptiles = p.tiles_x * p.tiles_y * p.batch;
+    r.nt = it / ptiles;
+    int pt = it - r.nt * ptiles;
+    r.tx = pt % p.tiles_x;
+    pt /= p.tiles_x;
+    r.ty = pt % p.tiles_y;
+    r.b = pt / p.tiles_y;
+    return r;
+}
+struct Walk {                                   // work items blockIdx.x, + gridDim.x, ...: decoded once, advanced with carries
+    Item cur, step;
+    __device__ __forceinline__ void init(const Params& p, int first, int stride) {
+        cur = decode_item(p, first);
+        step = decode_item(p, stride);
+    }
+    __device__ __forceinline__ void advance(const Params& p) {
+        cur.tx += step.tx;
+        int carry = 0;
+        if (cur.tx >= p.tiles_x) cur.tx -= p.tiles_x, carry = 1;
+        cur.ty += step.ty + carry, carry = 0;
+        if (cur.ty >= p.tiles_y) cur.ty -= p.tiles_y, carry = 1;
+        cur.b += step.b + carry, carry = 0;
+        if (cur.b >= p.batch) cur.b -= p.batch, carry = 1;
+        cur.nt += step.nt + carry;
+    }
+};
+
+// Regions among the outputs of a tile (all four parities of its valid pixels: patch columns 1..14); one whole warp.
+__device__ __forceinline__ uint32_t tile_classes(const Params& p, const Item& it, int lane) {
+    if (!p.label) return 1u;
+    const int wo = 2 * p.w;
+    uint32_t m = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = lane + 32 * i;
+        const int tx = r & 15;
+        const int iy = it.ty * TH + (r >> 4), ix = it.tx * TW + tx - 1;
+        if (tx >= 1 && tx <= TW && iy < p.h && ix < p.w) {
+            const uint8_t* lp = p.label + ((int64_t)it.b * 2 * p.h + 2 * iy) * wo + 2 * ix;
+            m |= (1u << min((int)lp[0], p.ncls - 1)) | (1u << min((int)lp[1], p.ncls - 1)) | (1u << min((int)lp[wo], p.ncls - 1)) |
+                 (1u << min((int)lp[wo + 1], p.ncls - 1));
+        }
+    }
+    m = __reduce_or_sync(0xffffffffu, m);
+    return m ? m : 1u;
+}
+// next pass of a tile: its one or two regions (cb < 0: one), taken off the remaining-regions mask
+__device__ __forceinline__ void next_pass(uint32_t& m, int& ca, int& cb) {
+    ca = __ffs(m) - 1;
+    m &= m - 1;
+    cb = -1;
+    if (m) cb = __ffs(m) - 1, m &= m - 1;
+}
+
+template <int NTC, int KC>
+__global__ void __launch_bounds__(NUM_THREADS, 1) modconv3x3_up_tch_kernel(const __grid_constant__ CUtensorMap wmap, Params p) {
+    constexpr int N = NG * NTC;
+    constexpr int ROWB = KC * 2;
+    constexpr int A_PLANE = A_ROWS * ROWB;
+    constexpr int A_STAGE = 2 * A_PLANE;
+    constexpr int B_SLOT = N * ROWB;
+    constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 4) << 24) | ((uint32_t)(N >> 3) << 17);
+    constexpr uint32_t DESC_HI = (uint32_t)((KC == 64 ? 1024u : 512u) >> 4) | (1u << 14) | ((KC == 64 ? 2u : 4u) << 29);
+    constexpr int KSTEPS = KC / 16;
+    constexpr int CPR = KC / 8;                       // 16-byte chunks per operand row
+    constexpr int PPS = NUM_XFORM / CPR;              // halo pixels covered per sweep of the transform threads
+    constexpr int NSW = (160 + PPS - 1) / PPS;
+    static_assert(N <= ACC_COLS && N % 16 == 0 && NTC % 8 == 0, "UMMA N");
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* a_buf = smem;                                                // [NSTAGE_A][hi|lo][A_ROWS][ROWB]
+    uint8_t* b_buf = a_buf + ((NSTAGE_A * A_STAGE + 1023) & ~1023);       // [nslot_b][N][ROWB]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(b_buf + (size_t)p.nslot_b * B_SLOT);
+    const int A_FULL = 0, A_EMPTY = A_FULL + NSTAGE_A, ACC_FULL = A_EMPTY + NSTAGE_A, ACC_EMPTY = ACC_FULL + NACC,
+              B_FULL = ACC_EMPTY + NACC, B_EMPTY = B_FULL + p.nslot_b, NBARS = B_EMPTY + p.nslot_b;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBARS);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nchunks = p.cin / KC;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NSTAGE_A; ++i) mbar_init(smem_u32(&bars[A_FULL + i]), NUM_XFORM), mbar_init(smem_u32(&bars[A_EMPTY + i]), NUM_MMA_WARPS);
+        for (int i = 0; i < NACC; ++i) mbar_init(smem_u32(&bars[ACC_FULL + i]), NUM_MMA_WARPS), mbar_init(smem_u32(&bars[ACC_EMPTY + i]), NUM_EPI);
+        for (int i = 0; i < p.nslot_b; ++i) mbar_init(smem_u32(&bars[B_FULL + i]), 1), mbar_init(smem_u32(&bars[B_EMPTY + i]), NUM_MMA_WARPS);
+        fence_barrier_init();
+    }
+    if (warp == 0 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&wmap) : "memory");
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (warp >= W_EPI0) {                               // every MMA accumulates: both accumulator buffers start at zero
+        const uint32_t lanes = tmem_base + (((uint32_t)(warp & 3) * 32u) << 16);
+#pragma unroll 1
+        for (int c = 0; c < TMEM_COLS; c += 32) tmem_zero32(lanes + (uint32_t)c);
+        tmem_wait_st();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    if (warp == 0) {
+        // ===================================================================== TMA producer: per (pass, chunk, row tap) ONE 4-D box =
+        // the (hi, lo) planes of all six column groups = one slot pair
+        int slot = 0;
+        uint32_t ph = 0;
+        Walk wk;
+        wk.init(p, blockIdx.x, gridDim.x);
+        for (int it = blockIdx.x; it < p.items; it += gridDim.x, wk.advance(p)) {
+            const Item item = wk.cur;
+            const int npass = (__popc(tile_classes(p, item, lane)) + 1) >> 1;
+            if (lane == 0) {
+                for (int ps = 0; ps < npass; ++ps)
+                    for (int kc = 0; kc < nchunks; ++kc)
+                        for (int tap = 0; tap < 3; ++tap) {
+                            mbar_wait(smem_u32(&bars[B_EMPTY + slot]), ph ^ 1);
+                            const uint32_t full = smem_u32(&bars[B_FULL + slot]);
+                            mbar_expect_tx(full, 2 * B_SLOT);
+                            tma_load_4d(smem_u32(b_buf + (size_t)slot * B_SLOT), &wmap, kc * KC, item.nt * NTC, tap, 0, full);
+                            slot += 2;
+                            if (slot >= p.nslot_b) slot = 0, ph ^= 1;
+                        }
+            }
+            __syncwarp();
+        }
+    } else if (warp <= NUM_MMA_WARPS) {
+        // ===================================================================== MMA issuers: role 0 x_hi w_hi, 1 x_lo w_hi, 2 x_hi w_lo
+        const int role = warp - 1;
+        const bool lo_w = role == 2;
+        int sa = 0, slot = 0, acc = 0;
+        uint32_t pa = 0, pb = 0, pacc[2] = {0, 0};
+        const bool leader = lane == 0;
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+        const uint32_t bars0 = smem_u32(bars);
+        const uint32_t a0 = smem_u32(a_buf) + (role == 1 ? A_PLANE : 0), b0 = smem_u32(b_buf);
+        auto desc = [](uint32_t lo) -> uint64_t { return ((uint64_t)DESC_HI << 32) | lo; };
+        auto lo_of = [](uint32_t addr) -> uint32_t { return (addr >> 4) | 0x10000u; };
+        Walk wk;
+        wk.init(p, blockIdx.x, gridDim.x);
+        for (int it = blockIdx.x; it < p.items; it += gridDim.x, wk.advance(p)) {
+            const Item item = wk.cur;
+            uint32_t rem = __shfl_sync(0xffffffffu, tile_classes(p, item, lane), 0);
+            while (rem) {
+                int ca, cb;
+                next_pass(rem, ca, cb);
+                const bool two = cb >= 0;
+                mbar_wait(bars0 + 8 * (ACC_EMPTY + acc), pacc[acc] ^ 1);
+                if (two) mbar_wait(bars0 + 8 * (ACC_EMPTY + (acc ^ 1)), pacc[acc ^ 1] ^ 1);
+                tc_fence_after();
+                const uint32_t d_a = tmem_u + (uint32_t)(acc * ACC_COLS), d_b = tmem_u + (uint32_t)((acc ^ 1) * ACC_COLS);
+#pragma unroll 1
+                for (int kc = 0; kc < nchunks; ++kc) {
+                    // region A's operand in stage sa; region B's (two-region pass) in the next stage of the ring
+                    const int sb = (sa + 1 == NSTAGE_A) ? 0 : sa + 1;
+                    const uint32_t pbs = (sa + 1 == NSTAGE_A) ? pa ^ 1 : pa;
+                    mbar_wait(bars0 + 8 * (A_FULL + sa), pa);
+                    if (two) mbar_wait(bars0 + 8 * (A_FULL + sb), pbs);
+                    tc_fence_after();
+                    const uint32_t apA = lo_of(a0 + sa * A_STAGE), apB = lo_of(a0 + sb * A_STAGE);
+#pragma unroll 1
+                    for (int tap = 0; tap < 3; ++tap) {
+                        mbar_wait(bars0 + 8 * (B_FULL + slot), pb);
+                        tc_fence_after();
+                        const uint32_t bp = lo_of(b0 + (slot + (lo_w ? 1 : 0)) * B_SLOT);
+                        const uint32_t roff = (uint32_t)((1 + 16 * tap) * ROWB) >> 4;       // halo pixel hp is operand row hp + 1
+                        if (leader) {
+#pragma unroll
+                            for (int k = 0; k < KSTEPS; ++k) umma_bf16(d_a, desc(apA + roff + 2 * k), desc(bp + 2 * k), IDESC, 1u);
+                            if (two) {
+#pragma unroll
+                                for (int k = 0; k < KSTEPS; ++k) umma_bf16(d_b, desc(apB + roff + 2 * k), desc(bp + 2 * k), IDESC, 1u);
+                            }
+                            umma_commit(bars0 + 8 * (B_EMPTY + slot));
+                        }
+                        slot += 2;
+                        if (slot >= p.nslot_b) slot = 0, pb ^= 1;
+                    }
+                    if (leader) {
+                        umma_commit(bars0 + 8 * (A_EMPTY + sa));
+                        if (two) umma_commit(bars0 + 8 * (A_EMPTY + sb));
+                    }
+                    if (++sa == NSTAGE_A) sa = 0, pa ^= 1;
+                    if (two && ++sa == NSTAGE_A) sa = 0, pa ^= 1;
+                }
+                if (leader) umma_commit(bars0 + 8 * (ACC_FULL + acc));
+                pacc[acc] ^= 1;
+                if (two) {                                   // both buffers used: hand both over, buffer order unchanged
+                    if (leader) umma_commit(bars0 + 8 * (ACC_FULL + (acc ^ 1)));
+                    pacc[acc ^ 1] ^= 1;
+                } else {
+                    acc ^= 1;
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp < W_EPI0) {
+        // ===================================================================== activation transform: fp32 x region style -> bf16 hi/lo stage
+        const int t = threadIdx.x - 32 * W_XFORM0;       // 0..255
+        const int c8 = t % CPR;
+        const int pix0 = t / CPR;
+        int sa = 0;
+        uint32_t pa = 0;
+        Walk wk;
+        wk.init(p, blockIdx.x, gridDim.x);
+        for (int it = blockIdx.x; it < p.items; it += gridDim.x, wk.advance(p)) {
+            const Item item = wk.cur;
+            uint32_t rem = tile_classes(p, item, lane);
+            const float* xb = p.x + (int64_t)item.b * p.h * p.w * p.cin;
+            const int y0 = item.ty * TH, x0 = item.tx * TW;
+            while (rem) {
+                int cls2[2];
+                next_pass(rem, cls2[0], cls2[1]);
+                const int nclass = cls2[1] >= 0 ? 2 : 1;
+                for (int kc = 0; kc < nchunks; ++kc) {
+                    const int ch = kc * KC + 8 * c8;
+                    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    float4 v0[NSW], v1[NSW];
+#pragma unroll
+                    for (int i = 0; i < NSW; ++i) {
+                        const int hp = pix0 + PPS * i;
+                        const int gy = y0 - 1 + (hp >> 4), gx = x0 - 1 + (hp & 15);
+                        v0[i] = zero4, v1[i] = zero4;
+                        if (hp < 160 && gy >= 0 && gy < p.h && gx >= 0 && gx < p.w) {
+                            const float* src = xb + ((int64_t)gy * p.w + gx) * p.cin + ch;
+                            v0[i] = __ldg(reinterpret_cast<const float4*>(src));
+                            v1[i] = __ldg(reinterpret_cast<const float4*>(src + 4));
+                        }
+                    }
+#pragma unroll 1
+                    for (int ci = 0; ci < nclass; ++ci) {
+                        const float* sc = p.s + ((int64_t)item.b * p.ncls + cls2[ci]) * p.cin;
+                        const float4 s0 = __ldg(reinterpret_cast<const float4*>(sc + ch));
+                        const float4 s1 = __ldg(reinterpret_cast<const float4*>(sc + ch + 4));
+                        mbar_wait(smem_u32(&bars[A_EMPTY + sa]), pa ^ 1);
+                        uint8_t* hi_plane = a_buf + sa * A_STAGE;
+                        uint8_t* lo_plane = hi_plane + A_PLANE;
+#pragma unroll
+                        for (int i = 0; i < NSW; ++i) {
+                            const int hp = pix0 + PPS * i;
+                            if (hp >= 160) continue;
+                            const int row = hp + 1;
+                            const float f[8] = {v0[i].x * s0.x, v0[i].y * s0.y, v0[i].z * s0.z, v0[i].w * s0.w,
+                                                v1[i].x * s1.x, v1[i].y * s1.y, v1[i].z * s1.z, v1[i].w * s1.w};
+                            uint32_t hi[4], lo[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float h0 = bf16_round(f[2 * j]), h1 = bf16_round(f[2 * j + 1]);
+                                hi[j] = pack_bf16x2(h0, h1);
+                                lo[j] = pack_bf16x2(f[2 * j] - h0, f[2 * j + 1] - h1);
+                            }
+                            const uint32_t sx = KC == 64 ? (uint32_t)(row & 7) : (uint32_t)((row >> 1) & 3);
+                            const uint32_t off = (uint32_t)row * ROWB + (((uint32_t)c8 ^ sx) << 4);
+                            *reinterpret_cast<uint4*>(hi_plane + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                            *reinterpret_cast<uint4*>(lo_plane + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                        }
+                        fence_proxy_async();
+                        mbar_arrive(smem_u32(&bars[A_FULL + sa]));
+                        if (++sa == NSTAGE_A) sa = 0, pa ^= 1;
+                    }
+                }
+            }
+        }
+    } else {
+        // ===================================================================== epilogue: horizontal half of the blur, region selection,
+        // demodulation, noise, bias, activation; one thread = one patch pixel (m, n') = two output rows x two output columns
+        const uint32_t quarter = (uint32_t)(warp & 3);
+        const int m_row = quarter * 32 + lane;
+        const int ty = m_row >> 4, tx = m_row & 15;
+        int acc = 0;
+        uint32_t pacc[2] = {0, 0};
+        const float nw = (p.noise && p.noise_w) ? __ldg(p.noise_w) : 0.f;
+        const float f0 = p.f0, f1 = p.f1, f2 = p.f2, f3 = p.f3;
+        const int ho = 2 * p.h, wo = 2 * p.w;
+        const uint32_t lanes = tmem_base + ((quarter * 32u) << 16);
+        auto fetch = [&](bool valid, const Item& i2, int (&c)[4], float (&z)[4]) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) c[q] = 0, z[q] = 0.f;
+            if (!valid) return;
+            const int iy = i2.ty * TH + ty, ix = i2.tx * TW + tx - 1;
+            if (!(tx >= 1 && tx <= TW && iy < p.h && ix < p.w)) return;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int oy = 2 * iy + (q >> 1), ox = 2 * ix + (q & 1);
+                if (p.label) c[q] = min((int)p.label[((int64_t)i2.b * ho + oy) * wo + ox], p.ncls - 1);
+                if (p.noise) z[q] = __ldg(p.noise + ((int64_t)(p.noise_b == 1 ? 0 : i2.b) * ho + oy) * wo + ox);
+            }
+        };
+        int cls_next[4];
+        float nz_next[4];
+        Walk wk;
+        wk.init(p, blockIdx.x, gridDim.x);
+        fetch(blockIdx.x < p.items, wk.cur, cls_next, nz_next);
+        for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
+            const Item item = wk.cur;
+            wk.advance(p);
+            const int iy = item.ty * TH + ty, ix = item.tx * TW + tx - 1;
+            const bool mine = tx >= 1 && tx <= TW && iy < p.h && ix < p.w;
+            const int n0 = item.nt * NTC;
+            int cls[4];
+            float nz[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) cls[q] = cls_next[q], nz[q] = nw * nz_next[q];
+            uint32_t rem = tile_classes(p, item, lane);
+            fetch(it + (int)gridDim.x < p.items, wk.cur, cls_next, nz_next);
+            while (rem) {
+                int ca, cb;
+                next_pass(rem, ca, cb);
+                const bool two = cb >= 0;
+                mbar_wait(smem_u32(&bars[ACC_FULL + acc]), pacc[acc]);
+                pacc[acc] ^= 1;
+                if (two) {
+                    mbar_wait(smem_u32(&bars[ACC_FULL + (acc ^ 1)]), pacc[acc ^ 1]);
+                    pacc[acc ^ 1] ^= 1;
+                }
+                tc_fence_after();
+                const uint32_t cbase = (uint32_t)(acc * ACC_COLS), cother = (uint32_t)((acc ^ 1) * ACC_COLS);
+#pragma unroll
+                for (int py = 0; py < 2; ++py) {
+                    const int c0 = cls[2 * py], c1 = cls[2 * py + 1];
+                    const bool w0 = mine && (c0 == ca || c0 == cb), w1 = mine && (c1 == ca || c1 == cb);
+                    const bool sel0 = two && c0 == cb, sel1 = two && c1 == cb;      // this output takes region B's combination
+                    const float* dm0 = p.demod ? p.demod + ((int64_t)item.b * p.ncls + c0) * p.cout + n0 : nullptr;
+                    const float* dm1 = p.demod ? p.demod + ((int64_t)item.b * p.ncls + c1) * p.cout + n0 : nullptr;
+                    float* dst0 = p.y + (((int64_t)item.b * ho + 2 * iy + py) * wo + 2 * ix) * p.cout + n0;
+                    float* dst1 = dst0 + p.cout;
+                    const float z0 = nz[2 * py], z1 = nz[2 * py + 1];
+#pragma unroll 1
+                    for (int jb = 0; jb < NTC / 8; ++jb) {
+                        float o0[8], o1[8];
+                        {
+                            uint32_t t0[8], t1[8], t2[8];
+                            const uint32_t col = cbase + (uint32_t)(3 * py * NTC + 8 * jb);
+                            tmem_ld8_nowait(lanes + col, t0);
+                            tmem_ld8_nowait(lanes + col + NTC, t1);
+                            tmem_ld8_nowait(lanes + col + 2 * NTC, t2);
+                            tmem_wait_ld();
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                const float a0 = __uint_as_float(t0[e]), a1 = __uint_as_float(t1[e]), a2 = __uint_as_float(t2[e]);
+                                const float l1 = __shfl_up_sync(0xffffffffu, a1, 1), l2 = __shfl_up_sync(0xffffffffu, a2, 1);
+                                const float r0 = __shfl_down_sync(0xffffffffu, a0, 1), r1 = __shfl_down_sync(0xffffffffu, a1, 1);
+                                o0[e] = f0 * l1 + f1 * l2 + f1 * a0 + f2 * a1 + f3 * a2 + f3 * r0;
+                                o1[e] = f0 * l2 + f0 * a0 + f1 * a1 + f2 * a2 + f2 * r0 + f3 * r1;
+                            }
+                        }
+                        if (two) {
+                            uint32_t t0[8], t1[8], t2[8];
+                            const uint32_t col = cother + (uint32_t)(3 * py * NTC + 8 * jb);
+                            tmem_ld8_nowait(lanes + col, t0);
+                            tmem_ld8_nowait(lanes + col + NTC, t1);
+                            tmem_ld8_nowait(lanes + col + 2 * NTC, t2);
+                            tmem_wait_ld();
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                const float a0 = __uint_as_float(t0[e]), a1 = __uint_as_float(t1[e]), a2 = __uint_as_float(t2[e]);
+                                const float l1 = __shfl_up_sync(0xffffffffu, a1, 1), l2 = __shfl_up_sync(0xffffffffu, a2, 1);
+                                const float r0 = __shfl_down_sync(0xffffffffu, a0, 1), r1 = __shfl_down_sync(0xffffffffu, a1, 1);
+                                const float b0 = f0 * l1 + f1 * l2 + f1 * a0 + f2 * a1 + f3 * a2 + f3 * r0;
+                                const float b1 = f0 * l2 + f0 * a0 + f1 * a1 + f2 * a2 + f2 * r0 + f3 * r1;
+                                if (sel0) o0[e] = b0;
+                                if (sel1) o1[e] = b1;
+                            }
+                        }
+                        const int co = 8 * jb;
+                        const float4 bv0 = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n0 + co)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        const float4 bv1 = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n0 + co + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        auto finish = [&](const float (&o)[8], const float* dm, float z, float* dst) {
+                            const float4 d0 = dm ? __ldg(reinterpret_cast<const float4*>(dm + co)) : make_float4(1.f, 1.f, 1.f, 1.f);
+                            const float4 d1 = dm ? __ldg(reinterpret_cast<const float4*>(dm + co + 4)) : make_float4(1.f, 1.f, 1.f, 1.f);
+                            float4 u, v;
+                            u.x = o[0] * d0.x + z + bv0.x, u.y = o[1] * d0.y + z + bv0.y, u.z = o[2] * d0.z + z + bv0.z, u.w = o[3] * d0.w + z + bv0.w;
+                            v.x = o[4] * d1.x + z + bv1.x, v.y = o[5] * d1.y + z + bv1.y, v.z = o[6] * d1.z + z + bv1.z, v.w = o[7] * d1.w + z + bv1.w;
+                            if (p.act) {
+                                const float k = 1.41421356237309515f;
+                                u.x = lrelu_scaled(u.x, 0.2f, k), u.y = lrelu_scaled(u.y, 0.2f, k), u.z = lrelu_scaled(u.z, 0.2f, k), u.w = lrelu_scaled(u.w, 0.2f, k);
+                                v.x = lrelu_scaled(v.x, 0.2f, k), v.y = lrelu_scaled(v.y, 0.2f, k), v.z = lrelu_scaled(v.z, 0.2f, k), v.w = lrelu_scaled(v.w, 0.2f, k);
+                            }
+                            st_global_v8(dst + co, u, v);
+                        };
+                        if (w0) finish(o0, dm0, z0, dst0);
+                        if (w1) finish(o1, dm1, z1, dst1);
+                    }
+                }
+                // every MMA accumulates: hand the buffers back zeroed
+#pragma unroll
+                for (int c = 0; c < N; c += 32) tmem_zero32(lanes + cbase + (uint32_t)c);
+                if (two) {
+#pragma unroll
+                    for (int c = 0; c < N; c += 32) tmem_zero32(lanes + cother + (uint32_t)c);
+                }
+                tmem_wait_st();
+                tc_fence_before();
+                mbar_arrive(smem_u32(&bars[ACC_EMPTY + acc]));
+                if (two) mbar_arrive(smem_u32(&bars[ACC_EMPTY + (acc ^ 1)]));
+                else acc ^= 1;
+            }
+        }
+    }
+
+    // ---- teardown
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+        else
+            cudaGetLastError();
+    });
+    return fn;
+}
+
+template <int NTC, int KC>
+static int launch(const void* v_hilo, Params p, cudaStream_t st) {
+    constexpr int N = NG * NTC, ROWB = KC * 2;
+    constexpr int A_BYTES = ((NSTAGE_A * 2 * A_ROWS * ROWB) + 1023) & ~1023;
+    constexpr int B_SLOT = N * ROWB;
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return E4S_ERR_ARCH;
+    CUtensorMap map;
+    // weights [2][6][3][Cout][Cin] bf16 as a 4-D tensor (Cin, Cout, row tap, hl * 6 + column group)
+    cuuint64_t dims[4] = {(cuuint64_t)p.cin, (cuuint64_t)p.cout, 3, (cuuint64_t)2 * NG};
+    cuuint64_t strides[3] = {(cuuint64_t)p.cin * 2, (cuuint64_t)p.cout * p.cin * 2, (cuuint64_t)3 * p.cout * p.cin * 2};
+    cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)NTC, 1, (cuuint32_t)2 * NG};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult cr = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(v_hilo), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return 700 + (int)cr;
+
+    p.tiles_x = (int)e4s_ceil_div(p.w, TW);
+    p.tiles_y = (int)e4s_ceil_div(p.h, TH);
+    p.n_tiles = p.cout / NTC;
+    const int64_t items = (int64_t)p.tiles_x * p.tiles_y * p.batch * p.n_tiles;
+    if (items >= (1ll << 31)) return E4S_ERR_SHAPE;
+    p.items = (int)items;
+    int max_slots = (SMEM_BUDGET - A_BYTES - 1024) / B_SLOT;
+    if (max_slots < 2) return E4S_ERR_SHAPE;
+    p.nslot_b = max_slots > 12 ? 12 : (max_slots & ~1);      // even: (hi, lo) slot pairs never straddle the ring wrap
+    const size_t smem = 1024 + A_BYTES + (size_t)p.nslot_b * B_SLOT + (size_t)(2 * NSTAGE_A + 2 * NACC + 2 * p.nslot_b) * 8 + 64;
+    static E4sSmemOptIn optin;
+    if (const int rc = e4s_smem_optin(optin, modconv3x3_up_tch_kernel<NTC, KC>, smem)) return rc;
+    const int sms = e4s_num_sms();
+    const int grid = p.items < sms ? p.items : sms;
+    modconv3x3_up_tch_kernel<NTC, KC><<<grid, NUM_THREADS, smem, st>>>(map, p);
+    return e4s_launch_status();
+}
+
+}  // namespace tch
+
+extern "C" int e4s_modconv3x3_up_tch_fwd(const float* x, const void* v_hilo_bf16, const float* s, const float* demod,
+                                         const uint8_t* label, const float* noise, const float* noise_w, const float* bias,
+                                         float* y, float fx0, float fx1, float fx2, float fx3, int batch, int h, int w, int cin,
+                                         int cout, int ncls, int noise_b, int act, void* stream) {
+    E4S_REQUIRE(x && v_hilo_bf16 && s && y, E4S_ERR_ARG);
+    E4S_REQUIRE(batch > 0 && h > 0 && w > 0 && cin > 0 && cout > 0 && ncls > 0 && ncls <= 32, E4S_ERR_ARG);
+    E4S_REQUIRE((cin % 32) == 0 && (cout % 32) == 0, E4S_ERR_SHAPE);
+    E4S_REQUIRE(label || ncls == 1, E4S_ERR_ARG);
+    E4S_REQUIRE(!noise || (noise_w && (noise_b == 1 || noise_b == batch)), E4S_ERR_ARG);
+    E4S_REQUIRE(e4s_aligned16(x) && e4s_aligned16(v_hilo_bf16) && e4s_aligned16(s) && (!demod || e4s_aligned16(demod)) &&
+                    (!bias || e4s_aligned16(bias)),
+                E4S_ERR_ALIGN);
+    E4S_REQUIRE((reinterpret_cast<uintptr_t>(y) & 31) == 0, E4S_ERR_ALIGN);          // 256-bit stores
+    tch::Params p{x, s, demod, label, noise, noise_w, bias, y, fx0, fx1, fx2, fx3, batch, h, w, cin, cout, ncls, noise_b, act ? 1 : 0,
+                  0, 0, 0, 0, 0};
+    if ((cin % 64) == 0) return tch::launch<32, 64>(v_hilo_bf16, p, (cudaStream_t)stream);
+    return tch::launch<32, 32>(v_hilo_bf16, p, (cudaStream_t)stream);
+}

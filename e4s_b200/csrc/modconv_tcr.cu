@@ -141,6 +141,12 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
         "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(dst),
+        "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(bar)
+        : "memory");
+}
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n.reg .pred p;\n"
@@ -220,18 +226,20 @@ struct Walk {
 };
 
 // Regions present among the valid (pixel, parity) outputs of a tile; one whole warp, every role recomputes it.
-template <int NPH>
+// UP2 (parity work items of an up-sampling layer): only the outputs (2 iy + py, 2 ix + px) of the item's own parity count.
+template <int NPH, bool UP2>
 __device__ __forceinline__ uint32_t tile_class_mask(const Params& p, const Item& it, int lane) {
     if (!p.label) return 1u;
-    constexpr int MUL = NPH == 4 ? 2 : 1;
+    constexpr int MUL = (NPH == 4 || UP2) ? 2 : 1;
     const int ho = p.h * MUL, wo = p.w * MUL;
+    const int py = UP2 ? ((it.nt >> 1) & 1) : 0, px = UP2 ? (it.nt & 1) : 0;
     uint32_t m = 0;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int r = lane + 32 * i;
         const int iy = it.ty * TH + (r >> 4), ix = it.tx * TW + (r & 15);
         if ((r & 15) < TW && iy < p.h && ix < p.w) {
-            const uint8_t* lp = p.label + ((int64_t)it.b * ho + iy * MUL) * wo + ix * MUL;
+            const uint8_t* lp = p.label + ((int64_t)it.b * ho + iy * MUL + py) * wo + ix * MUL + px;
             m |= 1u << min((int)lp[0], p.ncls - 1);
             if (NPH == 4) m |= (1u << min((int)lp[1], p.ncls - 1)) | (1u << min((int)lp[wo], p.ncls - 1)) | (1u << min((int)lp[wo + 1], p.ncls - 1));
         }
@@ -246,10 +254,19 @@ __device__ __forceinline__ void xform_barrier() { asm volatile("bar.sync 1, 256;
 // fill outside the image) through a 4-stage shared-memory ring by a dedicated producer warp, and the transform warps
 // convert shared -> shared.  Used for the small-K layers (Cin <= 64), which are HBM-bound: without it each tile
 // exposes a full DRAM latency in the transform warps (ncu: 11 % tensor pipe, 15 % DRAM on the 32->32 layer).
-template <int NTC, int KC, int NPH, bool XS>
+//
+// UP2 = true: an up-sampling layer run as PARITY WORK ITEMS.  A work item is (pixel tile, N tile, output parity): it is a
+// plain 3x3 convolution with that parity's folded kernel (NPH = 1 inside the MMA, N = NTC up to 256) whose outputs go to
+// (2 iy + py, 2 ix + px).  Against the NPH = 4 form (four parities along N, NTC <= 64) a region-pure tile costs the same
+// (N = 256 either way, one operand stage per chunk and 256 accumulator columns), but a tile that mixes regions stages
+// its row-class operand 9 times per chunk for MMAs of N = 256 instead of 36 times for MMAs of N = 64 - the masked
+// low-resolution up-sampling layers (>= 3 regions in most tiles at <= 64x64) were transform- and issue-bound at 27-33 %
+// tensor pipe (profiles/r1_ncu_tcr_17_layers.md).  Item::nt carries (N tile) * 4 + parity.
+template <int NTC, int KC, int NPH, bool XS, bool UP2>
 __global__ void __launch_bounds__(XS ? NUM_THREADS_XS : NUM_THREADS, 1)
 modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap xmap, Params p) {
     static_assert(!XS || KC == 32, "XS mode stages 32-channel chunks");
+    static_assert(!UP2 || (NPH == 1 && !XS), "parity work items are plain-convolution items");
     constexpr int N = NTC * NPH;
     constexpr int ROWB = KC * 2;
     constexpr int A_PLANE = A_ROWS * ROWB;
@@ -271,7 +288,7 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
     constexpr uint32_t IDESC_Q = IDESC_BASE | ((uint32_t)(NTC >> 3) << 17);       // one parity
     constexpr uint32_t DESC_HI = (uint32_t)((KC == 64 ? 1024u : 512u) >> 4) | (1u << 14) | ((KC == 64 ? 2u : 4u) << 29);
     constexpr int KSTEPS = KC / 16;
-    constexpr int MUL = NPH == 4 ? 2 : 1;
+    constexpr int MUL = (NPH == 4 || UP2) ? 2 : 1;
     constexpr int CPR = KC / 8;                       // 16-byte chunks per operand row
     constexpr int PPS = NUM_XFORM / CPR;              // pixels (rows) covered per sweep of the transform threads
     static_assert(N <= 256 && N % 16 == 0 && NTC % 16 == 0, "UMMA N");
@@ -364,7 +381,8 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                             if (!p.resident) MBAR_WAIT_P(smem_u32(&bars[B_EMPTY + slot]), ph ^ 1, 1);
                             const uint32_t full = smem_u32(&bars[B_FULL + slot]);
                             mbar_expect_tx(full, 2 * B_SLOT);
-                            tma_load_4d(smem_u32(b_buf + (size_t)slot * B_SLOT), &wmap, kc * KC, item.nt * NTC, tap, 0, full);
+                            if (UP2) tma_load_5d(smem_u32(b_buf + (size_t)slot * B_SLOT), &wmap, kc * KC, (item.nt >> 2) * NTC, tap, item.nt & 3, 0, full);
+                            else tma_load_4d(smem_u32(b_buf + (size_t)slot * B_SLOT), &wmap, kc * KC, item.nt * NTC, tap, 0, full);
                             slot += 2;
                             if (slot >= p.nslot_b) slot = 0, ph ^= 1;
                         }
@@ -394,7 +412,7 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
         wk.init(p, blockIdx.x, gridDim.x);
         for (int it = blockIdx.x; it < p.items; it += gridDim.x, wk.advance(p)) {
             const Item item = wk.cur;
-            const uint32_t classes = __shfl_sync(0xffffffffu, tile_class_mask<NPH>(p, item, lane), 0);
+            const uint32_t classes = __shfl_sync(0xffffffffu, tile_class_mask<NPH, UP2>(p, item, lane), 0);
             const bool mixed = (classes & (classes - 1)) != 0;
             const bool two = TWO_CLASS && __popc(classes) == 2;      // two regions: one accumulator buffer per region
             MBAR_WAIT_P(bars0 + 8 * (ACC_EMPTY + acc), (acc ? pacc1 : pacc0) ^ 1, 1);
@@ -518,7 +536,7 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
         wk.init(p, blockIdx.x, gridDim.x);
         for (int it = blockIdx.x; it < p.items; it += gridDim.x, wk.advance(p)) {
             const Item item = wk.cur;
-            const uint32_t classes = tile_class_mask<NPH>(p, item, lane);
+            const uint32_t classes = tile_class_mask<NPH, UP2>(p, item, lane);
             const bool mixed = (classes & (classes - 1)) != 0;
             const float* xb = p.x + (int64_t)item.b * p.h * p.w * p.cin;
             const int y0 = item.ty * TH, x0 = item.tx * TW;
@@ -608,7 +626,7 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                     const int iy = y0 + (r >> 4), ix = x0 + (r & 15);
                     rcls[i] = 0;
                     if ((r & 15) < TW && iy < p.h && ix < p.w) {
-                        const uint8_t* lp = p.label + ((int64_t)item.b * ho + iy * MUL) * wo + ix * MUL;
+                        const uint8_t* lp = p.label + ((int64_t)item.b * ho + iy * MUL + (UP2 ? ((item.nt >> 1) & 1) : 0)) * wo + ix * MUL + (UP2 ? (item.nt & 1) : 0);
                         uint32_t c0 = min((int)lp[0], p.ncls - 1);
                         rcls[i] = c0;
                         if (NPH == 4)
@@ -707,7 +725,8 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
             if (!(tx < TW && iy < p.h && ix < p.w && (!strided || ((iy | ix) & 1) == 0))) return;
 #pragma unroll
             for (int q = 0; q < NPH; ++q) {
-                const int oy = strided ? (iy >> 1) : iy * MUL + (q >> 1), ox = strided ? (ix >> 1) : ix * MUL + (q & 1);
+                const int qq = UP2 ? (i2.nt & 3) : q;
+                const int oy = strided ? (iy >> 1) : iy * MUL + (qq >> 1), ox = strided ? (ix >> 1) : ix * MUL + (qq & 1);
                 if (p.label) c[q] = min((int)p.label[((int64_t)i2.b * oh + oy) * ow + ox], p.ncls - 1);
                 if (p.noise) z[q] = __ldg(p.noise + ((int64_t)(p.noise_b == 1 ? 0 : i2.b) * oh + oy) * ow + ox);
             }
@@ -722,7 +741,7 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
             wk.advance(p);
             const int iy = item.ty * TH + ty, ix = item.tx * TW + tx;
             const bool mine = tx < TW && iy < p.h && ix < p.w && (!strided || ((iy | ix) & 1) == 0);
-            const int n0 = item.nt * NTC;
+            const int n0 = (UP2 ? (item.nt >> 2) : item.nt) * NTC;
             int cls[NPH];
             float nz[NPH];
 #pragma unroll
@@ -730,7 +749,7 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
             fetch(it + (int)gridDim.x < p.items, wk.cur, cls_next, nz_next);
             // two-region tile: region A (lowest index) accumulated in buffer `acc`, region B in the other one
             uint32_t classes = 1u;
-            if (TWO_CLASS) classes = tile_class_mask<NPH>(p, item, lane);
+            if (TWO_CLASS) classes = tile_class_mask<NPH, UP2>(p, item, lane);
             const bool two = TWO_CLASS && __popc(classes) == 2;
             const int cls_b = 31 - __clz(classes);
             MBAR_WAIT_P(smem_u32(&bars[ACC_FULL + acc]), pacc[acc], 1);
@@ -743,7 +762,8 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
             const uint32_t cbase = (uint32_t)(acc * ACC_COLS), cother = (uint32_t)((acc ^ 1) * ACC_COLS);
 #pragma unroll
             for (int q = 0; q < NPH; ++q) {
-                const int oy = strided ? (iy >> 1) : iy * MUL + (q >> 1), ox = strided ? (ix >> 1) : ix * MUL + (q & 1);
+                const int qq = UP2 ? (item.nt & 3) : q;
+                const int oy = strided ? (iy >> 1) : iy * MUL + (qq >> 1), ox = strided ? (ix >> 1) : ix * MUL + (qq & 1);
                 const float* dm = p.demod ? p.demod + ((int64_t)item.b * p.ncls + cls[q]) * p.cout + n0 : nullptr;
                 float* dst = p.y + (((int64_t)item.b * oh + oy) * ow + ox) * p.cout + n0;
 #pragma unroll 1
@@ -858,7 +878,7 @@ static int num_sms() { return e4s_num_sms(); }
 
 static long long* g_prof = nullptr;
 
-template <int NTC, int KC, int NPH, bool XS = false>
+template <int NTC, int KC, int NPH, bool XS = false, bool UP2 = false>
 static int launch(const void* w_hilo, Params p, cudaStream_t st) {
     p.prof = g_prof;
     constexpr int N = NTC * NPH, ROWB = KC * 2;
@@ -867,14 +887,27 @@ static int launch(const void* w_hilo, Params p, cudaStream_t st) {
     EncodeTiledFn enc = encode_fn();
     if (!enc) return E4S_ERR_ARCH;
     CUtensorMap map;
-    // weights [2][NPH][9][Cout][Cin] bf16 as a 4-D tensor (Cin, Cout, tap, hl * NPH + parity)
-    cuuint64_t dims[4] = {(cuuint64_t)p.cin, (cuuint64_t)p.cout, 9, (cuuint64_t)2 * NPH};
-    cuuint64_t strides[3] = {(cuuint64_t)p.cin * 2, (cuuint64_t)p.cout * p.cin * 2, (cuuint64_t)9 * p.cout * p.cin * 2};
-    cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)NTC, 1, (cuuint32_t)2 * NPH};
-    cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult cr = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(w_hilo), dims, strides, box, estr,
-                      CU_TENSOR_MAP_INTERLEAVE_NONE, KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
-                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult cr;
+    if (UP2) {
+        // weights [2][4][9][Cout][Cin] bf16 as a 5-D tensor (Cin, Cout, tap, parity, hl); one box = the (hi, lo) planes of ONE parity
+        cuuint64_t dims[5] = {(cuuint64_t)p.cin, (cuuint64_t)p.cout, 9, 4, 2};
+        cuuint64_t strides[4] = {(cuuint64_t)p.cin * 2, (cuuint64_t)p.cout * p.cin * 2, (cuuint64_t)9 * p.cout * p.cin * 2,
+                                 (cuuint64_t)4 * 9 * p.cout * p.cin * 2};
+        cuuint32_t box[5] = {(cuuint32_t)KC, (cuuint32_t)NTC, 1, 1, 2};
+        cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+        cr = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(w_hilo), dims, strides, box, estr,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+        // weights [2][NPH][9][Cout][Cin] bf16 as a 4-D tensor (Cin, Cout, tap, hl * NPH + parity)
+        cuuint64_t dims[4] = {(cuuint64_t)p.cin, (cuuint64_t)p.cout, 9, (cuuint64_t)2 * NPH};
+        cuuint64_t strides[3] = {(cuuint64_t)p.cin * 2, (cuuint64_t)p.cout * p.cin * 2, (cuuint64_t)9 * p.cout * p.cin * 2};
+        cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)NTC, 1, (cuuint32_t)2 * NPH};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        cr = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(w_hilo), dims, strides, box, estr,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
     if (cr != CUDA_SUCCESS) return 700 + (int)cr;
     CUtensorMap xmap = map;          // placeholder when the activation is not TMA-staged
     if (XS) {
@@ -891,7 +924,7 @@ static int launch(const void* w_hilo, Params p, cudaStream_t st) {
     p.tiles_x = (int)e4s_ceil_div(p.w, TW);
     p.tiles_y = (int)e4s_ceil_div(p.h, TH);
     p.n_tiles = p.cout / NTC;
-    const int64_t items = (int64_t)p.tiles_x * p.tiles_y * p.batch * p.n_tiles;
+    const int64_t items = (int64_t)p.tiles_x * p.tiles_y * p.batch * p.n_tiles * (UP2 ? 4 : 1);
     if (items >= (1ll << 31)) return E4S_ERR_SHAPE;
     p.items = (int)items;
     const int planes = (p.cin / KC) * 18;
@@ -899,15 +932,15 @@ static int launch(const void* w_hilo, Params p, cudaStream_t st) {
     int max_slots = (SMEM_BUDGET - A_BYTES - tab_bytes - 1024) / B_SLOT;
     if (max_slots > 36) max_slots = 36;
     if (max_slots < 4) return E4S_ERR_SHAPE;
-    p.resident = (p.n_tiles == 1 && planes <= max_slots) ? 1 : 0;
+    p.resident = (!UP2 && p.n_tiles == 1 && planes <= max_slots) ? 1 : 0;     // parity items change weights with every item
     // streamed weights: a deep ring (TMA latency ~2000 cycles against 4 MMAs per slot pair on the small-N layers);
     // even, so that (hi, lo) pairs never straddle the wrap
     p.nslot_b = p.resident ? planes : (max_slots > 16 ? 16 : (max_slots & ~1));
     const size_t smem = 1024 + A_BYTES + (size_t)p.nslot_b * B_SLOT + tab_bytes + (size_t)(2 * NSTAGE_A + 4 + 2 * p.nslot_b + 2 * NXS) * 8 + 64;
     static E4sSmemOptIn optin;
-    if (const int rc = e4s_smem_optin(optin, modconv3x3_tcr_kernel<NTC, KC, NPH, XS>, smem)) return rc;
+    if (const int rc = e4s_smem_optin(optin, modconv3x3_tcr_kernel<NTC, KC, NPH, XS, UP2>, smem)) return rc;
     const int grid = p.items < num_sms() ? p.items : num_sms();
-    modconv3x3_tcr_kernel<NTC, KC, NPH, XS><<<grid, XS ? NUM_THREADS_XS : NUM_THREADS, smem, st>>>(map, xmap, p);
+    modconv3x3_tcr_kernel<NTC, KC, NPH, XS, UP2><<<grid, XS ? NUM_THREADS_XS : NUM_THREADS, smem, st>>>(map, xmap, p);
     return e4s_launch_status();
 }
 
@@ -956,6 +989,22 @@ int dispatch(const void* w_hilo_bf16, Params p, int up, cudaStream_t st) {
         }
         if (pick_ntile(cout, 64, pixel_tiles) == 64) return launch<64, 32, 1>(w_hilo_bf16, p, st);
         return launch<32, 32, 1>(w_hilo_bf16, p, st);
+    }
+    // Up-sampling layer.  Parity work items (UP2, N tiles up to 256 wide) when the layer is wide enough for them to be no
+    // worse on region-pure tiles (Cout >= 256: same MMA shape and operand re-use as four parities x 64 channels) - i.e. the
+    // 512-channel layers up to 128x128, whose tiles mostly mix >= 3 regions; E4S_B200_UP2=1|0 forces / forbids it.
+    if (k64) {
+        int want = (cin >= 128 && cout >= 256) ? 1 : 0;
+        if (const char* f = getenv("E4S_B200_UP2")) want = atoi(f) != 0;
+        if (want) {
+            const int ntu = pick_ntile(cout, 256, pixel_tiles * 4);
+            int rc = E4S_ERR_SHAPE;
+            if (ntu == 256) rc = launch<256, 64, 1, false, true>(w_hilo_bf16, p, st);
+            if (rc == E4S_ERR_SHAPE && ntu >= 128 && cout % 128 == 0) rc = launch<128, 64, 1, false, true>(w_hilo_bf16, p, st);
+            if (rc == E4S_ERR_SHAPE && ntu >= 64 && cout % 64 == 0) rc = launch<64, 64, 1, false, true>(w_hilo_bf16, p, st);
+            if (rc == E4S_ERR_SHAPE) rc = launch<32, 64, 1, false, true>(w_hilo_bf16, p, st);
+            return rc;
+        }
     }
     const int nt = pick_ntile(cout, 64, pixel_tiles);
     if (k64) {

@@ -440,6 +440,28 @@ def test_tcr_kernel_every_n_tile_width(monkeypatch, ntile, b, cin, cout, hw, up,
     assert_close(out, ref, 1e-4, f"tcr vs simt, N tile {ntile}: {b},{cin},{cout},{hw},{up},{ncls},{kind}")
 
 
+@pytest.mark.parametrize("up2", ["0", "1"])
+@pytest.mark.parametrize("b,cin,cout,hw,up,ncls,kind", [
+    (1, 512, 512, 16, True, 3, "iid"),        # N tile 256 (the auto choice for the 512-channel up-sampling layers)
+    (4, 512, 512, 8, True, 12, "blobs"),
+    (2, 512, 256, 24, True, 12, "blobs"),     # c8's channels; partial tiles; pure, two-region and mixed tiles
+    (1, 256, 128, 40, True, 5, "blobs"),      # N tile 128
+    (2, 128, 64, 20, True, 2, "iid"),         # N tile 64
+    (1, 192, 32, 16, True, 12, "iid"),        # N tile 32, three K chunks
+    (1, 128, 256, 16, True, 1, "blobs"),      # unmasked
+])
+def test_tcr_kernel_parity_work_items(monkeypatch, up2, b, cin, cout, hw, up, ncls, kind):
+    """Up-sampling layers as parity work items (csrc/modconv_tcr.cu, UP2: one (tile, N tile, output parity) per item, N
+    tiles up to 256 wide) and as four parities along N give the same result as the fp32 SIMT kernel."""
+    monkeypatch.setenv("E4S_B200_UP2", up2)
+    K, prep, x, args = _tc_case(b, cin, cout, hw, up, ncls, kind, seed=cin + cout + hw)
+    ref = K.modconv3x3_fwd(x, prep.wt, *args)
+    out = K.modconv3x3_tcr_fwd(x, prep.w_hilo, *args)
+    torch.cuda.synchronize()
+    e = assert_close(out, ref, 1e-4, f"tcr (UP2={up2}) vs simt {b},{cin},{cout},{hw},{up},{ncls},{kind}")
+    print(f"tcr-vs-simt UP2={up2} rel err {e:.2e}")
+
+
 @pytest.mark.parametrize("b,cin,cout,hw,up,ncls,kind", PRODUCTION_CASES)
 def test_tcr_kernel_production_shapes(b, cin, cout, hw, up, ncls, kind):
     K, prep, x, args = _tc_case(b, cin, cout, hw, up, ncls, kind, seed=cin + cout + hw)
