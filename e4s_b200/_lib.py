@@ -36,8 +36,10 @@ SIGNATURES = {
     "e4s_demod_f32": [P, P, P, c_int, c_int, c_int, c_float, P],
     "e4s_modconv3x3_fwd_f32": [P] * 9 + [c_int] * 9 + [P],
     "e4s_modconv3x3_tcr_fwd": [P] * 9 + [c_int] * 9 + [P],
+    "e4s_modconv3x3_up_tch_fwd": [P] * 9 + [c_float] * 4 + [c_int] * 8 + [P],
     "e4s_conv3x3_tcr_f32": [P] * 6 + [c_int] * 6 + [P],
     "e4s_tcr_set_profile": [P],
+    "e4s_tch_set_profile": [P],
     "e4s_instnorm_affine_f32": [P] * 4 + [c_int] * 4 + [c_float, P],
     "e4s_norm_residual_f32": [P, P, P, c_float, P, P, P, c_int, P, P] + [c_int] * 4 + [P],
     "e4s_modconv3x3_bwd_f32": [P] * 9 + [c_int] * 8 + [P],

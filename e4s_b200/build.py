@@ -68,17 +68,17 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 def build_profile(verbose: bool = False) -> str:
-    """Diagnostic twin of the library with the gen-4 kernel's stall counters compiled in (tools/opbench.py --prof):
+    """Diagnostic twin of the library with the tensor-core kernels' stall counters compiled in (tools/opbench.py --prof):
     libe4s_b200_prof.so, selected with E4S_B200_LIB=<path>."""
     build(verbose=verbose)
     objdir = os.path.join(CSRC, "_obj_prof")
     os.makedirs(objdir, exist_ok=True)
-    src = os.path.join(CSRC, "modconv_tcr.cu")
-    obj, _ = _compile(src, verbose, objdir, ["-DE4S_TCR_PROFILE"])
-    others = [os.path.join(OBJ, os.path.basename(s)[:-3] + ".o") for s in sorted(glob.glob(os.path.join(CSRC, "*.cu"))) if s != src]
+    prof_srcs = [os.path.join(CSRC, "modconv_tcr.cu"), os.path.join(CSRC, "modconv_tch.cu")]
+    prof_objs = [_compile(src, verbose, objdir, ["-DE4S_TC_PROFILE"])[0] for src in prof_srcs]
+    others = [os.path.join(OBJ, os.path.basename(s)[:-3] + ".o") for s in sorted(glob.glob(os.path.join(CSRC, "*.cu"))) if s not in prof_srcs]
     lib = os.path.join(PKG, "libe4s_b200_prof.so")
-    if _newer([obj] + others, lib):
-        r = subprocess.run([NVCC] + ARCH + ["-shared", "-o", lib, obj] + others + ["-lcudart", "-lcuda"], capture_output=True, text=True)
+    if _newer(prof_objs + others, lib):
+        r = subprocess.run([NVCC] + ARCH + ["-shared", "-o", lib] + prof_objs + others + ["-lcudart", "-lcuda"], capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     return lib

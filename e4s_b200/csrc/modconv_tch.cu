@@ -58,7 +58,15 @@ struct Params {
     float f0, f1, f2, f3;                       // flipped horizontal FIR taps
     int batch, h, w, cin, cout, ncls, noise_b, act;
     int tiles_x, tiles_y, n_tiles, items, nslot_b;
+    long long* prof;      // optional [4 roles][4] cycle counters of CTA 0 (e4s_tch_set_profile; diagnostic build only)
 };
+
+// Stall attribution (tools/opbench.py --prof): only in the diagnostic build (-DE4S_TC_PROFILE, libe4s_b200_prof.so).
+#ifdef E4S_TC_PROFILE
+#define TCH_WAIT(bar, parity, k) do { if (prof_on) { const long long t_ = clock64(); mbar_wait(bar, parity); pw[k] += clock64() - t_; } else mbar_wait(bar, parity); } while (0)
+#else
+#define TCH_WAIT(bar, parity, k) mbar_wait(bar, parity)
+#endif
 
 struct Item {
     int b, ty, tx, nt;
@@ -145,6 +153,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) modconv3x3_up_tch_kernel(const
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nchunks = p.cin / KC;
+#ifdef E4S_TC_PROFILE
+    const bool prof_on = p.prof != nullptr && blockIdx.x == 0;
+    long long pw[4] = {0, 0, 0, 0};                      // [0] role time, [1..3] cycles in its barrier waits
+    const long long t_start = prof_on ? clock64() : 0;
+#endif
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < NSTAGE_A; ++i) mbar_init(smem_u32(&bars[A_FULL + i]), NUM_XFORM), mbar_init(smem_u32(&bars[A_EMPTY + i]), NUM_MMA_WARPS);
@@ -185,7 +198,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) modconv3x3_up_tch_kernel(const
                 for (int ps = 0; ps < npass; ++ps)
                     for (int kc = 0; kc < nchunks; ++kc)
                         for (int tap = 0; tap < 3; ++tap) {
-                            mbar_wait(smem_u32(&bars[B_EMPTY + slot]), ph ^ 1);
+                            TCH_WAIT(smem_u32(&bars[B_EMPTY + slot]), ph ^ 1, 1);
                             const uint32_t full = smem_u32(&bars[B_FULL + slot]);
                             mbar_expect_tx(full, 2 * B_SLOT);
                             tma_load_4d(smem_u32(b_buf + (size_t)slot * B_SLOT), &wmap, kc * KC, item.nt * NTC, tap, 0, full);
@@ -216,8 +229,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) modconv3x3_up_tch_kernel(const
                 int ca, cb;
                 next_pass(rem, ca, cb);
                 const bool two = cb >= 0;
-                mbar_wait(bars0 + 8 * (ACC_EMPTY + acc), pacc[acc] ^ 1);
-                if (two) mbar_wait(bars0 + 8 * (ACC_EMPTY + (acc ^ 1)), pacc[acc ^ 1] ^ 1);
+                TCH_WAIT(bars0 + 8 * (ACC_EMPTY + acc), pacc[acc] ^ 1, 1);
+                if (two) TCH_WAIT(bars0 + 8 * (ACC_EMPTY + (acc ^ 1)), pacc[acc ^ 1] ^ 1, 1);
                 tc_fence_after();
                 const uint32_t d_a = tmem_u + (uint32_t)(acc * ACC_COLS), d_b = tmem_u + (uint32_t)((acc ^ 1) * ACC_COLS);
 #pragma unroll 1
@@ -225,13 +238,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) modconv3x3_up_tch_kernel(const
                     // region A's operand in stage sa; region B's (two-region pass) in the next stage of the ring
                     const int sb = (sa + 1 == NSTAGE_A) ? 0 : sa + 1;
                     const uint32_t pbs = (sa + 1 == NSTAGE_A) ? pa ^ 1 : pa;
-                    mbar_wait(bars0 + 8 * (A_FULL + sa), pa);
-                    if (two) mbar_wait(bars0 + 8 * (A_FULL + sb), pbs);
+                    TCH_WAIT(bars0 + 8 * (A_FULL + sa), pa, 2);
+                    if (two) TCH_WAIT(bars0 + 8 * (A_FULL + sb), pbs, 2);
                     tc_fence_after();
                     const uint32_t apA = lo_of(a0 + sa * A_STAGE), apB = lo_of(a0 + sb * A_STAGE);
 #pragma unroll 1
                     for (int tap = 0; tap < 3; ++tap) {
-                        mbar_wait(bars0 + 8 * (B_FULL + slot), pb);
+                        TCH_WAIT(bars0 + 8 * (B_FULL + slot), pb, 3);
                         tc_fence_after();
                         const uint32_t bp = lo_of(b0 + (slot + (lo_w ? 1 : 0)) * B_SLOT);
                         const uint32_t roff = (uint32_t)((1 + 16 * tap) * ROWB) >> 4;       // halo pixel hp is operand row hp + 1
@@ -303,7 +316,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) modconv3x3_up_tch_kernel(const
                         const float* sc = p.s + ((int64_t)item.b * p.ncls + cls2[ci]) * p.cin;
                         const float4 s0 = __ldg(reinterpret_cast<const float4*>(sc + ch));
                         const float4 s1 = __ldg(reinterpret_cast<const float4*>(sc + ch + 4));
-                        mbar_wait(smem_u32(&bars[A_EMPTY + sa]), pa ^ 1);
+                        TCH_WAIT(smem_u32(&bars[A_EMPTY + sa]), pa ^ 1, 1);
                         uint8_t* hi_plane = a_buf + sa * A_STAGE;
                         uint8_t* lo_plane = hi_plane + A_PLANE;
 #pragma unroll
@@ -378,10 +391,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) modconv3x3_up_tch_kernel(const
                 int ca, cb;
                 next_pass(rem, ca, cb);
                 const bool two = cb >= 0;
-                mbar_wait(smem_u32(&bars[ACC_FULL + acc]), pacc[acc]);
+                TCH_WAIT(smem_u32(&bars[ACC_FULL + acc]), pacc[acc], 1);
                 pacc[acc] ^= 1;
                 if (two) {
-                    mbar_wait(smem_u32(&bars[ACC_FULL + (acc ^ 1)]), pacc[acc ^ 1]);
+                    TCH_WAIT(smem_u32(&bars[ACC_FULL + (acc ^ 1)]), pacc[acc ^ 1], 1);
                     pacc[acc ^ 1] ^= 1;
                 }
                 tc_fence_after();
@@ -402,10 +415,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) modconv3x3_up_tch_kernel(const
                         {
                             uint32_t t0[8], t1[8], t2[8];
                             const uint32_t col = cbase + (uint32_t)(3 * py * NTC + 8 * jb);
-                            tmem_ld8_nowait(lanes + col, t0);
-                            tmem_ld8_nowait(lanes + col + NTC, t1);
-                            tmem_ld8_nowait(lanes + col + 2 * NTC, t2);
-                            tmem_wait_ld();
+                            tmem_ld8x3(lanes + col, lanes + col + NTC, lanes + col + 2 * NTC, t0, t1, t2);
 #pragma unroll
                             for (int e = 0; e < 8; ++e) {
                                 const float a0 = __uint_as_float(t0[e]), a1 = __uint_as_float(t1[e]), a2 = __uint_as_float(t2[e]);
@@ -418,10 +428,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) modconv3x3_up_tch_kernel(const
                         if (two) {
                             uint32_t t0[8], t1[8], t2[8];
                             const uint32_t col = cother + (uint32_t)(3 * py * NTC + 8 * jb);
-                            tmem_ld8_nowait(lanes + col, t0);
-                            tmem_ld8_nowait(lanes + col + NTC, t1);
-                            tmem_ld8_nowait(lanes + col + 2 * NTC, t2);
-                            tmem_wait_ld();
+                            tmem_ld8x3(lanes + col, lanes + col + NTC, lanes + col + 2 * NTC, t0, t1, t2);
 #pragma unroll
                             for (int e = 0; e < 8; ++e) {
                                 const float a0 = __uint_as_float(t0[e]), a1 = __uint_as_float(t1[e]), a2 = __uint_as_float(t2[e]);
@@ -469,6 +476,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) modconv3x3_up_tch_kernel(const
         }
     }
 
+#ifdef E4S_TC_PROFILE
+    if (prof_on && lane == 0) {
+        const int role = warp == 0 ? 0 : warp == 1 ? 1 : warp == W_XFORM0 ? 2 : warp == W_EPI0 ? 3 : -1;
+        if (role >= 0) {
+            pw[0] = clock64() - t_start;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) p.prof[role * 4 + k] = pw[k];
+        }
+    }
+#endif
     // ---- teardown
     tc_fence_before();
     __syncthreads();
@@ -498,8 +515,11 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
+static long long* g_prof = nullptr;
+
 template <int NTC, int KC>
 static int launch(const void* v_hilo, Params p, cudaStream_t st) {
+    p.prof = g_prof;
     constexpr int N = NG * NTC, ROWB = KC * 2;
     constexpr int A_BYTES = ((NSTAGE_A * 2 * A_ROWS * ROWB) + 1023) & ~1023;
     constexpr int B_SLOT = N * ROWB;
@@ -550,7 +570,18 @@ extern "C" int e4s_modconv3x3_up_tch_fwd(const float* x, const void* v_hilo_bf16
                 E4S_ERR_ALIGN);
     E4S_REQUIRE((reinterpret_cast<uintptr_t>(y) & 31) == 0, E4S_ERR_ALIGN);          // 256-bit stores
     tch::Params p{x, s, demod, label, noise, noise_w, bias, y, fx0, fx1, fx2, fx3, batch, h, w, cin, cout, ncls, noise_b, act ? 1 : 0,
-                  0, 0, 0, 0, 0};
+                  0, 0, 0, 0, 0, nullptr};
     if ((cin % 64) == 0) return tch::launch<32, 64>(v_hilo_bf16, p, (cudaStream_t)stream);
     return tch::launch<32, 32>(v_hilo_bf16, p, (cudaStream_t)stream);
+}
+
+// Diagnostic: per-role stall attribution of CTA 0 of every following H-form launch ([4 roles][4] int64 cycle counters in
+// device memory: role time, then the cycles it spent in its barrier waits).  nullptr switches it off (the default).
+extern "C" int e4s_tch_set_profile(long long* device_counters) {
+#ifdef E4S_TC_PROFILE
+    tch::g_prof = device_counters;
+    return E4S_OK;
+#else
+    return device_counters ? E4S_ERR_ARG : E4S_OK;      // production build carries no counters
+#endif
 }

@@ -321,6 +321,22 @@ def modconv3x3_tcr_fwd(x_pm: Tensor, w_hilo: Tensor, s: Tensor, dm: Optional[Ten
     return y
 
 
+def modconv3x3_up_tch_fwd(x_pm: Tensor, v_hilo: Tensor, fx, s: Tensor, dm: Optional[Tensor], label: Optional[Tensor],
+                          noise: Optional[Tensor], noise_w: Optional[Tensor], bias: Optional[Tensor], act: bool) -> Tensor:
+    """Up-sampling layer in the H-form (half the MACs of the polyphase form); v_hilo: bf16 [2, 6, 3, Cout, Cin] (vertical half
+    of the blur folded into the weights), fx: the four flipped horizontal FIR taps (python floats)."""
+    b, h, w, cin = x_pm.shape
+    cout = v_hilo.shape[3]
+    ncls = s.shape[1]
+    y = torch.empty((b, 2 * h, 2 * w, cout), device=x_pm.device, dtype=torch.float32)
+    nb = noise.shape[0] if noise is not None else 1
+    with torch.cuda.device(x_pm.device):
+        _call("e4s_modconv3x3_up_tch_fwd", _lib.load().e4s_modconv3x3_up_tch_fwd, ptr(x_pm), ptr(v_hilo), ptr(s), ptr(dm), ptr(label),
+              ptr(noise), ptr(noise_w), ptr(bias), ptr(y), float(fx[0]), float(fx[1]), float(fx[2]), float(fx[3]),
+              b, h, w, cin, cout, ncls, nb, int(act), stream_ptr(), work=2.0 * 9 * cin * cout * b * h * w)
+    return y
+
+
 def torgb_fwd(x_pm: Tensor, wrgb: Tensor, s: Tensor, label: Optional[Tensor], bias: Optional[Tensor],
               skip: Optional[Tensor], fir: Optional[Tensor]) -> Tensor:
     """x_pm [B,H,W,Cin]; wrgb [3,Cin]; s [B,ncls,Cin]; skip planar [B,3,H/2,W/2]|None -> planar [B,3,H,W]."""

@@ -139,9 +139,20 @@ int e4s_modconv3x3_tcr_fwd(const float* x, const void* w_hilo_bf16, const float*
                            const uint8_t* label, const float* noise, const float* noise_w, const float* bias,
                            float* y, int batch, int h, int w, int cin, int cout, int ncls, int up, int noise_b,
                            int act, void* stream);
+/* Up-sampling StyledConv (conv_transpose2d stride 2 + 4x4 blur, model.py:287-300) in the H-FORM (csrc/modconv_tch.cu):
+ * same contract as e4s_modconv3x3_tcr_fwd with up = 1, at half its multiply-accumulates.  The blur must be separable
+ * (fir = outer(fy, fx), as every make_kernel() FIR is): its vertical half is folded into the weights,
+ * v_hilo_bf16 = [2 (hi, lo)][6 (py * 3 + kx)][3 (dy)][Cout][Cin], V[py, kx][dy] = sum_ky fy_flipped[2 (dy - 1) + ky + 1 - py] W[ky, kx];
+ * its horizontal half runs in the epilogue with fx0..fx3 = the FLIPPED horizontal taps.  x: [B, H, W, Cin], y: [B, 2H, 2W, Cout]. */
+int e4s_modconv3x3_up_tch_fwd(const float* x, const void* v_hilo_bf16, const float* s, const float* demod,
+                              const uint8_t* label, const float* noise, const float* noise_w, const float* bias,
+                              float* y, float fx0, float fx1, float fx2, float fx3, int batch, int h, int w, int cin,
+                              int cout, int ncls, int noise_b, int act, void* stream);
 /* Diagnostic (no reference counterpart): per-role stall attribution of CTA 0 of every following gen-4 launch.
  * device_counters: [5 roles][4] int64 in device memory (role time, cycles in its barrier waits); NULL = off. */
 int e4s_tcr_set_profile(long long* device_counters);
+/* Same for the H-form kernel: [4 roles][4] int64. */
+int e4s_tch_set_profile(long long* device_counters);
 
 /* ---- RGI encoder conv stack (src/models/encoders/helpers.py:122-144, psp_encoders.py:285-309) ------------------
  * Plain 3x3 convolution, padding 1, stride 1 or 2 (out_stride), on the persistent tensor-core kernel.

@@ -462,6 +462,55 @@ def test_tcr_kernel_parity_work_items(monkeypatch, up2, b, cin, cout, hw, up, nc
     print(f"tcr-vs-simt UP2={up2} rel err {e:.2e}")
 
 
+@pytest.mark.parametrize("b,cin,cout,hw,ncls,kind", [
+    (1, 64, 32, 16, 1, "blobs"),              # one K chunk of 64, one region, one N tile
+    (2, 128, 64, 20, 1, "blobs"),             # two chunks, two N tiles, partial tiles in both directions
+    (1, 96, 32, 18, 1, "blobs"),              # 32-channel chunks (64-byte swizzle) x 3
+    (2, 64, 128, 16, 4, "blobs"),             # region borders: one- and two-region passes
+    (1, 128, 64, 32, 2, "iid"),               # every tile holds exactly two regions: one pass, both accumulator buffers
+    (1, 128, 32, 30, 3, "iid"),               # three regions: a two-region pass, then a one-region pass
+    (1, 256, 64, 16, 12, "iid"),              # every tile holds all twelve regions: six passes
+    (4, 512, 512, 8, 12, "blobs"),            # the low-resolution 512-channel layers (16 N tiles)
+    (1, 256, 128, 128, 12, "blobs"),          # c10 ^256 of the 1024x1024 generator, masked, B = 1
+    (1, 128, 64, 256, 1, "blobs"),            # c12 ^512: several work items per persistent CTA
+    (1, 64, 32, 512, 1, "blobs"),             # c14 ^1024
+])
+def test_tch_kernel_matches_simt(b, cin, cout, hw, ncls, kind):
+    """The H-form up-sampling kernel (csrc/modconv_tch.cu: vertical blur half folded into the weights, horizontal half and
+    region selection in the epilogue; half the MACs of the polyphase form) against the fp32 SIMT kernel."""
+    K, prep, x, args = _tc_case(b, cin, cout, hw, True, ncls, kind, seed=cin + cout + hw)
+    assert prep.v_hilo is not None and tuple(prep.v_hilo.shape) == (2, 6, 3, cout, cin)
+    s, dm, label, noise, nw, bias, up, act = args
+    ref = K.modconv3x3_fwd(x, prep.wt, *args)
+    out = K.modconv3x3_up_tch_fwd(x, prep.v_hilo, prep.fx, s, dm, label, noise, nw, bias, act)
+    torch.cuda.synchronize()
+    e = assert_close(out, ref, 1e-4, f"tch vs simt {b},{cin},{cout},{hw},{ncls},{kind}")
+    print(f"tch-vs-simt rel err {e:.2e}")
+
+
+def test_tch_kernel_asymmetric_fir_and_no_epilogue_inputs():
+    """H-form with an asymmetric separable FIR (true convolution: the flipped taps matter), no noise, no bias, no activation,
+    no demodulation - against conv_transpose2d + upfirdn2d of the oracle."""
+    from e4s_b200 import kernels as K
+    from e4s_b200.stylegan2.modconv import PreparedConv
+    g = torch.Generator().manual_seed(11)
+    cin, cout, hw = 64, 32, 12
+    w = torch.randn(1, cout, cin, 3, 3, generator=g)
+    fa, fb = torch.tensor([1., 2., 4., 3.]), torch.tensor([2., 1., 5., 1.])
+    fir = torch.outer(fa, fb)
+    fir = fir / fir.sum() * 4
+    prep = PreparedConv().get(cu(w), True, cu(fir))
+    assert prep.v_hilo is not None
+    x = torch.randn(1, hw, hw, cin, generator=g)
+    s = 1.0 + 0.3 * torch.randn(1, 1, cin, generator=g)
+    out = K.modconv3x3_up_tch_fwd(cu(x), prep.v_hilo, prep.fx, cu(s), None, None, None, None, None, False)
+    xs = (x * s[:, 0][:, None, None, :]).permute(0, 3, 1, 2).double()
+    wt = (w[0] / (cin * 9) ** 0.5).double()
+    u = torch.nn.functional.conv_transpose2d(xs, wt.transpose(0, 1), stride=2)
+    ref = O.upfirdn2d(u.float(), fir, pad=(1, 1)).permute(0, 2, 3, 1)
+    assert_close(out, ref, 1e-4, "tch, asymmetric FIR, bare conv")
+
+
 @pytest.mark.parametrize("b,cin,cout,hw,up,ncls,kind", PRODUCTION_CASES)
 def test_tcr_kernel_production_shapes(b, cin, cout, hw, up, ncls, kind):
     K, prep, x, args = _tc_case(b, cin, cout, hw, up, ncls, kind, seed=cin + cout + hw)

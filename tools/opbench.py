@@ -43,7 +43,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "opbench.json"))
-    ap.add_argument("--conv", default="tcr", help="comma list of simt,tcr")
+    ap.add_argument("--conv", default="tcr", help="comma list of simt,tcr,tch")
     ap.add_argument("--layers", default="all")
     ap.add_argument("--prof", action="store_true", help="gen-4 kernel: per-role stall attribution of CTA 0 (e4s_tcr_set_profile)")
     ap.add_argument("--only-conv", action="store_true", help="skip the HBM-bound kernels")
@@ -139,21 +139,29 @@ def conv_rows(args, B, fir, flush, row, res):
                 if prep.w_hilo is None:
                     continue
                 fn = lambda: K.modconv3x3_tcr_fwd(xpm, prep.w_hilo, s, dm, label, noise, nw, bias, bool(up), True)
+            elif mode == "tch":                     # H-form kernel: up-sampling layers only
+                if not up or prep.v_hilo is None:
+                    continue
+                fn = lambda: K.modconv3x3_up_tch_fwd(xpm, prep.v_hilo, prep.fx, s, dm, label, noise, nw, bias, True)
             else:
                 fn = lambda: K.modconv3x3_fwd(xpm, prep.wt, s, dm, label, noise, nw, bias, bool(up), True)
             ms = timeit(fn, iters=1, warmup=0, flush=flush) if args.once else timeit(fn, iters=3, warmup=1, flush=flush)
             total[mode] += ms
             row(f"modconv[{mode}] {name} {cin}->{cout} in{r} up{up} ncls{ncls}", ms, flops, "TFLOP/s")
-            if args.prof and mode == "tcr":
+            if args.prof and mode in ("tcr", "tch"):
                 from e4s_b200._lib import load as lib
                 ctr = torch.zeros(20, dtype=torch.int64, device=DEV)
-                lib().e4s_tcr_set_profile(ctr.data_ptr())
+                setp = lib().e4s_tcr_set_profile if mode == "tcr" else lib().e4s_tch_set_profile
+                setp(ctr.data_ptr())
                 fn()
                 torch.cuda.synchronize()
-                lib().e4s_tcr_set_profile(None)
+                setp(None)
                 c = ctr.cpu().view(5, 4).tolist()
                 names = ["weights(TMA)  wait: B_EMPTY", "mma           wait: ACC_EMPTY, A_FULL, B_FULL", "transform     wait: XS_FULL, A_EMPTY",
                          "epilogue      wait: ACC_FULL, tmem ld+zero, wait::st", "x-tiles(TMA)  wait: XS_EMPTY"]
+                if mode == "tch":
+                    names = ["weights(TMA)  wait: B_EMPTY", "mma           wait: ACC_EMPTY, A_FULL, B_FULL", "transform     wait: A_EMPTY",
+                             "epilogue      wait: ACC_FULL", "-"]
                 for rname, cc in zip(names, c):
                     tot = max(cc[0], 1)
                     print(f"    prof {rname:48s} total {cc[0]:>10d} cyc  waits " + " ".join(f"{100.0 * v / tot:5.1f}%" for v in cc[1:]), flush=True)
