@@ -35,11 +35,29 @@ import torch
 
 METRIC = "{size}x{size} faces/sec (mask-guided StyleGAN2 synthesis, {ncls} regions, K=13)"
 ALGO_GFLOP_PER_FACE = {1024: 148.1, 512: 118.8, 256: 89.5}   # 3x3 modulated convs, SURVEY.md section 8d
-# dram__bytes_read.sum + dram__bytes_write.sum per modulated-conv launch, mean over the 17 launches of one step of the default
-# workload (1024x1024, 16 faces, 12-region face masks), from the ncu --set full capture profiles/r1_ncu_tcr_17_layers.md
-# (15.67 GB per step against 14.90 GB algorithmic: input + output once in fp32, weights once)
-NCU_CONV_DRAM_BYTES_PER_LAUNCH = 921.9e6
-NCU_CONV_TENSOR_PIPE_PCT = 48.3                               # time-weighted sm__pipe_tensor_cycles_active, same capture
+# Numbers only a profiler can give (dram__bytes per conv launch, tensor-pipe activity) come from a COMMITTED ncu --set full
+# capture of the 17 conv launches of one step of the default workload: profiles/ncu_conv_static.json, written by
+# tools/ncu_summary.py together with the SHA-256 of the kernel sources it was taken from.  bench.py reports them as
+# "static" and flags them "stale" when the sources have changed since (they are never silently reused).
+NCU_STATIC = os.path.join(ROOT, "profiles", "ncu_conv_static.json")
+KERNEL_SOURCES = ("e4s_b200/csrc/modconv_tcr.cu", "e4s_b200/csrc/modconv_tch.cu", "e4s_b200/csrc/tc_ptx.cuh")
+
+
+def kernel_source_hash() -> str:
+    import hashlib
+    h = hashlib.sha256()
+    for rel in KERNEL_SOURCES:
+        with open(os.path.join(ROOT, rel), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
+
+
+def ncu_static():
+    if not os.path.exists(NCU_STATIC):
+        return None
+    d = json.load(open(NCU_STATIC))
+    d["stale"] = d.get("kernel_source_sha16") != kernel_source_hash()
+    return d
 
 
 def parse_args():
@@ -53,12 +71,15 @@ def parse_args():
     ap.add_argument("--ncls", type=int, default=12)
     ap.add_argument("--mask", default="faces", choices=["faces", "iid"], help="region-mask distribution")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the reference's own GPU formulation (cuDNN grouped convolutions)")
+    ap.add_argument("--no-loss-nets", action="store_true", help="inversion: skip the full-loss (ID + l2 + LPIPS + parsing) measurement")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--gather", action="store_true",
                     help="N>1: also all-gather every rank's images inside the timed step (the path itself has no exchange step)")
-    ap.add_argument("--faceswap-pairs", type=int, default=8,
+    ap.add_argument("--faceswap-pairs", type=int, default=None,
                     help="also time steps 3-5 of scripts/face_swap.py (encoder, shape/texture swap, generator, blending masks) on "
-                         "this many (driven, target) pairs per GPU (BASELINE configs[3]: 64 pairs over 8 GPUs); 0 disables")
+                         "this many (driven, target) pairs per GPU; default: BASELINE configs[3]'s 64 pairs split over the ranks "
+                         "(strong scaling: 8 per GPU at 8 GPUs, capped at 16 per GPU); 0 disables")
     ap.add_argument("--gpen-batch", type=int, default=16,
                     help="also time GPEN-BFR-512's FullGenerator (stage 2 of scripts/face_swap.py:208; e4s_b200.gpen) on this many "
                          "512x512 faces per GPU; 0 disables")
@@ -199,7 +220,7 @@ def make_clock_sampler(index: int):
 
 
 # --------------------------------------------------------------------------------------- CPU baseline
-def cpu_reference_face(size: int, ncls: int, state=None, seed: int = 1):
+def cpu_reference_face(size: int, ncls: int, state=None, seed: int = 1, want_inputs: bool = False):
     """One full synthesis forward of ONE face through the reference-structured CPU oracle (all host threads)."""
     from oracle import e4s_oracle as O
     if state is None:
@@ -208,19 +229,59 @@ def cpu_reference_face(size: int, ncls: int, state=None, seed: int = 1):
     t0 = time.perf_counter()
     with torch.no_grad():
         img, _ = O.generator_forward(state, codes, mask, noise, size, 13)
-    return time.perf_counter() - t0, state, img
+    dt = time.perf_counter() - t0
+    return (dt, state, img, (codes, mask, noise)) if want_inputs else (dt, state, img)
 
 
-def pick_cpu_threads(ncls: int) -> int:
-    """torch's default (one thread per logical core) oversubscribes the small convolutions of this path badly on
-    many-core hosts; give the CPU arm its best setting: try a few thread counts on a 64x64 forward, keep the fastest."""
+def gpu_baseline_leg(net, size: int, ncls: int, batch: int, dev):
+    """The reference's own GPU formulation on this GPU (oracle/gpu_baseline.py: per-region loop, per-sample weights, cuDNN
+    grouped convolution with groups = batch, model.py:287-318 / 395-398) - the stronger baseline of BASELINE.md section 4.
+    TF32 off (fp32 parity setting) and on (torch's default for cuDNN convolutions = what the reference runs with)."""
+    from oracle import e4s_oracle as O, gpu_baseline as GB
+    gst = {k[2:]: v.detach() for k, v in net.state_dict().items() if k.startswith("G.")}
+    out = {"what": "reference-structured forward (12 grouped cuDNN convolutions + mask-sum per masked layer) on the same GPU, "
+                   "weights and inputs resident, torch " + torch.__version__, "runs": []}
+    for b in sorted({1, batch}):
+        codes, mask, _, noise = O.synthetic_inputs(1, ncls, size, 512, seed=21)
+        codes, mask = codes.to(dev).expand(b, -1, -1, -1).contiguous(), mask.to(dev).expand(b, -1, -1, -1).contiguous()
+        noise = [n.to(dev) for n in noise]
+        for tf32 in (False, True):
+            try:
+                with torch.no_grad(), torch.backends.cudnn.flags(enabled=True, benchmark=True, allow_tf32=tf32):
+                    GB.generator_forward(gst, codes, mask, noise, size, 13)            # warm-up (cuDNN algorithm search)
+                    torch.cuda.synchronize()
+                    reps = 3 if b == 1 else 2
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    for _ in range(reps):
+                        GB.generator_forward(gst, codes, mask, noise, size, 13)
+                    e1.record()
+                    torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / reps
+                out["runs"].append({"batch": b, "tf32": tf32, "ms_per_step": ms, "faces_per_sec": b / (ms * 1e-3)})
+            except Exception as exc:                                   # e.g. out of memory at the full batch: reported
+                out["runs"].append({"batch": b, "tf32": tf32, "error": repr(exc)[:200]})
+                torch.cuda.empty_cache()
+        del codes, mask, noise
+        torch.cuda.empty_cache()
+    ok = [r for r in out["runs"] if "faces_per_sec" in r]
+    if ok:
+        out["best_fp32_faces_per_sec"] = max((r["faces_per_sec"] for r in ok if not r["tf32"]), default=None)
+        out["best_tf32_faces_per_sec"] = max((r["faces_per_sec"] for r in ok if r["tf32"]), default=None)
+    return out
+
+
+def pick_cpu_threads(ncls: int, probe: int = 256) -> int:
+    """torch's default (one thread per logical core) oversubscribes this path's convolutions on many-core hosts; give the CPU
+    arm its best setting: try a few thread counts on a 256x256 forward (convolutions of the size class that dominates the
+    timed 1024x1024 face: a 64x64 probe, as in round 1, favoured too few threads) and keep the fastest."""
     ncpu = os.cpu_count() or 1
-    cands = sorted({c for c in (8, 16, 32, 64, ncpu) if c <= ncpu})
+    cands = sorted({c for c in (8, 16, 32, 64, 96, ncpu) if c <= ncpu})
     best, best_t, state = cands[-1], float("inf"), None
     for c in cands:
         torch.set_num_threads(c)
-        _, state, _ = cpu_reference_face(64, ncls, state)
-        dt, state, _ = cpu_reference_face(64, ncls, state, seed=3)
+        _, state, _ = cpu_reference_face(probe, ncls, state)
+        dt, state, _ = cpu_reference_face(probe, ncls, state, seed=3)
         if dt < best_t:
             best, best_t = c, dt
     torch.set_num_threads(best)
@@ -248,7 +309,10 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC.format(size=args.size, ncls=args.ncls), "value": val, "unit": "faces/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": max(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.size}x{args.size} synthesis, CPU reference path, 1 face per step", "ncls": args.ncls},
+            "config": {"workload": f"{args.size}x{args.size} synthesis, CPU reference path, 1 face per step", "ncls": args.ncls,
+                       "faces_per_step": 1,
+                       "note": "the CPU arm times ONE face per step (a 16-face step would take minutes); the unit is faces/s, so the "
+                               "ratio to the GPU arm's 16-face steps stands"},
             "cpu_baseline": {"value": val, "unit": "faces/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "faces/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -273,6 +337,8 @@ def run_ours(args):
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
 
     B, size, ncls = args.batch, args.size, args.ncls
+    if args.faceswap_pairs is None:
+        args.faceswap_pairs = min(16, max(1, 64 // world))
     net = build_net(size, ncls, dev)
     g = torch.Generator().manual_seed(100 + rank)
     codes_host = torch.randn(B, ncls, 18, 512, generator=g).pin_memory()
@@ -342,6 +408,48 @@ def run_ours(args):
                "d2h_bytes_per_step": int(images_host.numel() * 4),
                "api": "e4s_b200.pipeline.SynthesisPipeline.submit (3 streams, depth 2)"}
 
+    # ---- the path's only collective: all-gather of the final images, alone and overlapped with the next step
+    gather = None
+    if world > 1:
+        with torch.no_grad():
+            img = step_device() if not args.gather else net.gen_img(None, codes_dev, onehot_dev)[0]
+            for _ in range(2):
+                gather_images(img)
+            barrier()
+            reps = 5
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            for _ in range(reps):
+                gathered = gather_images(img)
+            g1.record()
+            barrier()
+            alone = g0.elapsed_time(g1) / reps
+            # overlapped: the gather of step i runs on a side stream while step i + 1 computes
+            side = torch.cuda.Stream()
+            o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            o0.record()
+            prev = img
+            for _ in range(reps):
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    gathered = gather_images(prev)
+                prev, _, _ = net.gen_img(None, codes_dev, onehot_dev)
+                torch.cuda.current_stream().wait_stream(side)
+            o1.record()
+            barrier()
+            overlapped = o0.elapsed_time(o1) / reps
+        t = torch.tensor([alone, overlapped], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        alone, overlapped = float(t[0]), float(t[1])
+        recv = float(img.numel() * 4 * (world - 1))
+        gather = {"collective": "ncclAllGather (all_gather_into_tensor) of the final images", "bytes_per_rank_in": img.numel() * 4,
+                  "bytes_per_rank_received": recv, "ms_alone": alone, "recv_GBps_per_rank": recv / (alone * 1e-3) / 1e9,
+                  "ms_step_plus_overlapped_gather": overlapped, "ms_step": ms / args.steps,
+                  "overlap_cost_ms": overlapped - ms / args.steps,
+                  "nvlink_note": "NVLink 5 gives 900 GB/s per direction and GPU; a 16-face step's images are 201 MB per rank"}
+        del gathered, img
+
     # ---- roofline of the dominant kernel family: the modulated 3x3 convolutions
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
@@ -351,6 +459,7 @@ def run_ours(args):
     else:
         peak_tf, peak_src, hbm_gbs = 1590.0, "fallback (B200_PROFILING.md)", 6650.0
     roofline, kernels = None, {}
+    static = ncu_static()
     default_workload = (size, B, ncls, args.mask) == (1024, 16, 12, "faces")
     for name, (n, kms, work) in summary.items():
         kernels[name] = {"launches": n, "ms": round(kms, 3), "share": round(kms / ms, 4)}
@@ -363,9 +472,12 @@ def run_ours(args):
         ach = flops / (kms * 1e-3) / 1e12
         roofline = {"kernel": f"modulated 3x3 convolutions (all 17 StyledConv layers; dominant entry point {top})",
                     "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-                    "traffic": NCU_CONV_DRAM_BYTES_PER_LAUNCH if default_workload else None,
-                    "traffic_source": "ncu --set full, mean of the 17 launches of one step (profiles/r1_ncu_tcr_17_layers.md)" if default_workload else None,
-                    "tensor_pipe_active_pct_ncu": NCU_CONV_TENSOR_PIPE_PCT if default_workload else None,
+                    "traffic": (static or {}).get("dram_bytes_per_launch") if default_workload else None,
+                    "tensor_pipe_active_pct_ncu": (static or {}).get("tensor_pipe_active_pct") if default_workload else None,
+                    "static": None if (static is None or not default_workload) else
+                              {"what": "traffic and tensor_pipe_active_pct_ncu are NOT measured in this run: they come from the committed ncu "
+                                       "--set full capture of the 17 conv launches of one step", "source": static.get("source"),
+                               "kernel_source_sha16": static.get("kernel_source_sha16"), "stale": static["stale"]},
                     "peak_source": peak_src, "algorithmic_gflop_per_face": flops / 1e9 / (B * args.steps), "launches": n,
                     "avg_launch_ms": kms / n, "share_of_step": kms / ms,
                     "note": "achieved = ALGORITHMIC fp32 FLOPs / event time; the kernel issues 3 bf16 MMAs per algorithmic MAC "
@@ -451,7 +563,54 @@ def run_ours(args):
                 del target_b, svb, onehot_b
             except Exception as exc:                              # reported, never hidden
                 batched = {"error": repr(exc)[:300]}
-        inversion = {"steps_timed": args.inversion_steps, "ms_per_step": ims, "batched": batched, "launches_per_step": inv_launches / args.inversion_steps,
+        full_loss = None
+        if not args.no_loss_nets:
+            # the reference's default loss (scripts/optimization.py:88-122: 0.1 ID + 1.0 l2 + 0.8 LPIPS x3 scales + 0.1 parsing) on
+            # seeded stand-in loss networks (their checkpoints cannot be downloaded), target features cached, whole step graphed
+            try:
+                from e4s_b200.criteria import InversionLoss
+                from e4s_b200.synthetic import load_synthetic_losses
+                crit = InversionLoss()
+                load_synthetic_losses(crit, 11)
+                crit = crit.to(dev)
+                invert(net, target, onehot1, style_vectors=sv, steps=3, criterion=crit)           # warm-up (cuDNN algorithm choice)
+                barrier()
+                l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                l0.record()
+                _, _, lhist = invert(net, target, onehot1, style_vectors=sv, steps=args.inversion_steps, criterion=crit)
+                l1.record()
+                barrier()
+                lms = l0.elapsed_time(l1) / args.inversion_steps
+                invert(net, target, onehot1, style_vectors=sv, steps=6, criterion=crit, cuda_graph=True)      # capture warm-up
+                barrier()
+                q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                q0.record()
+                qstats = {}
+                _, _, qhist = invert(net, target, onehot1, style_vectors=sv, steps=100, criterion=crit, cuda_graph=True, stats=qstats)
+                q1.record()
+                barrier()
+                qtot = q0.elapsed_time(q1)
+                # what the reference's loop pays in addition: the target image through all three networks every step
+                with torch.no_grad():
+                    for _ in range(2):
+                        crit.set_target(target)
+                    barrier()
+                    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    r0.record()
+                    for _ in range(5):
+                        crit.set_target(target)
+                    r1.record()
+                    barrier()
+                full_loss = {"lambdas": {"id": 0.1, "l2": 1.0, "lpips": 0.8, "face_parsing": 0.1}, "ms_per_step_eager": lms,
+                             "ms_per_replayed_step": qstats.get("replay_ms_per_step"), "ms_total_100_steps": qtot,
+                             "faces_per_sec_100_steps": world / (qtot * 1e-3), "loss_first": float(qhist[0]), "loss_last": float(qhist[-1]),
+                             "target_feature_pass_ms": r0.elapsed_time(r1) / 5,
+                             "note": "loss networks = library convolutions (cuDNN, fp32); target-image features cached once per face - the "
+                                     "reference recomputes them every step (target_feature_pass_ms each); seeded stand-in weights"}
+                del crit
+            except Exception as exc:                                  # reported, never hidden
+                full_loss = {"error": repr(exc)[:300]}
+        inversion = {"steps_timed": args.inversion_steps, "full_loss": full_loss, "ms_per_step": ims, "batched": batched, "launches_per_step": inv_launches / args.inversion_steps,
                      "cuda_graph": graphed, "kernels": inv_kernels,
                      "faces_per_sec_100_steps": world / (ims * 100 * 1e-3), "loss_first": float(hist[0]), "loss_last": float(hist[-1]),
                      "config": f"one {size}x{size} face per GPU, {ncls} regions, Adam lr 1e-2, l2 loss, fresh noise per step"}
@@ -527,16 +686,46 @@ def run_ours(args):
         except Exception as exc:                                      # reported, never hidden
             gpen = {"error": repr(exc)[:300]}
 
-    cpu = None
+    gpu_base = None
+    if rank == 0 and world == 1 and not args.no_gpu_baseline:
+        try:
+            gpu_base = gpu_baseline_leg(net, size, ncls, B, dev)
+            if gpu_base.get("best_fp32_faces_per_sec"):
+                gpu_base["speedup_vs_fp32"] = value / gpu_base["best_fp32_faces_per_sec"]
+            if gpu_base.get("best_tf32_faces_per_sec"):
+                gpu_base["speedup_vs_tf32"] = value / gpu_base["best_tf32_faces_per_sec"]
+        except Exception as exc:                                      # reported, never hidden
+            gpu_base = {"error": repr(exc)[:300]}
+
+    cpu, parity = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         pick_cpu_threads(ncls)                                        # also warms the thread pool / allocator
-        dt, _, _ = cpu_reference_face(size, ncls)
+        # the timed CPU face runs with THIS net's generator weights, so that its image is also the parity reference
+        gst = {k[2:]: v.detach().cpu() for k, v in net.state_dict().items() if k.startswith("G.")}
+        dt, _, cpu_img, (pc, pm, pn) = cpu_reference_face(size, ncls, gst, want_inputs=True)
+        with torch.no_grad():
+            gpu_img, _, _ = net.G([pc.to(dev)], None, pm.to(dev), input_is_latent=True, noise=[n.to(dev) for n in pn])
+            # the same face as sample 5 of a full batch: batching must not change a face
+            pcb = torch.randn(B, *pc.shape[1:], generator=torch.Generator().manual_seed(77))
+            pmb = labelMap2OneHot(labels_host.to(dev), ncls).clone()
+            slot = min(5, B - 1)
+            pcb[slot] = pc[0]
+            pmb[slot] = pm[0].to(dev)
+            batch_img, _, _ = net.G([pcb.to(dev)], None, pmb, input_is_latent=True, noise=[n.to(dev) for n in pn])
+        d = (gpu_img.cpu().double() - cpu_img.double())
+        db = (batch_img[slot:slot + 1].cpu().double() - cpu_img.double())
+        ref_max, ref_rms = float(cpu_img.abs().max()), float(cpu_img.double().pow(2).mean().sqrt())
+        parity = {"what": f"one {size}x{size} face, {ncls} regions, K=13, fixed noise: e4s_b200 (default kernels) vs the CPU oracle",
+                  "max_rel": float(d.abs().max()) / ref_max, "rel_rms": float(d.pow(2).mean().sqrt()) / ref_rms,
+                  "in_batch_max_rel": float(db.abs().max()) / ref_max, "in_batch_rel_rms": float(db.pow(2).mean().sqrt()) / ref_rms,
+                  "tolerance": 1e-3}
+        del gpu_img, batch_img
         dt256 = min(cpu_reference_face(256, ncls)[0] for _ in range(2)) if size != 256 else dt      # BASELINE configs[0]'s size
         cpu = {"value": 1.0 / dt, "unit": "faces/s", "cores": torch.get_num_threads(), "kind": "port",
                "value_256x256": 1.0 / dt256,
                "host_logical_cpus": os.cpu_count(),
                "sample": f"one full {size}x{size} face (B=1, {ncls} regions, K=13) through the reference-structured CPU "
-                         f"oracle (fp32, torch CPU; thread count = fastest of 8/16/32/64/all on a 64x64 probe)"}
+                         f"oracle (fp32, torch CPU; thread count = fastest of 8/16/32/64/96/all on a 256x256 probe)"}
 
     if rank == 0:
         line = {"metric": METRIC.format(size=args.size, ncls=args.ncls), "value": value, "unit": "faces/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -548,6 +737,7 @@ def run_ours(args):
                            "parallelism": (f"dp{world}: faces sharded across ranks, weights replicated, no data-path collective"
                                            + (" + NCCL all-gather of the final images" if args.gather else "")) if world > 1 else "single GPU"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+                f"parity_{size}": parity, "gpu_baseline": gpu_base, "gather": gather,
                 "kernels": kernels, "hbm_peak_gbs": hbm_gbs, "inversion": inversion, "faceswap": faceswap, "gpen": gpen}
         emit(json.dumps(line))
     if world > 1:

@@ -99,6 +99,12 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// one lane by elect.sync: single-lane to the compiler, no ELECT / R2UR.BROADCAST waterfall around every MMA (tc_ptx.cuh)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -252,7 +258,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) modconv3x3_dgrad_tc_kernel(con
         for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
             const Item item = decode_item(p, it);
             const int npass = __popc(halo_class_mask<NPH>(p, item, lane));
-            if (lane == 0) {
+            if (elect_one()) {
                 const int q0 = item.hq * (NPH / p.hsplit), q1 = q0 + NPH / p.hsplit;
                 for (int pass = 0; pass < npass; ++pass)
                     for (int q = q0; q < q1; ++q)
@@ -273,7 +279,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) modconv3x3_dgrad_tc_kernel(con
         // ===================================================================== MMA issuers: x_hi w_hi | x_lo w_hi | x_hi w_lo
         const int role = warp - 1;
         const bool lo_w = role == 2;
-        const bool leader = lane == 0;
         int sa = 0, slot = 0, acc = 0;
         uint32_t pa = 0, pb = 0, pacc0 = 0, pacc1 = 0;
         const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
@@ -298,7 +303,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) modconv3x3_dgrad_tc_kernel(con
                         mbar_wait(bars0 + 8 * (B_FULL + sl), pb);
                         tc_fence_after();
                         const uint32_t bb = b0 + sl * B_SLOT;
-                        if (leader) {
+                        if (elect_one()) {
 #pragma unroll
                             for (int k = 0; k < KSTEPS; ++k)
                                 umma_bf16(d_tmem, smem_desc<KC>(ap + row_off + k * 32), smem_desc<KC>(bb + k * 32), IDESC, 1u);
@@ -307,10 +312,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) modconv3x3_dgrad_tc_kernel(con
                         slot += 2;
                         if (slot >= p.nslot_b) slot = 0, pb ^= 1;
                     }
-                    if (leader) umma_commit(bars0 + 8 * (A_EMPTY + sa));
+                    if (elect_one()) umma_commit(bars0 + 8 * (A_EMPTY + sa));
                     if (++sa == NSTAGE_A) sa = 0, pa ^= 1;
                 }
-                if (leader) umma_commit(bars0 + 8 * (ACC_FULL + acc));
+                if (elect_one()) umma_commit(bars0 + 8 * (ACC_FULL + acc));
                 if (acc) pacc1 ^= 1; else pacc0 ^= 1;
                 if (NACC == 2) acc ^= 1;
             }

@@ -22,7 +22,7 @@
 // weight slots multiplied into both); the epilogue combines within one region's buffer and each output pixel takes the
 // result of its own region.  One region: one pass, double-buffered across tiles.  k regions: ceil(k / 2) passes.
 //
-// Roles (persistent CTAs, 16 warps), barriers, split-bf16 x3 accumulation, zeroing of read accumulators by the epilogue:
+// Roles (persistent CTAs, 20 warps: 1 TMA, 3 MMA issue, 8 transform, 8 epilogue), barriers, split-bf16 x3 accumulation, zeroing of read accumulators by the epilogue:
 // as in modconv_tcr.cu.
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -39,9 +39,9 @@ constexpr int TH = 8, TW = 14;
 constexpr int A_ROWS = 168;                     // 160 halo pixels + the leading row of the 3x3 kernel's layout
 constexpr int NSTAGE_A = 2;
 constexpr int NUM_MMA_WARPS = 3;
-constexpr int W_XFORM0 = 1 + NUM_MMA_WARPS, W_EPI0 = W_XFORM0 + 8, W_END = W_EPI0 + 4;
-constexpr int NUM_THREADS = 32 * W_END;         // 512
-constexpr int NUM_XFORM = 256, NUM_EPI = 128;
+constexpr int W_XFORM0 = 1 + NUM_MMA_WARPS, W_EPI0 = W_XFORM0 + 8, W_END = W_EPI0 + 8;
+constexpr int NUM_THREADS = 32 * W_END;         // 640: registers are capped at 96 per thread
+constexpr int NUM_XFORM = 256, NUM_EPI = 256;
 constexpr int SMEM_BUDGET = 227 * 1024 - 2048;
 constexpr int NG = 6;                           // (py, kx) accumulator column groups
 constexpr int ACC_COLS = 256, NACC = 2, TMEM_COLS = 512;
@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) modconv3x3_up_tch_kernel(const
     constexpr int CPR = KC / 8;                       // 16-byte chunks per operand row
     constexpr int PPS = NUM_XFORM / CPR;              // halo pixels covered per sweep of the transform threads
     constexpr int NSW = (160 + PPS - 1) / PPS;
-    static_assert(N <= ACC_COLS && N % 16 == 0 && NTC % 8 == 0, "UMMA N");
+    static_assert(N <= ACC_COLS && N % 16 == 0 && NTC % 32 == 0, "UMMA N; the epilogue zeroes 32-column blocks per row parity");
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) modconv3x3_up_tch_kernel(const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    if (warp >= W_EPI0) {                               // every MMA accumulates: both accumulator buffers start at zero
+    if (warp >= W_EPI0 && warp < W_EPI0 + 4) {          // every MMA accumulates: both accumulator buffers start at zero
         const uint32_t lanes = tmem_base + (((uint32_t)(warp & 3) * 32u) << 16);
 #pragma unroll 1
         for (int c = 0; c < TMEM_COLS; c += 32) tmem_zero32(lanes + (uint32_t)c);
@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) modconv3x3_up_tch_kernel(const
         for (int it = blockIdx.x; it < p.items; it += gridDim.x, wk.advance(p)) {
             const Item item = wk.cur;
             const int npass = (__popc(tile_classes(p, item, lane)) + 1) >> 1;
-            if (lane == 0) {
+            if (elect_one()) {
                 for (int ps = 0; ps < npass; ++ps)
                     for (int kc = 0; kc < nchunks; ++kc)
                         for (int tap = 0; tap < 3; ++tap) {
@@ -213,8 +213,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) modconv3x3_up_tch_kernel(const
         const int role = warp - 1;
         const bool lo_w = role == 2;
         int sa = 0, slot = 0, acc = 0;
-        uint32_t pa = 0, pb = 0, pacc[2] = {0, 0};
-        const bool leader = lane == 0;
+        uint32_t pa = 0, pb = 0, pacc = 0;                // bit b = phase of accumulator buffer b
         const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
         const uint32_t bars0 = smem_u32(bars);
         const uint32_t a0 = smem_u32(a_buf) + (role == 1 ? A_PLANE : 0), b0 = smem_u32(b_buf);
@@ -229,8 +228,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) modconv3x3_up_tch_kernel(const
                 int ca, cb;
                 next_pass(rem, ca, cb);
                 const bool two = cb >= 0;
-                TCH_WAIT(bars0 + 8 * (ACC_EMPTY + acc), pacc[acc] ^ 1, 1);
-                if (two) TCH_WAIT(bars0 + 8 * (ACC_EMPTY + (acc ^ 1)), pacc[acc ^ 1] ^ 1, 1);
+                TCH_WAIT(bars0 + 8 * (ACC_EMPTY + acc), ((pacc >> acc) & 1u) ^ 1u, 1);
+                if (two) TCH_WAIT(bars0 + 8 * (ACC_EMPTY + (acc ^ 1)), ((pacc >> (acc ^ 1)) & 1u) ^ 1u, 1);
                 tc_fence_after();
                 const uint32_t d_a = tmem_u + (uint32_t)(acc * ACC_COLS), d_b = tmem_u + (uint32_t)((acc ^ 1) * ACC_COLS);
 #pragma unroll 1
@@ -248,7 +247,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) modconv3x3_up_tch_kernel(const
                         tc_fence_after();
                         const uint32_t bp = lo_of(b0 + (slot + (lo_w ? 1 : 0)) * B_SLOT);
                         const uint32_t roff = (uint32_t)((1 + 16 * tap) * ROWB) >> 4;       // halo pixel hp is operand row hp + 1
-                        if (leader) {
+                        if (elect_one()) {
 #pragma unroll
                             for (int k = 0; k < KSTEPS; ++k) umma_bf16(d_a, desc(apA + roff + 2 * k), desc(bp + 2 * k), IDESC, 1u);
                             if (two) {
@@ -260,18 +259,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) modconv3x3_up_tch_kernel(const
                         slot += 2;
                         if (slot >= p.nslot_b) slot = 0, pb ^= 1;
                     }
-                    if (leader) {
+                    if (elect_one()) {
                         umma_commit(bars0 + 8 * (A_EMPTY + sa));
                         if (two) umma_commit(bars0 + 8 * (A_EMPTY + sb));
                     }
                     if (++sa == NSTAGE_A) sa = 0, pa ^= 1;
                     if (two && ++sa == NSTAGE_A) sa = 0, pa ^= 1;
                 }
-                if (leader) umma_commit(bars0 + 8 * (ACC_FULL + acc));
-                pacc[acc] ^= 1;
+                if (elect_one()) umma_commit(bars0 + 8 * (ACC_FULL + acc));
+                pacc ^= 1u << acc;
                 if (two) {                                   // both buffers used: hand both over, buffer order unchanged
-                    if (leader) umma_commit(bars0 + 8 * (ACC_FULL + (acc ^ 1)));
-                    pacc[acc ^ 1] ^= 1;
+                    if (elect_one()) umma_commit(bars0 + 8 * (ACC_FULL + (acc ^ 1)));
+                    pacc ^= 1u << (acc ^ 1);
                 } else {
                     acc ^= 1;
                 }
@@ -347,31 +346,53 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) modconv3x3_up_tch_kernel(const
         }
     } else {
         // ===================================================================== epilogue: horizontal half of the blur, region selection,
-        // demodulation, noise, bias, activation; one thread = one patch pixel (m, n') = two output rows x two output columns
+        // demodulation, noise, bias, activation.  One thread = one patch pixel (m, n') and ONE output row parity py (two output
+        // columns): warps W_EPI0..+3 take py = 0, the next four py = 1 - eight warps, two per TMEM lane quarter (the first
+        // version's four warps, one per scheduler with nothing to switch to, ran this role at 0.27 instructions per cycle and
+        // bound the kernel: profiles/r2_stall_attribution_tch_v1.log).  Arithmetic on packed fp32 pairs (FFMA2 / FMUL2 / FADD2).
         const uint32_t quarter = (uint32_t)(warp & 3);
+        const int py = (warp - W_EPI0) >> 2;
         const int m_row = quarter * 32 + lane;
         const int ty = m_row >> 4, tx = m_row & 15;
         int acc = 0;
-        uint32_t pacc[2] = {0, 0};
+        uint32_t pacc = 0;                                // bit b = phase of accumulator buffer b
         const float nw = (p.noise && p.noise_w) ? __ldg(p.noise_w) : 0.f;
-        const float f0 = p.f0, f1 = p.f1, f2 = p.f2, f3 = p.f3;
+        const uint64_t F0 = pk2(p.f0, p.f0), F1 = pk2(p.f1, p.f1), F2 = pk2(p.f2, p.f2), F3 = pk2(p.f3, p.f3);
+        const float k2 = 1.41421356237309515f;
+        const uint64_t S2 = pk2(k2, k2), S02 = pk2(0.2f * k2, 0.2f * k2);
         const int ho = 2 * p.h, wo = 2 * p.w;
         const uint32_t lanes = tmem_base + ((quarter * 32u) << 16);
-        auto fetch = [&](bool valid, const Item& i2, int (&c)[4], float (&z)[4]) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) c[q] = 0, z[q] = 0.f;
+        auto fetch = [&](bool valid, const Item& i2, int (&c)[2], float (&z)[2]) {
+            c[0] = c[1] = 0, z[0] = z[1] = 0.f;
             if (!valid) return;
             const int iy = i2.ty * TH + ty, ix = i2.tx * TW + tx - 1;
             if (!(tx >= 1 && tx <= TW && iy < p.h && ix < p.w)) return;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int oy = 2 * iy + (q >> 1), ox = 2 * ix + (q & 1);
-                if (p.label) c[q] = min((int)p.label[((int64_t)i2.b * ho + oy) * wo + ox], p.ncls - 1);
-                if (p.noise) z[q] = __ldg(p.noise + ((int64_t)(p.noise_b == 1 ? 0 : i2.b) * ho + oy) * wo + ox);
+            const int64_t o = ((int64_t)i2.b * ho + 2 * iy + py) * wo + 2 * ix;
+            if (p.label) c[0] = min((int)p.label[o], p.ncls - 1), c[1] = min((int)p.label[o + 1], p.ncls - 1);
+            if (p.noise) {
+                const float* nzp = p.noise + ((int64_t)(p.noise_b == 1 ? 0 : i2.b) * ho + 2 * iy + py) * wo + 2 * ix;
+                z[0] = __ldg(nzp), z[1] = __ldg(nzp + 1);
             }
         };
-        int cls_next[4];
-        float nz_next[4];
+        // six-term horizontal combination of 8 channels (4 packed pairs) from one region's accumulators
+        auto combine = [&](uint32_t col, uint64_t (&o0)[4], uint64_t (&o1)[4]) {
+            uint32_t t0[8], t1[8], t2[8];
+            tmem_ld8x3(lanes + col, lanes + col + NTC, lanes + col + 2 * NTC, t0, t1, t2);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const uint64_t a0 = pk2u(t0[2 * e], t0[2 * e + 1]), a1 = pk2u(t1[2 * e], t1[2 * e + 1]), a2 = pk2u(t2[2 * e], t2[2 * e + 1]);
+                const uint64_t l1 = pk2u(__shfl_up_sync(0xffffffffu, t1[2 * e], 1), __shfl_up_sync(0xffffffffu, t1[2 * e + 1], 1));
+                const uint64_t l2 = pk2u(__shfl_up_sync(0xffffffffu, t2[2 * e], 1), __shfl_up_sync(0xffffffffu, t2[2 * e + 1], 1));
+                const uint64_t r0 = pk2u(__shfl_down_sync(0xffffffffu, t0[2 * e], 1), __shfl_down_sync(0xffffffffu, t0[2 * e + 1], 1));
+                const uint64_t r1 = pk2u(__shfl_down_sync(0xffffffffu, t1[2 * e], 1), __shfl_down_sync(0xffffffffu, t1[2 * e + 1], 1));
+                // px = 0: f0 T1[n-1] + f1 T2[n-1] + f1 T0[n] + f2 T1[n] + f3 T2[n] + f3 T0[n+1]
+                o0[e] = fma2(F3, r0, fma2(F3, a2, fma2(F2, a1, fma2(F1, a0, fma2(F1, l2, mul2(F0, l1))))));
+                // px = 1: f0 T2[n-1] + f0 T0[n] + f1 T1[n] + f2 T2[n] + f2 T0[n+1] + f3 T1[n+1]
+                o1[e] = fma2(F3, r1, fma2(F2, r0, fma2(F2, a2, fma2(F1, a1, fma2(F0, a0, mul2(F0, l2))))));
+            }
+        };
+        int cls_next[2];
+        float nz_next[2];
         Walk wk;
         wk.init(p, blockIdx.x, gridDim.x);
         fetch(blockIdx.x < p.items, wk.cur, cls_next, nz_next);
@@ -381,91 +402,77 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) modconv3x3_up_tch_kernel(const
             const int iy = item.ty * TH + ty, ix = item.tx * TW + tx - 1;
             const bool mine = tx >= 1 && tx <= TW && iy < p.h && ix < p.w;
             const int n0 = item.nt * NTC;
-            int cls[4];
-            float nz[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) cls[q] = cls_next[q], nz[q] = nw * nz_next[q];
+            const int c0 = cls_next[0], c1 = cls_next[1];
+            const uint64_t Z0 = pk2(nw * nz_next[0], nw * nz_next[0]), Z1 = pk2(nw * nz_next[1], nw * nz_next[1]);
             uint32_t rem = tile_classes(p, item, lane);
             fetch(it + (int)gridDim.x < p.items, wk.cur, cls_next, nz_next);
+            const float* dm0 = p.demod ? p.demod + ((int64_t)item.b * p.ncls + c0) * p.cout + n0 : nullptr;
+            const float* dm1 = p.demod ? p.demod + ((int64_t)item.b * p.ncls + c1) * p.cout + n0 : nullptr;
+            float* dst0 = p.y + (((int64_t)item.b * ho + 2 * iy + py) * wo + 2 * ix) * p.cout + n0;
+            float* dst1 = dst0 + p.cout;
             while (rem) {
                 int ca, cb;
                 next_pass(rem, ca, cb);
                 const bool two = cb >= 0;
-                TCH_WAIT(smem_u32(&bars[ACC_FULL + acc]), pacc[acc], 1);
-                pacc[acc] ^= 1;
+                TCH_WAIT(smem_u32(&bars[ACC_FULL + acc]), (pacc >> acc) & 1u, 1);
+                pacc ^= 1u << acc;
                 if (two) {
-                    TCH_WAIT(smem_u32(&bars[ACC_FULL + (acc ^ 1)]), pacc[acc ^ 1], 1);
-                    pacc[acc ^ 1] ^= 1;
+                    TCH_WAIT(smem_u32(&bars[ACC_FULL + (acc ^ 1)]), (pacc >> (acc ^ 1)) & 1u, 1);
+                    pacc ^= 1u << (acc ^ 1);
                 }
                 tc_fence_after();
-                const uint32_t cbase = (uint32_t)(acc * ACC_COLS), cother = (uint32_t)((acc ^ 1) * ACC_COLS);
-#pragma unroll
-                for (int py = 0; py < 2; ++py) {
-                    const int c0 = cls[2 * py], c1 = cls[2 * py + 1];
-                    const bool w0 = mine && (c0 == ca || c0 == cb), w1 = mine && (c1 == ca || c1 == cb);
-                    const bool sel0 = two && c0 == cb, sel1 = two && c1 == cb;      // this output takes region B's combination
-                    const float* dm0 = p.demod ? p.demod + ((int64_t)item.b * p.ncls + c0) * p.cout + n0 : nullptr;
-                    const float* dm1 = p.demod ? p.demod + ((int64_t)item.b * p.ncls + c1) * p.cout + n0 : nullptr;
-                    float* dst0 = p.y + (((int64_t)item.b * ho + 2 * iy + py) * wo + 2 * ix) * p.cout + n0;
-                    float* dst1 = dst0 + p.cout;
-                    const float z0 = nz[2 * py], z1 = nz[2 * py + 1];
+                const uint32_t cbase = (uint32_t)(acc * ACC_COLS + 3 * py * NTC), cother = (uint32_t)((acc ^ 1) * ACC_COLS + 3 * py * NTC);
+                const bool w0 = mine && (c0 == ca || c0 == cb), w1 = mine && (c1 == ca || c1 == cb);
+                const bool sel0 = two && c0 == cb, sel1 = two && c1 == cb;      // this output takes region B's combination
 #pragma unroll 1
-                    for (int jb = 0; jb < NTC / 8; ++jb) {
-                        float o0[8], o1[8];
-                        {
-                            uint32_t t0[8], t1[8], t2[8];
-                            const uint32_t col = cbase + (uint32_t)(3 * py * NTC + 8 * jb);
-                            tmem_ld8x3(lanes + col, lanes + col + NTC, lanes + col + 2 * NTC, t0, t1, t2);
+                for (int jb = 0; jb < NTC / 8; ++jb) {
+                    const int co = 8 * jb;
+                    // epilogue operands first: their (L1-hit) latency overlaps the TMEM loads and shuffles below
+                    float4 bv[2], d0v[2], d1v[2];
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) {
-                                const float a0 = __uint_as_float(t0[e]), a1 = __uint_as_float(t1[e]), a2 = __uint_as_float(t2[e]);
-                                const float l1 = __shfl_up_sync(0xffffffffu, a1, 1), l2 = __shfl_up_sync(0xffffffffu, a2, 1);
-                                const float r0 = __shfl_down_sync(0xffffffffu, a0, 1), r1 = __shfl_down_sync(0xffffffffu, a1, 1);
-                                o0[e] = f0 * l1 + f1 * l2 + f1 * a0 + f2 * a1 + f3 * a2 + f3 * r0;
-                                o1[e] = f0 * l2 + f0 * a0 + f1 * a1 + f2 * a2 + f2 * r0 + f3 * r1;
-                            }
-                        }
-                        if (two) {
-                            uint32_t t0[8], t1[8], t2[8];
-                            const uint32_t col = cother + (uint32_t)(3 * py * NTC + 8 * jb);
-                            tmem_ld8x3(lanes + col, lanes + col + NTC, lanes + col + 2 * NTC, t0, t1, t2);
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) {
-                                const float a0 = __uint_as_float(t0[e]), a1 = __uint_as_float(t1[e]), a2 = __uint_as_float(t2[e]);
-                                const float l1 = __shfl_up_sync(0xffffffffu, a1, 1), l2 = __shfl_up_sync(0xffffffffu, a2, 1);
-                                const float r0 = __shfl_down_sync(0xffffffffu, a0, 1), r1 = __shfl_down_sync(0xffffffffu, a1, 1);
-                                const float b0 = f0 * l1 + f1 * l2 + f1 * a0 + f2 * a1 + f3 * a2 + f3 * r0;
-                                const float b1 = f0 * l2 + f0 * a0 + f1 * a1 + f2 * a2 + f2 * r0 + f3 * r1;
-                                if (sel0) o0[e] = b0;
-                                if (sel1) o1[e] = b1;
-                            }
-                        }
-                        const int co = 8 * jb;
-                        const float4 bv0 = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n0 + co)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                        const float4 bv1 = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n0 + co + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                        auto finish = [&](const float (&o)[8], const float* dm, float z, float* dst) {
-                            const float4 d0 = dm ? __ldg(reinterpret_cast<const float4*>(dm + co)) : make_float4(1.f, 1.f, 1.f, 1.f);
-                            const float4 d1 = dm ? __ldg(reinterpret_cast<const float4*>(dm + co + 4)) : make_float4(1.f, 1.f, 1.f, 1.f);
-                            float4 u, v;
-                            u.x = o[0] * d0.x + z + bv0.x, u.y = o[1] * d0.y + z + bv0.y, u.z = o[2] * d0.z + z + bv0.z, u.w = o[3] * d0.w + z + bv0.w;
-                            v.x = o[4] * d1.x + z + bv1.x, v.y = o[5] * d1.y + z + bv1.y, v.z = o[6] * d1.z + z + bv1.z, v.w = o[7] * d1.w + z + bv1.w;
-                            if (p.act) {
-                                const float k = 1.41421356237309515f;
-                                u.x = lrelu_scaled(u.x, 0.2f, k), u.y = lrelu_scaled(u.y, 0.2f, k), u.z = lrelu_scaled(u.z, 0.2f, k), u.w = lrelu_scaled(u.w, 0.2f, k);
-                                v.x = lrelu_scaled(v.x, 0.2f, k), v.y = lrelu_scaled(v.y, 0.2f, k), v.z = lrelu_scaled(v.z, 0.2f, k), v.w = lrelu_scaled(v.w, 0.2f, k);
-                            }
-                            st_global_v8(dst + co, u, v);
-                        };
-                        if (w0) finish(o0, dm0, z0, dst0);
-                        if (w1) finish(o1, dm1, z1, dst1);
+                    for (int h2 = 0; h2 < 2; ++h2) {
+                        bv[h2] = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n0 + co + 4 * h2)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        d0v[h2] = dm0 ? __ldg(reinterpret_cast<const float4*>(dm0 + co + 4 * h2)) : make_float4(1.f, 1.f, 1.f, 1.f);
+                        d1v[h2] = dm1 ? __ldg(reinterpret_cast<const float4*>(dm1 + co + 4 * h2)) : make_float4(1.f, 1.f, 1.f, 1.f);
                     }
-                }
-                // every MMA accumulates: hand the buffers back zeroed
+                    uint64_t o0[4], o1[4];
+                    combine(cbase + (uint32_t)co, o0, o1);
+                    if (two) {
+                        uint64_t q0[4], q1[4];
+                        combine(cother + (uint32_t)co, q0, q1);
 #pragma unroll
-                for (int c = 0; c < N; c += 32) tmem_zero32(lanes + cbase + (uint32_t)c);
+                        for (int e = 0; e < 4; ++e) {
+                            if (sel0) o0[e] = q0[e];
+                            if (sel1) o1[e] = q1[e];
+                        }
+                    }
+                    auto finish = [&](const uint64_t (&o)[4], const float4 (&d)[2], uint64_t Z, float* dst) {
+                        const uint64_t dp[4] = {pk2(d[0].x, d[0].y), pk2(d[0].z, d[0].w), pk2(d[1].x, d[1].y), pk2(d[1].z, d[1].w)};
+                        const uint64_t bp[4] = {pk2(bv[0].x, bv[0].y), pk2(bv[0].z, bv[0].w), pk2(bv[1].x, bv[1].y), pk2(bv[1].z, bv[1].w)};
+                        float r[8];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const uint64_t t = fma2(o[e], dp[e], add2(bp[e], Z));
+                            if (p.act) {                                  // sqrt(2) * lrelu_0.2(t) = max(sqrt(2) t, 0.2 sqrt(2) t)
+                                float a_lo, a_hi, b_lo, b_hi;
+                                upk2(mul2(t, S2), a_lo, a_hi);
+                                upk2(mul2(t, S02), b_lo, b_hi);
+                                r[2 * e] = fmaxf(a_lo, b_lo), r[2 * e + 1] = fmaxf(a_hi, b_hi);
+                            } else {
+                                upk2(t, r[2 * e], r[2 * e + 1]);
+                            }
+                        }
+                        st_global_v8(dst + co, make_float4(r[0], r[1], r[2], r[3]), make_float4(r[4], r[5], r[6], r[7]));
+                    };
+                    if (w0) finish(o0, d0v, Z0, dst0);
+                    if (w1) finish(o1, d1v, Z1, dst1);
+                }
+                // every MMA accumulates: hand this row parity's column groups back zeroed
+#pragma unroll
+                for (int c = 0; c < 3 * NTC; c += 32) tmem_zero32(lanes + cbase + (uint32_t)c);
                 if (two) {
 #pragma unroll
-                    for (int c = 0; c < N; c += 32) tmem_zero32(lanes + cother + (uint32_t)c);
+                    for (int c = 0; c < 3 * NTC; c += 32) tmem_zero32(lanes + cother + (uint32_t)c);
                 }
                 tmem_wait_st();
                 tc_fence_before();

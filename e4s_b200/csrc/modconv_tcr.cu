@@ -255,7 +255,7 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
         int slot = 0, st = 0;
         uint32_t ph = 0, phx = 0;
         bool loaded_resident = false;
-        if (lane == 0) {
+        if (elect_one()) {
             // the activation tile runs one chunk AHEAD of the weights it is consumed with (the transform warps need a
             // few thousand cycles to turn it into an operand stage)
             auto issue_x = [&](const Item& i2, int kc2) {
@@ -305,7 +305,6 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
         int sa = 0, slot = 0, acc = 0;
         uint32_t pa = 0, pb = 0, pacc0 = 0, pacc1 = 0;
         bool b_ready = false;                            // resident weights: waited for once
-        const bool leader = lane == 0;
         const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
         const uint32_t bars0 = smem_u32(bars);
         const uint32_t a0 = smem_u32(a_buf) + (role == 1 ? A_PLANE : 0), b0 = smem_u32(b_buf);
@@ -342,7 +341,7 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                             tc_fence_after();
                         }
                         const uint32_t bp = lo_of(b0 + (slot + (lo_w ? 1 : 0)) * B_SLOT);
-                        if (leader) {
+                        if (elect_one()) {
 #pragma unroll
                             for (int k = 0; k < KSTEPS; ++k) umma_bf16(d_tmem, desc(apA + roff + 2 * k), desc(bp + 2 * k), IDESC_N, 1u);
 #pragma unroll
@@ -353,7 +352,7 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                         if (slot >= p.nslot_b) slot = 0, pb ^= 1;
                         roff += (uint32_t)(((tap % 3) == 2 ? (TWP - 2) : 1) * ROWB) >> 4;
                     }
-                    if (leader) {
+                    if (elect_one()) {
                         umma_commit(bars0 + 8 * (A_EMPTY + sa));
                         umma_commit(bars0 + 8 * (A_EMPTY + sb));
                     }
@@ -374,7 +373,7 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                             tc_fence_after();
                         }
                         const uint32_t bp = lo_of(b0 + (slot + (lo_w ? 1 : 0)) * B_SLOT);
-                        if (leader) {
+                        if (elect_one()) {
 #pragma unroll
                             for (int k = 0; k < KSTEPS; ++k) umma_bf16(d_tmem, desc(ap + roff + 2 * k), desc(bp + 2 * k), IDESC_N, 1u);
                             if (!p.resident) umma_commit(bars0 + 8 * (B_EMPTY + slot));
@@ -384,7 +383,7 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                         // next tap: +1 row, or to the start of the next halo row (+16 - 2) after dx = 2
                         roff += (uint32_t)(((tap % 3) == 2 ? (TWP - 2) : 1) * ROWB) >> 4;
                     }
-                    if (leader) umma_commit(bars0 + 8 * (A_EMPTY + sa));
+                    if (elect_one()) umma_commit(bars0 + 8 * (A_EMPTY + sa));
                     if (++sa == NSTAGE_A) sa = 0, pa ^= 1;
                 }
             } else {
@@ -401,24 +400,24 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                             const uint32_t ap = lo_of(a0 + sa * A_STAGE);
                             const uint32_t boff = (uint32_t)(q * NTC * ROWB) >> 4;
                             const uint32_t dq = d_tmem + (uint32_t)(q * NTC);
-                            if (leader) {
+                            if (elect_one()) {
 #pragma unroll
                                 for (int k = 0; k < KSTEPS; ++k) umma_bf16(dq, desc(ap + 2 * k), desc(bp + boff + 2 * k), IDESC_Q, 1u);
                                 umma_commit(bars0 + 8 * (A_EMPTY + sa));
                             }
                             if (++sa == NSTAGE_A) sa = 0, pa ^= 1;
                         }
-                        if (!p.resident && leader) umma_commit(bars0 + 8 * (B_EMPTY + slot));
+                        if (!p.resident && elect_one()) umma_commit(bars0 + 8 * (B_EMPTY + slot));
                         slot += 2;
                         if (slot >= p.nslot_b) slot = 0, pb ^= 1;
                     }
                 }
             }
-            if (leader) umma_commit(bars0 + 8 * (ACC_FULL + acc));
+            if (elect_one()) umma_commit(bars0 + 8 * (ACC_FULL + acc));
             if (acc) pacc1 ^= 1; else pacc0 ^= 1;
             acc ^= 1;
             if (two) {                                   // the tile used both buffers: hand both over, buffer order unchanged
-                if (leader) umma_commit(bars0 + 8 * (ACC_FULL + acc));
+                if (elect_one()) umma_commit(bars0 + 8 * (ACC_FULL + acc));
                 if (acc) pacc1 ^= 1; else pacc0 ^= 1;
                 acc ^= 1;
             }

@@ -66,6 +66,15 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map
         "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(bar)
         : "memory");
 }
+// One lane of the (converged) warp, by elect.sync.  A region guarded by this predicate is single-lane TO THE COMPILER: its
+// tcgen05.mma operands go to uniform registers with plain R2UR moves.  Guarded by `lane == 0` instead, every tcgen05.mma
+// was wrapped in an ELECT / R2UR.BROADCAST x5 / BRA.U.ANY "waterfall" loop (~17 dependent instructions per MMA; SASS of
+// round 1) - that, not the hardware, was the ~120-190 cycles per MMA and issuing warp measured by tools/ubench/umma_bench.cu.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n.reg .pred p;\n"
@@ -122,6 +131,34 @@ __device__ __forceinline__ void tmem_ld8x3(uint32_t ta, uint32_t tb, uint32_t tc
           "=r"(c[4]), "=r"(c[5]), "=r"(c[6]), "=r"(c[7])
         : "r"(ta), "r"(tb), "r"(tc)
         : "memory");
+}
+
+// Packed fp32 pairs (sm_100: FFMA2 / FMUL2 / FADD2 - two lanes per instruction).
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ uint64_t pk2u(uint32_t lo, uint32_t hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
 }
 
 }  // namespace tcx

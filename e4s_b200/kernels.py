@@ -447,3 +447,29 @@ def norm_residual(y: Tensor, y_scale: Tensor, y_shift: Tensor, alpha: float, sho
               ptr(shortcut), ptr(sc_scale), ptr(sc_shift), int(sc_stride), ptr(prelu), ptr(out), b, h, w, c, stream_ptr(),
               work=12.0 * y.numel())
     return out
+
+
+# ------------------------------------------------------------------------------ loss-network inputs
+def avgpool_pyramid(x: Tensor):
+    """planar x [N, C, H, W] -> (2x2 block means [N, C, H/2, W/2], 4x4 block means [N, C, H/4, W/4]) in one pass."""
+    x = _f32c(x, "input")
+    _lib.ensure_device(x)
+    n, c, h, w = x.shape
+    y2 = torch.empty((n, c, h // 2, w // 2), device=x.device, dtype=torch.float32)
+    y4 = torch.empty((n, c, h // 4, w // 4), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        _call("e4s_avgpool_pyramid_f32", _lib.load().e4s_avgpool_pyramid_f32, ptr(x), ptr(y2), ptr(y4), n * c, h, w, stream_ptr(),
+              work=4.0 * x.numel() * (1 + 0.25 + 0.0625))
+    return y2, y4
+
+
+def avgpool_pyramid_bwd(g1: Optional[Tensor], g2: Optional[Tensor], g4: Optional[Tensor], shape) -> Tensor:
+    """gx [N, C, H, W] = g1 + up2(g2) / 4 + up4(g4) / 16."""
+    n, c, h, w = shape
+    ref = next(g for g in (g1, g2, g4) if g is not None)
+    g1, g2, g4 = (None if g is None else _f32c(g, "grad") for g in (g1, g2, g4))
+    gx = torch.empty((n, c, h, w), device=ref.device, dtype=torch.float32)
+    with torch.cuda.device(ref.device):
+        _call("e4s_avgpool_pyramid_bwd_f32", _lib.load().e4s_avgpool_pyramid_bwd_f32, ptr(g1), ptr(g2), ptr(g4), ptr(gx), n * c, h, w,
+              stream_ptr(), work=4.0 * gx.numel() * (2 + 0.25 + 0.0625))
+    return gx

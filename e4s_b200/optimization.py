@@ -6,9 +6,10 @@ Mirror of the hot loop of ``Optimizer.invertion`` (scripts/optimization.py:209-2
 evaluates the loss against the target image and back-propagates through the generator.
 
 Loss: the reference sums l2 (:98-101) with LPIPS, ArcFace-ID and a parsing-net loss (:92-116), each switchable by
-its lambda.  Those three are third-party pretrained networks (out of scope; section 8f.1 "next") and their
-checkpoints cannot be downloaded here, so this loop provides the l2 term natively and accepts the others as
-callables ``extra_losses = [(weight, fn(recon, target) -> scalar)]``.
+its lambda.  Pass ``criterion=e4s_b200.criteria.InversionLoss(...)`` for that full loss (reference default weights
+0.1 ID + 1.0 l2 + 0.8 LPIPS x3 scales + 0.1 parsing; the target image's features are cached once per inversion instead
+of being recomputed every step).  Without a criterion the loop uses the l2 term plus optional callables
+``extra_losses = [(weight, fn(recon, target) -> scalar)]``.
 """
 from __future__ import annotations
 
@@ -37,7 +38,8 @@ def setup_W_optimizer(W_init: torch.Tensor, opt_name: str = "adam", lr: float = 
 def invert(net, target: torch.Tensor, onehot: torch.Tensor, style_vectors: Optional[torch.Tensor] = None,
            steps: int = 200, lr: float = 1e-2, opt_name: str = "adam", l2_lambda: float = 1.0,
            extra_losses: Sequence[Tuple[float, Callable]] = (), noise: Optional[List[torch.Tensor]] = None,
-           callback: Optional[Callable] = None, cuda_graph: bool = False, stats: Optional[dict] = None):
+           callback: Optional[Callable] = None, cuda_graph: bool = False, stats: Optional[dict] = None,
+           criterion=None):
     """Optimise the texture vectors of ONE batch of faces so that net.gen_img reproduces `target`.
 
     net: e4s_b200.networks.Net3 (eval, latent_avg set).  target [B,3,S,S]; onehot [B,ncls,Hm,Wm].
@@ -45,6 +47,8 @@ def invert(net, target: torch.Tensor, onehot: torch.Tensor, style_vectors: Optio
     noise: fixed noise list, or None for fresh noise every step (the reference's behaviour, :216).
     cuda_graph: capture one step and replay it (Adam only); stats (optional dict) then receives the device time of the
     replayed steps alone ("replay_ms_per_step", "replayed_steps").
+    criterion: an e4s_b200.criteria.InversionLoss (scripts/optimization.py:88-122 with cached target features); replaces
+    l2_lambda / extra_losses.
     Returns (latent [B,ncls,1280], final reconstruction, list of per-step loss values as 0-d tensors).
     """
     if style_vectors is None:
@@ -55,16 +59,16 @@ def invert(net, target: torch.Tensor, onehot: torch.Tensor, style_vectors: Optio
             raise ValueError(f"cuda_graph=True supports opt_name='adam' only (capturable optimiser), got {opt_name!r}")
         if callback is not None:
             raise ValueError("cuda_graph=True replays a captured step: a per-step Python callback cannot run inside it")
-        return _invert_graphed(net, target, onehot, style_vectors, steps, lr, l2_lambda, extra_losses, noise, stats)
+        return _invert_graphed(net, target, onehot, style_vectors, steps, lr, l2_lambda, extra_losses, noise, stats, criterion)
+    if criterion is not None:
+        criterion.set_target(target)
     opt, latent = setup_W_optimizer(style_vectors, opt_name, lr)
     history, recon = [], None
     for step in range(steps):
         opt.zero_grad(set_to_none=True)
         codes = net.cal_style_codes(latent)
         recon, _, _ = net.gen_img(None, codes, onehot, noise=noise) if noise is not None else net.gen_img(None, codes, onehot)
-        loss = l2_lambda * F.mse_loss(recon, target) if l2_lambda > 0 else recon.new_zeros(())
-        for weight, fn in extra_losses:
-            loss = loss + weight * fn(recon, target)
+        loss = _loss(recon, target, l2_lambda, extra_losses, criterion)
         loss.backward()
         opt.step()
         history.append(loss.detach())
@@ -73,7 +77,16 @@ def invert(net, target: torch.Tensor, onehot: torch.Tensor, style_vectors: Optio
     return latent.detach(), recon.detach(), history
 
 
-def _invert_graphed(net, target, onehot, style_vectors, steps, lr, l2_lambda, extra_losses, noise, stats=None):
+def _loss(recon, target, l2_lambda, extra_losses, criterion):
+    if criterion is not None:
+        return criterion(recon)
+    loss = l2_lambda * F.mse_loss(recon, target) if l2_lambda > 0 else recon.new_zeros(())
+    for weight, fn in extra_losses:
+        loss = loss + weight * fn(recon, target)
+    return loss
+
+
+def _invert_graphed(net, target, onehot, style_vectors, steps, lr, l2_lambda, extra_losses, noise, stats=None, criterion=None):
     """The same loop with one optimisation step (zero_grad, forward, loss, backward, Adam) captured in a CUDA graph and
     replayed: at one face per GPU the eager loop is bound by ~400 kernel launches per step, not by the kernels.
     Adam only (capturable); fresh noise comes from the graph-safe CUDA generator, so every replay draws new noise."""
@@ -81,14 +94,14 @@ def _invert_graphed(net, target, onehot, style_vectors, steps, lr, l2_lambda, ex
     opt = torch.optim.Adam([latent], lr=lr, capturable=True)
     static_loss = torch.zeros((), device=latent.device)
     static_recon = torch.empty_like(target)
+    if criterion is not None:
+        criterion.set_target(target)
 
     def one_step():
         opt.zero_grad(set_to_none=False)
         codes = net.cal_style_codes(latent)
         recon, _, _ = net.gen_img(None, codes, onehot, noise=noise) if noise is not None else net.gen_img(None, codes, onehot)
-        loss = l2_lambda * F.mse_loss(recon, target) if l2_lambda > 0 else recon.new_zeros(())
-        for weight, fn in extra_losses:
-            loss = loss + weight * fn(recon, target)
+        loss = _loss(recon, target, l2_lambda, extra_losses, criterion)
         loss.backward()
         opt.step()
         static_loss.copy_(loss.detach())

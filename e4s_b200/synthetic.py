@@ -55,3 +55,50 @@ def load_synthetic(module: torch.nn.Module, salt: int = 0, parameters_only: bool
     src = dict(module.named_parameters()) if parameters_only else module.state_dict()
     state = synthetic_state({k: tuple(v.shape) for k, v in src.items()}, salt)
     module.load_state_dict(state, strict=not parameters_only)
+
+
+def synthetic_loss_state(module: torch.nn.Module, salt: int = 0) -> Dict[str, torch.Tensor]:
+    """Seeded stand-in for the loss networks' checkpoints (e4s_b200.criteria: AlexNet + LPIPS linear layers and IR-SE50 cannot
+    be downloaded; only the parsing UNet ships with the reference).  Conv / linear weights ~ N(0, 2 / fan_in), BatchNorm
+    weight 1 + 0.1 n, bias 0.1 n, running_mean 0.1 n, running_var 1 + 0.1 |n|, PReLU slopes 0.25 + 0.05 n, LPIPS linear
+    weights |n| / C; one generator per tensor, seeded by a hash of its key.  The test oracle has its own copy of this recipe
+    (oracle/loss_oracle.py:synthetic_loss_state); tests/test_losses.py asserts that the two produce bit-identical tensors."""
+    prelu = {name + ".weight" for name, m in module.named_modules() if isinstance(m, torch.nn.PReLU)}
+    out = {}
+    for key, ref in sorted(module.state_dict().items()):
+        shape = tuple(ref.shape)
+        g = torch.Generator().manual_seed(_key_seed(key) ^ salt)
+        if key.endswith("num_batches_tracked"):
+            out[key] = torch.zeros(shape, dtype=torch.int64)
+            continue
+        if key.endswith("net.mean") or key.endswith("net.std"):
+            out[key] = ref.detach().clone().cpu()
+            continue
+        t = torch.randn(shape, generator=g, dtype=torch.float32)
+        if key.endswith("running_var"):
+            t = 1.0 + 0.1 * t.abs()
+        elif key.endswith("running_mean"):
+            t = 0.1 * t
+        elif key.startswith("lin.") or ".lin." in key:
+            t = t.abs() / shape[1]
+        elif len(shape) >= 2:
+            fan_in = 1
+            for d in shape[1:]:
+                fan_in *= d
+            t = t * math.sqrt(2.0 / fan_in)
+        elif key.endswith(".bias"):
+            t = 0.1 * t
+        elif key in prelu:
+            t = 0.25 + 0.05 * t
+        elif key.endswith(".weight") and len(shape) == 1:
+            t = 1.0 + 0.1 * t
+        out[key] = t
+    return out
+
+
+def load_synthetic_losses(criterion: torch.nn.Module, salt: int = 0) -> None:
+    """Seeded weights for the three loss networks of an e4s_b200.criteria.InversionLoss (salts as oracle/loss_oracle.py:loss_states)."""
+    for off, name in enumerate(("lpips_loss", "id_loss", "face_parsing_loss")):
+        sub = getattr(criterion, name, None)
+        if sub is not None:
+            sub.load_state_dict(synthetic_loss_state(sub, salt + off), strict=True)

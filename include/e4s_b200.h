@@ -213,6 +213,16 @@ int e4s_class_reduce_f32(const float* gy, const float* y, const uint8_t* label, 
 int e4s_torgb_bwd_f32(const float* g, const float* x, const float* wrgb, const float* s, const uint8_t* label,
                       float* gx, float* gs, int batch, int h, int w, int cin, int ncls, void* stream);
 
+/* ---- loss networks of the inversion loop (scripts/optimization.py:88-122) -------------------------------------------
+ * Average-pooling pyramid: y2 = 2x2 block means, y4 = 4x4 block means of planar x [planes, H, W] (H % 4 == 0, W % 8 == 0):
+ * for a 1024x1024 image these are adaptive_avg_pool2d(x, 512) and (x, 256), the inputs of LPIPS at scales 1 and 2
+ * (optimization.py:105-108), of the parsing loss (face_parsing_loss.py:47) and of the identity loss (id_loss.py:26), in
+ * one pass over x.  The backward adds the three incoming gradients at full resolution: gx = g1 + up2(g2)/4 + up4(g4)/16
+ * (each of g1, g2, g4 may be NULL). */
+int e4s_avgpool_pyramid_f32(const float* x, float* y2, float* y4, long long planes, int h, int w, void* stream);
+int e4s_avgpool_pyramid_bwd_f32(const float* g1, const float* g2, const float* g4, float* gx, long long planes, int h, int w,
+                                void* stream);
+
 /* Layout shuffles between planar and pixel-major (boundary of the module-level API). */
 int e4s_planar_to_pixel_f32(const float* x, float* y, int batch, int c, int h, int w, void* stream);
 int e4s_pixel_to_planar_f32(const float* x, float* y, int batch, int c, int h, int w, void* stream);

@@ -79,3 +79,18 @@ def test_mask_conversion_table(golden):
     for who in ("source", "target"):
         raw, c12 = golden[f"mask/{who}_raw19"], golden[f"mask/{who}_cls12"]
         assert np.array_equal(np.asarray(CELEBA19_TO_12, dtype=np.uint8)[raw], c12)
+
+
+def test_gpu_baseline_structure_equals_oracle():
+    """oracle/gpu_baseline.py (the reference's own execution structure: per-region loop, per-sample weights, ONE grouped
+    convolution with groups = batch, model.py:287-318 - the cuDNN baseline bench.py times on the GPU) computes what the
+    pinned oracle computes."""
+    from oracle import gpu_baseline as GB
+    size, K = 64, 5
+    st = O.synthetic_state(O.generator_param_shapes(size), salt=size)
+    codes, mask, _, noise = O.synthetic_inputs(2, 5, size, 32, seed=3)
+    with torch.no_grad():
+        a, fa = O.generator_forward(st, codes, mask, noise, size, K)
+        b, fb = GB.generator_forward(st, codes, mask, noise, size, K)
+    assert float((a - b).abs().max() / a.abs().max()) < 1e-5
+    assert float((fa - fb).abs().max() / fa.abs().max()) < 1e-5
