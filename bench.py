@@ -247,7 +247,8 @@ def gpu_baseline_leg(net, size: int, ncls: int, batch: int, dev):
         noise = [n.to(dev) for n in noise]
         for tf32 in (False, True):
             try:
-                with torch.no_grad(), torch.backends.cudnn.flags(enabled=True, benchmark=True, allow_tf32=tf32):
+                from e4s_b200.criteria.inversion_loss import conv_precision      # sets the legacy AND the new cuDNN precision switch
+                with torch.no_grad(), torch.backends.cudnn.flags(enabled=True, benchmark=True), conv_precision(not tf32):
                     GB.generator_forward(gst, codes, mask, noise, size, 13)            # warm-up (cuDNN algorithm search)
                     torch.cuda.synchronize()
                     reps = 3 if b == 1 else 2

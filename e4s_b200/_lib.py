@@ -48,6 +48,7 @@ SIGNATURES = {
     "e4s_class_reduce_f32": [P] * 7 + [c_int] * 7 + [P],
     "e4s_torgb_bwd_f32": [P] * 7 + [c_int] * 5 + [P],
     "e4s_torgb_fwd_f32": [P] * 8 + [c_int] * 5 + [P],
+    "e4s_linear_f32": [P, P, P, P, c_int, c_int, c_int, c_int, c_int64, c_int64, c_int64, c_int64, c_int, c_float, P],
     "e4s_avgpool_pyramid_f32": [P, P, P, c_int64, c_int, c_int, P],
     "e4s_avgpool_pyramid_bwd_f32": [P, P, P, P, c_int64, c_int, c_int, P],
     "e4s_planar_to_pixel_f32": [P, P, c_int, c_int, c_int, c_int, P],

@@ -27,6 +27,40 @@ from .id_loss import IDLoss
 from .lpips import LPIPS
 
 
+class conv_precision:
+    """Context manager: cuDNN convolutions in full fp32 (exact=True: the parity setting) or TF32 (what torch and the reference
+    use by default).  Sets both the legacy switch (torch.backends.cudnn.allow_tf32) and, where this torch has it, the newer
+    torch.backends.cudnn.conv.fp32_precision - with only the legacy one, cuDNN still picked TF32-class algorithms for some
+    layers (AlexNet's 5x5 convolution: 2e-3 against 1e-6, gpurun diagnostics of round 2)."""
+
+    def __init__(self, exact: bool):
+        self.exact = exact
+
+    def __enter__(self):
+        self.legacy = torch.backends.cudnn.allow_tf32
+        conv = getattr(torch.backends.cudnn, "conv", None)
+        self.new = getattr(conv, "fp32_precision", None) if conv is not None else None
+        try:
+            if self.new is not None:
+                conv.fp32_precision = "ieee" if self.exact else "tf32"
+            else:
+                torch.backends.cudnn.allow_tf32 = not self.exact
+        except Exception:                                  # mixing the two APIs is an error in some versions: fall back
+            torch.backends.cudnn.allow_tf32 = not self.exact
+        return self
+
+    def __exit__(self, *exc):
+        conv = getattr(torch.backends.cudnn, "conv", None)
+        try:
+            if self.new is not None:
+                conv.fp32_precision = self.new
+            else:
+                torch.backends.cudnn.allow_tf32 = self.legacy
+        except Exception:
+            pass
+        return False
+
+
 class _Pyramid(torch.autograd.Function):
     """(x) -> (2x2 block means, 4x4 block means) with a fused backward."""
 
@@ -79,7 +113,7 @@ class InversionLoss(nn.Module):
     def _features(self, img: torch.Tensor) -> Dict[str, object]:
         pyr, for_id, for_parsing = self._views(img)
         out: Dict[str, object] = {}
-        with torch.backends.cudnn.flags(enabled=True, allow_tf32=not self.exact):
+        with conv_precision(self.exact):
             if self.lpips_loss is not None:
                 out["lpips"] = [self.lpips_loss.features(t) for t in pyr]
             if self.id_loss is not None:

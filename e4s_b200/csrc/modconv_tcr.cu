@@ -694,22 +694,36 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                         }
                     }
                     if (mine) {
+                        // packed fp32 pairs (FFMA2 / FMUL2 / FADD2): t = acc * demod + (noise + bias), and for the fused leaky
+                        // ReLU sqrt(2) * lrelu_0.2(t) = max(sqrt(2) t, 0.2 sqrt(2) t) with sqrt(2) folded into both operands -
+                        // ~3 instructions per output instead of ~7 (the epilogue warps, one per scheduler, bound the
+                        // small-K layers: profiles/r2_stall_attribution_tcr_elect.log)
+                        const float k2 = 1.41421356237309515f;
+                        const uint64_t S2 = pk2(k2, k2), P2 = pk2(0.2f, 0.2f);
+                        const uint64_t ZQ = p.act == 1 ? pk2(k2 * nz[q], k2 * nz[q]) : pk2(nz[q], nz[q]);
                         float4 keep = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                         for (int g = 0; g < 8; ++g) {
                             const int co = j * 32 + 4 * g;
                             const float4 d = dmr[g & 1], bv = bvr[g & 1];
                             if (g + 2 < 8) dmr[g & 1] = ld_dm(g + 2), bvr[g & 1] = ld_bv(g + 2);
-                            float4 o;
-                            o.x = __uint_as_float(r[4 * g + 0]) * d.x + nz[q] + bv.x;
-                            o.y = __uint_as_float(r[4 * g + 1]) * d.y + nz[q] + bv.y;
-                            o.z = __uint_as_float(r[4 * g + 2]) * d.z + nz[q] + bv.z;
-                            o.w = __uint_as_float(r[4 * g + 3]) * d.w + nz[q] + bv.w;
-                            if (p.act == 1) {
-                                const float k = 1.41421356237309515f;
-                                o.x = lrelu_scaled(o.x, 0.2f, k), o.y = lrelu_scaled(o.y, 0.2f, k);
-                                o.z = lrelu_scaled(o.z, 0.2f, k), o.w = lrelu_scaled(o.w, 0.2f, k);
-                            } else if (p.act == 2) {
+                            uint64_t dd[2] = {pk2(d.x, d.y), pk2(d.z, d.w)}, zz[2] = {pk2(bv.x, bv.y), pk2(bv.z, bv.w)};
+                            const uint64_t rr[2] = {pk2u(r[4 * g + 0], r[4 * g + 1]), pk2u(r[4 * g + 2], r[4 * g + 3])};
+                            float o4[4];
+#pragma unroll
+                            for (int h2 = 0; h2 < 2; ++h2) {
+                                if (p.act == 1) dd[h2] = mul2(dd[h2], S2), zz[h2] = fma2(zz[h2], S2, ZQ);
+                                else zz[h2] = add2(zz[h2], ZQ);
+                                const uint64_t t = fma2(rr[h2], dd[h2], zz[h2]);
+                                upk2(t, o4[2 * h2], o4[2 * h2 + 1]);
+                                if (p.act == 1) {
+                                    float u0, u1;
+                                    upk2(mul2(t, P2), u0, u1);
+                                    o4[2 * h2] = fmaxf(o4[2 * h2], u0), o4[2 * h2 + 1] = fmaxf(o4[2 * h2 + 1], u1);
+                                }
+                            }
+                            float4 o = make_float4(o4[0], o4[1], o4[2], o4[3]);
+                            if (p.act == 2) {
                                 const float4 sl = __ldg(reinterpret_cast<const float4*>(p.slope + n0 + co));
                                 o.x = o.x > 0.f ? o.x : o.x * sl.x, o.y = o.y > 0.f ? o.y : o.y * sl.y;
                                 o.z = o.z > 0.f ? o.z : o.z * sl.z, o.w = o.w > 0.f ? o.w : o.w * sl.w;

@@ -473,3 +473,26 @@ def avgpool_pyramid_bwd(g1: Optional[Tensor], g2: Optional[Tensor], g4: Optional
         _call("e4s_avgpool_pyramid_bwd_f32", _lib.load().e4s_avgpool_pyramid_bwd_f32, ptr(g1), ptr(g2), ptr(g4), ptr(gx), n * c, h, w,
               stream_ptr(), work=4.0 * gx.numel() * (2 + 0.25 + 0.0625))
     return gx
+
+
+# ------------------------------------------------------------------------------ small GEMMs (style modulation, LocalMLP)
+def linear(x: Tensor, w: Tensor, bias: Optional[Tensor] = None, act_slope: float = 1.0, w_is_kn: bool = False) -> Tensor:
+    """Grouped small fp32 GEMM on the library's own kernel (csrc/linear.cu).
+
+    x: [G, M, K] or [M, K]; w: [G, N, K] / [N, K] (nn.Linear layout) or, with w_is_kn, [G, K, N] / [K, N]; bias [G, N] / [N].
+    A 2-D operand is shared by every group.  Returns [G, M, N] (or [M, N] when nothing is grouped)."""
+    x, w = _f32c(x, "input"), _f32c(w, "weight")
+    _lib.ensure_device(x)
+    groups = max(x.shape[0] if x.ndim == 3 else 1, w.shape[0] if w.ndim == 3 else 1)
+    m, k = x.shape[-2], x.shape[-1]
+    n = w.shape[-1] if w_is_kn else w.shape[-2]
+    assert (w.shape[-2] if w_is_kn else w.shape[-1]) == k, (tuple(x.shape), tuple(w.shape))
+    if bias is not None:
+        bias = _f32c(bias, "bias")
+    grouped = x.ndim == 3 or w.ndim == 3
+    y = torch.empty((groups, m, n) if grouped else (m, n), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        _call("e4s_linear_f32", _lib.load().e4s_linear_f32, ptr(x), ptr(w), ptr(bias), ptr(y), groups, m, n, k,
+              m * k if x.ndim == 3 else 0, n * k if w.ndim == 3 else 0, (n if (bias is not None and bias.ndim == 2) else 0), m * n,
+              int(w_is_kn), float(act_slope), stream_ptr(), work=2.0 * groups * m * n * k)
+    return y

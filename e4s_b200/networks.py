@@ -64,23 +64,27 @@ class Net3(nn.Module):
             with torch.no_grad():
                 l0 = [m.mlp[0] for m in self.MLPs]
                 l2 = [m.mlp[2] for m in self.MLPs]
-                w0 = torch.stack([(l.weight * l.scale).t() for l in l0]).contiguous()      # [ncls, 1280, 512]
-                b0 = torch.stack([l.bias * l.lr_mul for l in l0]).unsqueeze(1)             # [ncls, 1, 512]
-                w2 = torch.stack([(l.weight * l.scale).t() for l in l2]).contiguous()      # [ncls, 512, K*512]
-                b2 = torch.stack([l.bias * l.lr_mul for l in l2]).unsqueeze(1)
+                w0 = torch.stack([l.weight * l.scale for l in l0]).float().contiguous()    # [ncls, 512, 1280]  (nn.Linear layout)
+                b0 = torch.stack([l.bias * l.lr_mul for l in l0]).float().contiguous()     # [ncls, 512]
+                w2 = torch.stack([l.weight * l.scale for l in l2]).float().contiguous()    # [ncls, K*512, 512]
+                b2 = torch.stack([l.bias * l.lr_mul for l in l2]).float().contiguous()
             self._mlp_cache = (key, w0, b0, w2, b2)
         return self._mlp_cache[1:]
 
     def _region_codes(self, style_vectors):
-        """[B, ncls, 1280] -> [B, ncls, K, 512]: the ncls LocalMLPs as two batched GEMMs."""
+        """[B, ncls, 1280] -> [B, ncls, K, 512]: the ncls LocalMLPs (networks.py:15-39) as two grouped GEMMs on the library's own
+        small-GEMM kernel (csrc/linear.cu), leaky ReLU 0.01 fused into the first."""
         bs, ncls = style_vectors.shape[:2]
         trainable = torch.is_grad_enabled() and any(p.requires_grad for p in self.MLPs.parameters())
         if trainable:   # keep the parameter graph (training is outside the hot path)
             return torch.stack([self.MLPs[i](style_vectors[:, i, :]) for i in range(ncls)], dim=1)
         w0, b0, w2, b2 = self._stacked_mlps()
-        h = torch.baddbmm(b0, style_vectors.transpose(0, 1), w0)           # [ncls, B, 512]
-        h = F.leaky_relu(h, 0.01)
-        o = torch.baddbmm(b2, h, w2)                                       # [ncls, B, K*512]
+        if not style_vectors.is_cuda:
+            raise RuntimeError("input must be a CUDA tensor")
+        from .stylegan2.modconv import LinearFn
+        x = style_vectors.float().transpose(0, 1).contiguous()              # [ncls, B, 1280]
+        h = LinearFn.apply(x, w0, b0, 0.01)                                 # [ncls, B, 512]   EqualLinear + LeakyReLU(0.01)
+        o = LinearFn.apply(h, w2, b2, 1.0)                                  # [ncls, B, K*512]
         return o.transpose(0, 1).reshape(bs, ncls, -1, 512)
 
     def _add_latent_avg(self, codes):

@@ -210,6 +210,25 @@ def up_form(prep: "PreparedConv") -> str:
 
 
 # ================================================================================== autograd
+class LinearFn(Function):
+    """y = leaky_relu(x @ w^T + bias, slope) on the library's small-GEMM kernel (csrc/linear.cu); w, bias are frozen prepared
+    tensors (scale / lr_mul folded in), grouped or shared (kernels.linear).  Differentiable wrt x."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, slope):
+        y = K.linear(x, w, bias, slope)
+        ctx.slope = float(slope)
+        ctx.save_for_backward(w, y if slope != 1.0 else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        w, y = ctx.saved_tensors
+        if ctx.slope != 1.0:
+            gy = gy * torch.where(y > 0, 1.0, ctx.slope)
+        return K.linear(gy.contiguous(), w, None, 1.0, w_is_kn=True), None, None, None
+
+
 class StyledConvFn(Function):
     """y = act(demod * conv(x*s) + noise_w*noise + bias) on pixel-major tensors; differentiable wrt x, s, noise."""
 

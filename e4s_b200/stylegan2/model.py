@@ -106,7 +106,25 @@ class EqualLinear(nn.Module):
         self.scale = (1 / math.sqrt(in_dim)) * lr_mul
         self.lr_mul = lr_mul
 
+    def _frozen(self):
+        """(weight * scale, bias * lr_mul) of the frozen parameters, cached per parameter version."""
+        key = (self.weight.data_ptr(), self.weight._version, None if self.bias is None else (self.bias.data_ptr(), self.bias._version))
+        if getattr(self, "_prep_key", None) != key:
+            with torch.no_grad():
+                self._prep = ((self.weight * self.scale).float().contiguous(),
+                              None if self.bias is None else (self.bias * self.lr_mul).float().contiguous())
+            self._prep_key = key
+        return self._prep
+
     def forward(self, input):
+        trainable = torch.is_grad_enabled() and (self.weight.requires_grad or (self.bias is not None and self.bias.requires_grad))
+        if (input.is_cuda and not self.activation and not trainable and input.dtype == torch.float32
+                and self.weight.shape[0] % 4 == 0 and self.weight.shape[1] % 4 == 0):
+            # the style modulations of the synthesis path (model.py:276): own small-GEMM kernel, no library GEMM
+            w, b = self._frozen()
+            lead = input.shape[:-1]
+            y = MC.LinearFn.apply(input.reshape(-1, input.shape[-1]).contiguous(), w, b, 1.0)
+            return y.reshape(*lead, w.shape[0])
         w = self.weight * self.scale
         if self.activation:
             return fused_leaky_relu(F.linear(input, w), self.bias * self.lr_mul)

@@ -59,9 +59,10 @@ def load_synthetic(module: torch.nn.Module, salt: int = 0, parameters_only: bool
 
 def synthetic_loss_state(module: torch.nn.Module, salt: int = 0) -> Dict[str, torch.Tensor]:
     """Seeded stand-in for the loss networks' checkpoints (e4s_b200.criteria: AlexNet + LPIPS linear layers and IR-SE50 cannot
-    be downloaded; only the parsing UNet ships with the reference).  Conv / linear weights ~ N(0, 2 / fan_in), BatchNorm
-    weight 1 + 0.1 n, bias 0.1 n, running_mean 0.1 n, running_var 1 + 0.1 |n|, PReLU slopes 0.25 + 0.05 n, LPIPS linear
-    weights |n| / C; one generator per tensor, seeded by a hash of its key.  The test oracle has its own copy of this recipe
+    be downloaded; only the parsing UNet ships with the reference).  Conv / linear weights ~ N(0, 2 / fan_in) (ReLU networks)
+    or N(0, 1 / fan_in) with the last BatchNorm of every residual branch at 0.25 (IR-SE50: a stand-in has to be as well
+    conditioned as a trained network), BatchNorm otherwise weight 1 + 0.1 n, bias 0.1 n, running_mean 0.1 n, running_var
+    1 + 0.1 |n|, PReLU slopes 0.25 + 0.05 n, LPIPS linear weights |n| / C; one generator per tensor, seeded by a hash of its key.  The test oracle has its own copy of this recipe
     (oracle/loss_oracle.py:synthetic_loss_state); tests/test_losses.py asserts that the two produce bit-identical tensors."""
     prelu = {name + ".weight" for name, m in module.named_modules() if isinstance(m, torch.nn.PReLU)}
     out = {}
@@ -85,11 +86,13 @@ def synthetic_loss_state(module: torch.nn.Module, salt: int = 0) -> Dict[str, to
             fan_in = 1
             for d in shape[1:]:
                 fan_in *= d
-            t = t * math.sqrt(2.0 / fan_in)
+            t = t * math.sqrt((1.0 if key.startswith("facenet.") else 2.0) / fan_in)
         elif key.endswith(".bias"):
             t = 0.1 * t
         elif key in prelu:
             t = 0.25 + 0.05 * t
+        elif key.endswith("res_layer.4.weight"):
+            t = 0.25 * (1.0 + 0.1 * t)
         elif key.endswith(".weight") and len(shape) == 1:
             t = 1.0 + 0.1 * t
         out[key] = t

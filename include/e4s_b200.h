@@ -213,6 +213,16 @@ int e4s_class_reduce_f32(const float* gy, const float* y, const uint8_t* label, 
 int e4s_torgb_bwd_f32(const float* g, const float* x, const float* wrgb, const float* s, const uint8_t* label,
                       float* gx, float* gs, int batch, int h, int w, int cin, int ncls, void* stream);
 
+/* ---- small fp32 GEMMs: EqualLinear style modulation (model.py:135-169, :276) and LocalMLP (networks.py:15-39) -----------
+ * w_is_kn == 0:  y[g, m, n] = act( sum_k x[g, m, k] * w[g, n, k] + bias[g, n] )   (w in nn.Linear layout [N, K]; the caller has
+ *                folded EqualLinear's scale / lr_mul into w and bias)
+ * w_is_kn != 0:  y[g, m, n] = sum_k x[g, m, k] * w[g, k, n]                        (input gradient of the above; bias must be NULL)
+ * act = leaky ReLU with slope act_slope (1 = none).  *_gstride: element strides between groups (0 = shared operand).
+ * n % 4 == 0, k % 4 == 0, 16-byte aligned pointers. */
+int e4s_linear_f32(const float* x, const float* w, const float* bias, float* y, int groups, int m, int n, int k,
+                   long long x_gstride, long long w_gstride, long long bias_gstride, long long y_gstride, int w_is_kn,
+                   float act_slope, void* stream);
+
 /* ---- loss networks of the inversion loop (scripts/optimization.py:88-122) -------------------------------------------
  * Average-pooling pyramid: y2 = 2x2 block means, y4 = 4x4 block means of planar x [planes, H, W] (H % 4 == 0, W % 8 == 0):
  * for a 1024x1024 image these are adaptive_avg_pool2d(x, 512) and (x, 256), the inputs of LPIPS at scales 1 and 2

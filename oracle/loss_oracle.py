@@ -32,9 +32,12 @@ def _key_seed(key: str) -> int:
 
 def synthetic_loss_state(shapes: Dict[str, Sequence[int]], salt: int = 0, prelu_keys: Sequence[str] = ()) -> Dict[str, Tensor]:
     """Seeded stand-in for the loss networks' checkpoints (AlexNet + LPIPS linear layers and IR-SE50 cannot be downloaded).
-    Convolution / linear weights ~ N(0, 2 / fan_in) keep the activations O(1); BatchNorm gets weight 1 + 0.1 n, bias 0.1 n,
-    running_mean 0.1 n, running_var 1 + 0.1 |n|; PReLU slopes 0.25 + 0.05 n; LPIPS linear weights |n| / C (non-negative
-    like the trained ones).  Each tensor has its own generator seeded by a hash of its key."""
+    Convolution / linear weights ~ N(0, 2 / fan_in) in the ReLU networks (AlexNet, UNet) and N(0, 1 / fan_in) in the residual
+    IR-SE50, whose last BatchNorm of every residual branch gets weight 0.25 (1 + 0.1 n): a plain He-initialised 24-unit residual
+    stack doubles its activation variance per unit (|x| ~ 2500 at the output) and its input gradient then amplifies fp32
+    rounding differences between devices to O(1) - a stand-in must be as well conditioned as a trained network.  BatchNorm
+    otherwise weight 1 + 0.1 n, bias 0.1 n, running_mean 0.1 n, running_var 1 + 0.1 |n|; PReLU slopes 0.25 + 0.05 n; LPIPS
+    linear weights |n| / C (non-negative like the trained ones).  Each tensor has its own generator seeded by a hash of its key."""
     out = {}
     for key in sorted(shapes):
         shape = tuple(shapes[key])
@@ -59,11 +62,13 @@ def synthetic_loss_state(shapes: Dict[str, Sequence[int]], salt: int = 0, prelu_
             fan_in = 1
             for d in shape[1:]:
                 fan_in *= d
-            t = t * math.sqrt(2.0 / fan_in)
+            t = t * math.sqrt((1.0 if key.startswith("facenet.") else 2.0) / fan_in)
         elif key.endswith(".bias"):
             t = 0.1 * t
         elif key in prelu_keys:                                      # PReLU slopes share the '.weight' suffix with BatchNorm scales
             t = 0.25 + 0.05 * t
+        elif key.endswith("res_layer.4.weight"):                     # last BatchNorm of an IR-SE residual branch
+            t = 0.25 * (1.0 + 0.1 * t)
         elif key.endswith(".weight") and len(shape) == 1:            # BatchNorm scale
             t = 1.0 + 0.1 * t
         out[key] = t

@@ -95,6 +95,11 @@ def test_product_loss_modules_state_dict_contract():
 
 
 # ---------------------------------------------------------------------------------------------- GPU: the product
+def conv_precision(exact):
+    from e4s_b200.criteria.inversion_loss import conv_precision as cp
+    return cp(exact)
+
+
 def _criterion(**kw):
     from e4s_b200.criteria import InversionLoss
     from e4s_b200.synthetic import load_synthetic_losses
@@ -125,7 +130,7 @@ def test_pool_pyramid_kernel():
 def test_loss_modules_match_reference_vectors(gold):
     m = _criterion()
     img, recon, far = (t.to(DEV) for t in LO.golden_inputs())
-    with torch.no_grad(), torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+    with torch.no_grad(), conv_precision(True):
         for tag, r in (("near", recon), ("far", far)):
             _close(m.lpips_loss(r, img), gold[f"lpips/{tag}"], 1e-3)
             _close(m.id_loss(r, img)[0], gold[f"id/{tag}"], 1e-3, COS_ATOL)
@@ -154,7 +159,7 @@ def test_inversion_loss_matches_reference_calc_loss(gold):
     g = torch.Generator().manual_seed(9)
     big = (torch.rand(1, 3, 1024, 1024, generator=g) * 2 - 1).to(DEV)
     big_r = (big + 0.1 * torch.randn(1, 3, 1024, 1024, generator=g).to(DEV)).clamp(-1, 1)
-    with torch.no_grad(), torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+    with torch.no_grad(), conv_precision(True):
         fused = m(big_r, big)
         lp = sum(m.lpips_loss(torch.nn.functional.adaptive_avg_pool2d(big_r, (s, s)), torch.nn.functional.adaptive_avg_pool2d(big, (s, s)))
                  for s in (1024, 512, 256))

@@ -342,6 +342,47 @@ def test_streaming_pipeline_matches_direct_calls():
         pipe.result(tickets[0])                         # only `depth` results are held
 
 
+# ---------------------------------------------------------------- small GEMMs (style modulation, LocalMLP)
+@pytest.mark.parametrize("g,m,n,k,shared_x,shared_w", [
+    (1, 192, 512, 512, True, True),        # one style modulation: [B * regions, 512] x [512, Cin]
+    (1, 1, 32, 512, True, True),           # one face, unmasked layer
+    (12, 16, 512, 1280, False, False),     # LocalMLP layer 1, grouped over the regions
+    (12, 3, 6656, 512, False, False),      # LocalMLP layer 2, odd batch
+    (5, 37, 68, 36, False, True),          # partial tiles in every dimension, shared weight
+])
+def test_linear_kernel(g, m, n, k, shared_x, shared_w):
+    from e4s_b200 import kernels as K
+    gen = torch.Generator().manual_seed(g + m + n + k)
+    x = torch.randn((m, k) if (shared_x and shared_w) else (g, m, k), generator=gen)
+    w = torch.randn((n, k) if shared_w else (g, n, k), generator=gen) / k ** 0.5
+    bias = torch.randn((n,) if shared_w else (g, n), generator=gen)
+    ref = torch.matmul(x.double(), w.double().transpose(-1, -2)) + (bias.double() if shared_w else bias.double()[:, None, :])
+    out = K.linear(cu(x), cu(w), cu(bias), 0.01)
+    assert_close(out, torch.nn.functional.leaky_relu(ref, 0.01).float(), 1e-5, "linear TN + bias + leaky")
+    gy = torch.randn(ref.shape, generator=gen)
+    gx = K.linear(cu(gy), cu(w), None, 1.0, w_is_kn=True)
+    assert_close(gx, torch.matmul(gy.double(), w.double()).float(), 1e-5, "linear NN (input gradient)")
+
+
+def test_local_mlps_match_oracle_and_autograd():
+    """Net3.cal_style_codes (12 LocalMLPs, networks.py:135-158) on the own GEMM kernel: values and the gradient wrt the texture
+    vectors (what the inversion loop optimises) against the oracle's autograd."""
+    net, st = _net3()
+    for prm in net.parameters():
+        prm.requires_grad = False
+    net.latent_avg = cu(0.5 * torch.randn(18, 512, generator=torch.Generator().manual_seed(77)))
+    sv = torch.randn(3, 12, 1280, generator=torch.Generator().manual_seed(1))
+    go = torch.randn(3, 12, 18, 512, generator=torch.Generator().manual_seed(2))
+    a = cu(sv).requires_grad_(True)
+    ours = net.cal_style_codes(a)
+    ours.backward(cu(go))
+    b = sv.clone().requires_grad_(True)
+    ref = O.cal_style_codes(st, b, net.latent_avg.cpu(), 13)
+    ref.backward(go)
+    assert_close(ours, ref, 1e-5, "cal_style_codes")
+    assert_close(a.grad, b.grad, 1e-5, "d cal_style_codes / d texture vectors")
+
+
 # ---------------------------------------------------------------- tensor-core (tcgen05) kernel
 def _tc_case(b, cin, cout, hw, up, ncls, kind, seed, act=True):
     from e4s_b200 import kernels as K
