@@ -248,7 +248,9 @@ def gpu_baseline_leg(net, size: int, ncls: int, batch: int, dev):
         for tf32 in (False, True):
             try:
                 from e4s_b200.criteria.inversion_loss import conv_precision      # sets the legacy AND the new cuDNN precision switch
-                with torch.no_grad(), torch.backends.cudnn.flags(enabled=True, benchmark=True), conv_precision(not tf32):
+                bench_before = torch.backends.cudnn.benchmark
+                torch.backends.cudnn.benchmark = True                                  # let cuDNN pick its fastest algorithms
+                with torch.no_grad(), conv_precision(not tf32):
                     GB.generator_forward(gst, codes, mask, noise, size, 13)            # warm-up (cuDNN algorithm search)
                     torch.cuda.synchronize()
                     reps = 3 if b == 1 else 2
@@ -258,6 +260,7 @@ def gpu_baseline_leg(net, size: int, ncls: int, batch: int, dev):
                         GB.generator_forward(gst, codes, mask, noise, size, 13)
                     e1.record()
                     torch.cuda.synchronize()
+                torch.backends.cudnn.benchmark = bench_before
                 ms = e0.elapsed_time(e1) / reps
                 out["runs"].append({"batch": b, "tf32": tf32, "ms_per_step": ms, "faces_per_sec": b / (ms * 1e-3)})
             except Exception as exc:                                   # e.g. out of memory at the full batch: reported

@@ -84,7 +84,26 @@ def build_profile(verbose: bool = False) -> str:
     return lib
 
 
+def build_variant(name: str, defines, verbose: bool = False) -> str:
+    """A/B twin of the library with extra -D switches on the tensor-core kernels (diagnostics only): libe4s_b200_<name>.so."""
+    build(verbose=verbose)
+    objdir = os.path.join(CSRC, "_obj_" + name)
+    os.makedirs(objdir, exist_ok=True)
+    srcs = [os.path.join(CSRC, "modconv_tcr.cu"), os.path.join(CSRC, "modconv_tch.cu")]
+    objs = [_compile(src, verbose, objdir, ["-D" + d for d in defines])[0] for src in srcs]
+    others = [os.path.join(OBJ, os.path.basename(s)[:-3] + ".o") for s in sorted(glob.glob(os.path.join(CSRC, "*.cu"))) if s not in srcs]
+    lib = os.path.join(PKG, f"libe4s_b200_{name}.so")
+    r = subprocess.run([NVCC] + ARCH + ["-shared", "-o", lib] + objs + others + ["-lcudart", "-lcuda"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return lib
+
+
 if __name__ == "__main__":
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], sys.argv[i + 2:]))
+        sys.exit(0)
     if "--profile" in sys.argv:
         print(build_profile(verbose="--verbose" in sys.argv))
         sys.exit(0)

@@ -37,27 +37,26 @@ class conv_precision:
         self.exact = exact
 
     def __enter__(self):
-        self.legacy = torch.backends.cudnn.allow_tf32
-        conv = getattr(torch.backends.cudnn, "conv", None)
-        self.new = getattr(conv, "fp32_precision", None) if conv is not None else None
-        try:
-            if self.new is not None:
-                conv.fp32_precision = "ieee" if self.exact else "tf32"
-            else:
-                torch.backends.cudnn.allow_tf32 = not self.exact
-        except Exception:                                  # mixing the two APIs is an error in some versions: fall back
+        # new API (torch >= 2.9): per-operator switches; conv and rnn are set TOGETHER - torch raises on any legacy-flag read when
+        # they differ ("mix of the legacy and new APIs")
+        self.saved = []
+        mods = [getattr(torch.backends.cudnn, n, None) for n in ("conv", "rnn")]
+        mods = [m for m in mods if m is not None and hasattr(m, "fp32_precision")]
+        if mods:
+            for m in mods:
+                self.saved.append((m, m.fp32_precision))
+                m.fp32_precision = "ieee" if self.exact else "tf32"
+        else:
+            self.saved.append((None, torch.backends.cudnn.allow_tf32))
             torch.backends.cudnn.allow_tf32 = not self.exact
         return self
 
     def __exit__(self, *exc):
-        conv = getattr(torch.backends.cudnn, "conv", None)
-        try:
-            if self.new is not None:
-                conv.fp32_precision = self.new
+        for m, v in self.saved:
+            if m is None:
+                torch.backends.cudnn.allow_tf32 = v
             else:
-                torch.backends.cudnn.allow_tf32 = self.legacy
-        except Exception:
-            pass
+                m.fp32_precision = v
         return False
 
 

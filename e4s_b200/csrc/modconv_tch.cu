@@ -58,6 +58,7 @@ struct Params {
     float f0, f1, f2, f3;                       // flipped horizontal FIR taps
     int batch, h, w, cin, cout, ncls, noise_b, act;
     int tiles_x, tiles_y, n_tiles, items, nslot_b;
+    int det;              // 1: one warp issues the three split-precision products in a fixed order (bit-reproducible)
     long long* prof;      // optional [4 roles][4] cycle counters of CTA 0 (e4s_tch_set_profile; diagnostic build only)
 };
 
@@ -160,9 +161,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) modconv3x3_up_tch_kernel(const
 #endif
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < NSTAGE_A; ++i) mbar_init(smem_u32(&bars[A_FULL + i]), NUM_XFORM), mbar_init(smem_u32(&bars[A_EMPTY + i]), NUM_MMA_WARPS);
-        for (int i = 0; i < NACC; ++i) mbar_init(smem_u32(&bars[ACC_FULL + i]), NUM_MMA_WARPS), mbar_init(smem_u32(&bars[ACC_EMPTY + i]), NUM_EPI);
-        for (int i = 0; i < p.nslot_b; ++i) mbar_init(smem_u32(&bars[B_FULL + i]), 1), mbar_init(smem_u32(&bars[B_EMPTY + i]), NUM_MMA_WARPS);
+        const uint32_t nmma = p.det ? 1u : (uint32_t)NUM_MMA_WARPS;      // issuing warps that commit to each barrier
+        for (int i = 0; i < NSTAGE_A; ++i) mbar_init(smem_u32(&bars[A_FULL + i]), NUM_XFORM), mbar_init(smem_u32(&bars[A_EMPTY + i]), nmma);
+        for (int i = 0; i < NACC; ++i) mbar_init(smem_u32(&bars[ACC_FULL + i]), nmma), mbar_init(smem_u32(&bars[ACC_EMPTY + i]), NUM_EPI);
+        for (int i = 0; i < p.nslot_b; ++i) mbar_init(smem_u32(&bars[B_FULL + i]), 1), mbar_init(smem_u32(&bars[B_EMPTY + i]), nmma);
         fence_barrier_init();
     }
     if (warp == 0 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&wmap) : "memory");
@@ -209,14 +211,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) modconv3x3_up_tch_kernel(const
             __syncwarp();
         }
     } else if (warp <= NUM_MMA_WARPS) {
-        // ===================================================================== MMA issuers: role 0 x_hi w_hi, 1 x_lo w_hi, 2 x_hi w_lo
+      if (!p.det || warp == 1) {
+        // ===================================================================== MMA issuers: product 0 x_hi w_hi, 1 x_lo w_hi, 2 x_hi w_lo,
+        // one warp each; deterministic mode (p.det): warp 1 issues all three in this order, the other two idle
         const int role = warp - 1;
-        const bool lo_w = role == 2;
+        constexpr uint32_t A_LO = (uint32_t)A_PLANE >> 4, W_LO = (uint32_t)B_SLOT >> 4;
+        const uint32_t a_role = role == 1 ? A_LO : 0u, w_role = role == 2 ? W_LO : 0u;
         int sa = 0, slot = 0, acc = 0;
         uint32_t pa = 0, pb = 0, pacc = 0;                // bit b = phase of accumulator buffer b
         const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
         const uint32_t bars0 = smem_u32(bars);
-        const uint32_t a0 = smem_u32(a_buf) + (role == 1 ? A_PLANE : 0), b0 = smem_u32(b_buf);
+        const uint32_t a0 = smem_u32(a_buf), b0 = smem_u32(b_buf);
         auto desc = [](uint32_t lo) -> uint64_t { return ((uint64_t)DESC_HI << 32) | lo; };
         auto lo_of = [](uint32_t addr) -> uint32_t { return (addr >> 4) | 0x10000u; };
         Walk wk;
@@ -245,14 +250,27 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) modconv3x3_up_tch_kernel(const
                     for (int tap = 0; tap < 3; ++tap) {
                         TCH_WAIT(bars0 + 8 * (B_FULL + slot), pb, 3);
                         tc_fence_after();
-                        const uint32_t bp = lo_of(b0 + (slot + (lo_w ? 1 : 0)) * B_SLOT);
+                        const uint32_t bp = lo_of(b0 + slot * B_SLOT);
                         const uint32_t roff = (uint32_t)((1 + 16 * tap) * ROWB) >> 4;       // halo pixel hp is operand row hp + 1
                         if (elect_one()) {
+                            if (!p.det) {
 #pragma unroll
-                            for (int k = 0; k < KSTEPS; ++k) umma_bf16(d_a, desc(apA + roff + 2 * k), desc(bp + 2 * k), IDESC, 1u);
-                            if (two) {
+                                for (int k = 0; k < KSTEPS; ++k) umma_bf16(d_a, desc(apA + a_role + roff + 2 * k), desc(bp + w_role + 2 * k), IDESC, 1u);
+                                if (two) {
 #pragma unroll
-                                for (int k = 0; k < KSTEPS; ++k) umma_bf16(d_b, desc(apB + roff + 2 * k), desc(bp + 2 * k), IDESC, 1u);
+                                    for (int k = 0; k < KSTEPS; ++k) umma_bf16(d_b, desc(apB + a_role + roff + 2 * k), desc(bp + w_role + 2 * k), IDESC, 1u);
+                                }
+                            } else {
+#pragma unroll 1
+                                for (int r = 0; r < 3; ++r) {
+                                    const uint32_t ao = r == 1 ? A_LO : 0u, wo2 = r == 2 ? W_LO : 0u;
+#pragma unroll
+                                    for (int k = 0; k < KSTEPS; ++k) umma_bf16(d_a, desc(apA + ao + roff + 2 * k), desc(bp + wo2 + 2 * k), IDESC, 1u);
+                                    if (two) {
+#pragma unroll
+                                        for (int k = 0; k < KSTEPS; ++k) umma_bf16(d_b, desc(apB + ao + roff + 2 * k), desc(bp + wo2 + 2 * k), IDESC, 1u);
+                                    }
+                                }
                             }
                             umma_commit(bars0 + 8 * (B_EMPTY + slot));
                         }
@@ -277,6 +295,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) modconv3x3_up_tch_kernel(const
                 __syncwarp();
             }
         }
+      }
     } else if (warp < W_EPI0) {
         // ===================================================================== activation transform: fp32 x region style -> bf16 hi/lo stage
         const int t = threadIdx.x - 32 * W_XFORM0;       // 0..255
@@ -527,6 +546,7 @@ static long long* g_prof = nullptr;
 template <int NTC, int KC>
 static int launch(const void* v_hilo, Params p, cudaStream_t st) {
     p.prof = g_prof;
+    p.det = e4s_get_deterministic();
     constexpr int N = NG * NTC, ROWB = KC * 2;
     constexpr int A_BYTES = ((NSTAGE_A * 2 * A_ROWS * ROWB) + 1023) & ~1023;
     constexpr int B_SLOT = N * ROWB;
@@ -577,7 +597,7 @@ extern "C" int e4s_modconv3x3_up_tch_fwd(const float* x, const void* v_hilo_bf16
                 E4S_ERR_ALIGN);
     E4S_REQUIRE((reinterpret_cast<uintptr_t>(y) & 31) == 0, E4S_ERR_ALIGN);          // 256-bit stores
     tch::Params p{x, s, demod, label, noise, noise_w, bias, y, fx0, fx1, fx2, fx3, batch, h, w, cin, cout, ncls, noise_b, act ? 1 : 0,
-                  0, 0, 0, 0, 0, nullptr};
+                  0, 0, 0, 0, 0, 0, nullptr};
     if ((cin % 64) == 0) return tch::launch<32, 64>(v_hilo_bf16, p, (cudaStream_t)stream);
     return tch::launch<32, 32>(v_hilo_bf16, p, (cudaStream_t)stream);
 }

@@ -69,6 +69,7 @@ struct Params {
     const float* shift;
     const float* slope;
     int out_stride;
+    int det;              // 1: ONE warp issues the three split-precision products in a fixed order (bit-reproducible accumulation)
     long long* prof;      // optional [5 roles][4] cycle counters of CTA 0 (e4s_tcr_set_profile); nullptr in production
 };
 
@@ -221,9 +222,10 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
         // every MMA warp commits to the barriers of what it read: both operand planes are read by two of them
         // (x_hi: warps 0 and 2, w_hi: warps 0 and 1) - A stages, accumulators and (hi, lo) weight slot PAIRS (the ring unit:
         // one TMA box, the barriers of the even slot) are released by all three
-        for (int i = 0; i < NSTAGE_A; ++i) mbar_init(smem_u32(&bars[A_FULL + i]), NUM_XFORM), mbar_init(smem_u32(&bars[A_EMPTY + i]), NUM_MMA_WARPS);
-        for (int i = 0; i < NACC; ++i) mbar_init(smem_u32(&bars[ACC_FULL + i]), NUM_MMA_WARPS), mbar_init(smem_u32(&bars[ACC_EMPTY + i]), NUM_EPI);
-        for (int i = 0; i < p.nslot_b; ++i) mbar_init(smem_u32(&bars[B_FULL + i]), 1), mbar_init(smem_u32(&bars[B_EMPTY + i]), NUM_MMA_WARPS);
+        const uint32_t nmma = p.det ? 1u : (uint32_t)NUM_MMA_WARPS;      // issuing warps that commit to each barrier
+        for (int i = 0; i < NSTAGE_A; ++i) mbar_init(smem_u32(&bars[A_FULL + i]), NUM_XFORM), mbar_init(smem_u32(&bars[A_EMPTY + i]), nmma);
+        for (int i = 0; i < NACC; ++i) mbar_init(smem_u32(&bars[ACC_FULL + i]), nmma), mbar_init(smem_u32(&bars[ACC_EMPTY + i]), NUM_EPI);
+        for (int i = 0; i < p.nslot_b; ++i) mbar_init(smem_u32(&bars[B_FULL + i]), 1), mbar_init(smem_u32(&bars[B_EMPTY + i]), nmma);
         for (int i = 0; i < NXS; ++i) mbar_init(smem_u32(&bars[XS_FULL + i]), 1), mbar_init(smem_u32(&bars[XS_EMPTY + i]), NUM_XFORM);
         fence_barrier_init();
     }
@@ -296,18 +298,21 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
         }
         __syncwarp();
     } else if (warp <= NUM_MMA_WARPS) {
+      if (!p.det || warp == 1) {
         // ===================================================================== MMA issuers (one split-precision product each)
-        // role 0: x_hi * w_hi, role 1: x_lo * w_hi, role 2: x_hi * w_lo.  Each warp walks the loops with warp-uniform state
-        // (barrier waits included); only the tcgen05 instructions are predicated on one lane, descriptors live in uniform
-        // registers (shfl-from-lane-0 marks a value as warp-uniform for the compiler).
+        // product 0: x_hi * w_hi, 1: x_lo * w_hi, 2: x_hi * w_lo.  Each warp walks the loops with warp-uniform state (barrier
+        // waits included) and one lane, chosen by elect.sync, issues.  Deterministic mode (p.det): warp 1 alone issues the
+        // three products of every (tap, K step) in this order, the other two warps idle - MMAs of one thread execute in issue
+        // order, so the accumulation order, hence every output bit, is the same in every run (at ~1/3 of the issue rate).
         const int role = warp - 1;
-        const bool lo_w = role == 2;                     // this warp reads the w_lo slot of every (hi, lo) pair
+        constexpr uint32_t A_LO = (uint32_t)A_PLANE >> 4, W_LO = (uint32_t)B_SLOT >> 4;      // descriptor offsets of the x_lo plane / w_lo slot
+        const uint32_t a_role = role == 1 ? A_LO : 0u, w_role = role == 2 ? W_LO : 0u;     // this warp's product (default mode)
         int sa = 0, slot = 0, acc = 0;
         uint32_t pa = 0, pb = 0, pacc0 = 0, pacc1 = 0;
         bool b_ready = false;                            // resident weights: waited for once
         const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
         const uint32_t bars0 = smem_u32(bars);
-        const uint32_t a0 = smem_u32(a_buf) + (role == 1 ? A_PLANE : 0), b0 = smem_u32(b_buf);
+        const uint32_t a0 = smem_u32(a_buf), b0 = smem_u32(b_buf);
         auto desc = [](uint32_t lo) -> uint64_t { return ((uint64_t)DESC_HI << 32) | lo; };
         auto lo_of = [](uint32_t addr) -> uint32_t { return (addr >> 4) | 0x10000u; };
         Walk wk;
@@ -340,12 +345,23 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                             MBAR_WAIT_P(bars0 + 8 * (B_FULL + slot), pb, 3);
                             tc_fence_after();
                         }
-                        const uint32_t bp = lo_of(b0 + (slot + (lo_w ? 1 : 0)) * B_SLOT);
+                        const uint32_t bp = lo_of(b0 + slot * B_SLOT);
                         if (elect_one()) {
+                            if (!p.det) {
 #pragma unroll
-                            for (int k = 0; k < KSTEPS; ++k) umma_bf16(d_tmem, desc(apA + roff + 2 * k), desc(bp + 2 * k), IDESC_N, 1u);
+                                for (int k = 0; k < KSTEPS; ++k) umma_bf16(d_tmem, desc(apA + a_role + roff + 2 * k), desc(bp + w_role + 2 * k), IDESC_N, 1u);
 #pragma unroll
-                            for (int k = 0; k < KSTEPS; ++k) umma_bf16(d_other, desc(apB + roff + 2 * k), desc(bp + 2 * k), IDESC_N, 1u);
+                                for (int k = 0; k < KSTEPS; ++k) umma_bf16(d_other, desc(apB + a_role + roff + 2 * k), desc(bp + w_role + 2 * k), IDESC_N, 1u);
+                            } else {
+#pragma unroll 1
+                                for (int r = 0; r < 3; ++r) {
+                                    const uint32_t ao = r == 1 ? A_LO : 0u, wo2 = r == 2 ? W_LO : 0u;
+#pragma unroll
+                                    for (int k = 0; k < KSTEPS; ++k) umma_bf16(d_tmem, desc(apA + ao + roff + 2 * k), desc(bp + wo2 + 2 * k), IDESC_N, 1u);
+#pragma unroll
+                                    for (int k = 0; k < KSTEPS; ++k) umma_bf16(d_other, desc(apB + ao + roff + 2 * k), desc(bp + wo2 + 2 * k), IDESC_N, 1u);
+                                }
+                            }
                             if (!p.resident) umma_commit(bars0 + 8 * (B_EMPTY + slot));
                         }
                         slot += 2;
@@ -358,8 +374,51 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                     }
                     pa ^= 1;                             // both stages consumed: same stage index, next phase
                 }
+#ifndef E4S_TCR_NO_FAST_ISSUE
+            } else if (!mixed && !p.det) {
+                // ---------------- region-pure tile, fast issue path.  ONE elected thread runs the whole tile: waits, then per chunk
+                // 9 taps x KSTEPS MMAs fully unrolled, operand descriptors = two bases + compile-time offsets.  (The loop below,
+                // walked by all lanes with a barrier check, an elect and a descriptor rebuild per tap, cost ~35 dependent
+                // instructions per tap: the three issuing warps were 85 % busy on the 32->32 layer while the tensor pipe idled,
+                // profiles/r2_stall_attribution_tcr_elect.log.)  State (stage / slot rings) is advanced by every lane afterwards.
+                if (elect_one()) {
+                    const uint32_t a_mine = a0 + (role == 1 ? A_PLANE : 0), b_mine = b0 + (role == 2 ? B_SLOT : 0);
+                    int sa2 = sa, slot2 = slot;
+                    uint32_t pa2 = pa, pb2 = pb;
+#pragma unroll 1
+                    for (int kc = 0; kc < nchunks; ++kc) {
+                        MBAR_WAIT_P(bars0 + 8 * (A_FULL + sa2), pa2, 2);
+                        tc_fence_after();
+                        const uint32_t ap = lo_of(a_mine + sa2 * A_STAGE);
+#pragma unroll
+                        for (int tap = 0; tap < 9; ++tap) {
+                            const uint32_t roff = (uint32_t)((1 + (tap / 3) * TWP + (tap % 3)) * ROWB) >> 4;   // halo pixel hp is operand row hp + 1
+                            if (wait_b) {
+                                MBAR_WAIT_P(bars0 + 8 * (B_FULL + slot2), pb2, 3);
+                                tc_fence_after();
+                            }
+                            const uint32_t bp = lo_of(b_mine + slot2 * B_SLOT);
+#pragma unroll
+                            for (int k = 0; k < KSTEPS; ++k) umma_bf16(d_tmem, desc(ap + roff + 2 * k), desc(bp + 2 * k), IDESC_N, 1u);
+                            if (!p.resident) umma_commit(bars0 + 8 * (B_EMPTY + slot2));
+                            slot2 += 2;
+                            if (slot2 >= p.nslot_b) slot2 = 0, pb2 ^= 1;
+                        }
+                        umma_commit(bars0 + 8 * (A_EMPTY + sa2));
+                        if (++sa2 == NSTAGE_A) sa2 = 0, pa2 ^= 1;
+                    }
+                }
+                __syncwarp();
+                for (int kc = 0; kc < nchunks; ++kc) {               // the same ring arithmetic on every lane
+                    for (int tap = 0; tap < 9; ++tap) {
+                        slot += 2;
+                        if (slot >= p.nslot_b) slot = 0, pb ^= 1;
+                    }
+                    if (++sa == NSTAGE_A) sa = 0, pa ^= 1;
+                }
+#endif
             } else if (!mixed) {
-                // ---------------- region-pure tile: operand staged once per chunk, taps are row shifts
+                // ---------------- region-pure tile, generic loop (deterministic mode): operand staged once per chunk, taps are row shifts
 #pragma unroll 1
                 for (int kc = 0; kc < nchunks; ++kc) {
                     MBAR_WAIT_P(bars0 + 8 * (A_FULL + sa), pa, 2);
@@ -372,10 +431,19 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                             MBAR_WAIT_P(bars0 + 8 * (B_FULL + slot), pb, 3);
                             tc_fence_after();
                         }
-                        const uint32_t bp = lo_of(b0 + (slot + (lo_w ? 1 : 0)) * B_SLOT);
+                        const uint32_t bp = lo_of(b0 + slot * B_SLOT);
                         if (elect_one()) {
+                            if (!p.det) {
 #pragma unroll
-                            for (int k = 0; k < KSTEPS; ++k) umma_bf16(d_tmem, desc(ap + roff + 2 * k), desc(bp + 2 * k), IDESC_N, 1u);
+                                for (int k = 0; k < KSTEPS; ++k) umma_bf16(d_tmem, desc(ap + a_role + roff + 2 * k), desc(bp + w_role + 2 * k), IDESC_N, 1u);
+                            } else {
+#pragma unroll 1
+                                for (int r = 0; r < 3; ++r) {
+                                    const uint32_t ao = r == 1 ? A_LO : 0u, wo2 = r == 2 ? W_LO : 0u;
+#pragma unroll
+                                    for (int k = 0; k < KSTEPS; ++k) umma_bf16(d_tmem, desc(ap + ao + roff + 2 * k), desc(bp + wo2 + 2 * k), IDESC_N, 1u);
+                                }
+                            }
                             if (!p.resident) umma_commit(bars0 + 8 * (B_EMPTY + slot));
                         }
                         slot += 2;
@@ -392,7 +460,7 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
 #pragma unroll 1
                     for (int tap = 0; tap < 9; ++tap) {
                         if (wait_b) MBAR_WAIT_P(bars0 + 8 * (B_FULL + slot), pb, 3);
-                        const uint32_t bp = lo_of(b0 + (slot + (lo_w ? 1 : 0)) * B_SLOT);
+                        const uint32_t bp = lo_of(b0 + slot * B_SLOT);
 #pragma unroll
                         for (int q = 0; q < NPH; ++q) {
                             MBAR_WAIT_P(bars0 + 8 * (A_FULL + sa), pa, 2);
@@ -401,8 +469,17 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                             const uint32_t boff = (uint32_t)(q * NTC * ROWB) >> 4;
                             const uint32_t dq = d_tmem + (uint32_t)(q * NTC);
                             if (elect_one()) {
+                                if (!p.det) {
 #pragma unroll
-                                for (int k = 0; k < KSTEPS; ++k) umma_bf16(dq, desc(ap + 2 * k), desc(bp + boff + 2 * k), IDESC_Q, 1u);
+                                    for (int k = 0; k < KSTEPS; ++k) umma_bf16(dq, desc(ap + a_role + 2 * k), desc(bp + w_role + boff + 2 * k), IDESC_Q, 1u);
+                                } else {
+#pragma unroll 1
+                                    for (int r = 0; r < 3; ++r) {
+                                        const uint32_t ao = r == 1 ? A_LO : 0u, wo2 = r == 2 ? W_LO : 0u;
+#pragma unroll
+                                        for (int k = 0; k < KSTEPS; ++k) umma_bf16(dq, desc(ap + ao + 2 * k), desc(bp + wo2 + boff + 2 * k), IDESC_Q, 1u);
+                                    }
+                                }
                                 umma_commit(bars0 + 8 * (A_EMPTY + sa));
                             }
                             if (++sa == NSTAGE_A) sa = 0, pa ^= 1;
@@ -424,6 +501,7 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
             b_ready = true;
             __syncwarp();
         }
+      }
     } else if (warp < W_EPI0) {
         // ===================================================================== activation transform (A producers), 256 threads
         const int t = threadIdx.x - 32 * W_XFORM0;       // 0..255
@@ -707,6 +785,20 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                             const int co = j * 32 + 4 * g;
                             const float4 d = dmr[g & 1], bv = bvr[g & 1];
                             if (g + 2 < 8) dmr[g & 1] = ld_dm(g + 2), bvr[g & 1] = ld_bv(g + 2);
+#ifdef E4S_TCR_SCALAR_EPI      // A/B switch of the diagnostic twin builds: the scalar arithmetic of round 1
+                            float4 o;
+                            {
+                                const float zq = p.act == 1 ? nz[q] : nz[q];
+                                o.x = __uint_as_float(r[4 * g + 0]) * d.x + zq + bv.x;
+                                o.y = __uint_as_float(r[4 * g + 1]) * d.y + zq + bv.y;
+                                o.z = __uint_as_float(r[4 * g + 2]) * d.z + zq + bv.z;
+                                o.w = __uint_as_float(r[4 * g + 3]) * d.w + zq + bv.w;
+                                if (p.act == 1) {
+                                    o.x = lrelu_scaled(o.x, 0.2f, k2), o.y = lrelu_scaled(o.y, 0.2f, k2);
+                                    o.z = lrelu_scaled(o.z, 0.2f, k2), o.w = lrelu_scaled(o.w, 0.2f, k2);
+                                }
+                            }
+#else
                             uint64_t dd[2] = {pk2(d.x, d.y), pk2(d.z, d.w)}, zz[2] = {pk2(bv.x, bv.y), pk2(bv.z, bv.w)};
                             const uint64_t rr[2] = {pk2u(r[4 * g + 0], r[4 * g + 1]), pk2u(r[4 * g + 2], r[4 * g + 3])};
                             float o4[4];
@@ -723,6 +815,7 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                                 }
                             }
                             float4 o = make_float4(o4[0], o4[1], o4[2], o4[3]);
+#endif
                             if (p.act == 2) {
                                 const float4 sl = __ldg(reinterpret_cast<const float4*>(p.slope + n0 + co));
                                 o.x = o.x > 0.f ? o.x : o.x * sl.x, o.y = o.y > 0.f ? o.y : o.y * sl.y;
@@ -797,6 +890,7 @@ static long long* g_prof = nullptr;
 template <int NTC, int KC, int NPH, bool XS = false, bool UP2 = false>
 static int launch(const void* w_hilo, Params p, cudaStream_t st) {
     p.prof = g_prof;
+    p.det = e4s_get_deterministic();
     constexpr int N = NTC * NPH, ROWB = KC * 2;
     constexpr int A_BYTES = (((NSTAGE_A * 2 * A_ROWS * ROWB) + 1023) & ~1023) + (XS ? NXS * XS_STAGE : 0);
     constexpr int B_SLOT = N * ROWB;

@@ -211,13 +211,23 @@ def up_form(prep: "PreparedConv") -> str:
 
 # ================================================================================== autograd
 class LinearFn(Function):
-    """y = leaky_relu(x @ w^T + bias, slope) on the library's small-GEMM kernel (csrc/linear.cu); w, bias are frozen prepared
-    tensors (scale / lr_mul folded in), grouped or shared (kernels.linear).  Differentiable wrt x."""
+    """y = leaky_relu(x @ w^T + bias, slope) on the library's small-GEMM kernels (csrc/linear.cu); w, bias are frozen prepared
+    tensors (scale / lr_mul folded in), grouped [G, N, K] or shared [N, K].  With at most 16 rows and the transposed copy
+    w_kn ([G,] K, N) at hand, forward and input gradient run in the weight-streaming form (the LocalMLPs stream 163 MB of
+    weights for a handful of rows).  Differentiable wrt x."""
 
     @staticmethod
-    def forward(ctx, x, w, bias, slope):
-        y = K.linear(x, w, bias, slope)
-        ctx.slope = float(slope)
+    def forward(ctx, x, w, bias, slope, w_kn=None):
+        skinny = w_kn is not None and x.shape[-2] <= 16
+        if skinny:
+            x3 = x if x.ndim == 3 else x.unsqueeze(0)
+            wk = w_kn if w_kn.ndim == 3 else w_kn.unsqueeze(0)
+            b2 = None if bias is None else (bias if bias.ndim == 2 else bias.unsqueeze(0))
+            y = K.linear_skinny(x3, wk, b2, slope)
+            y = y if x.ndim == 3 else y[0]
+        else:
+            y = K.linear(x, w, bias, slope)
+        ctx.slope, ctx.skinny = float(slope), skinny
         ctx.save_for_backward(w, y if slope != 1.0 else None)
         return y
 
@@ -226,7 +236,15 @@ class LinearFn(Function):
         w, y = ctx.saved_tensors
         if ctx.slope != 1.0:
             gy = gy * torch.where(y > 0, 1.0, ctx.slope)
-        return K.linear(gy.contiguous(), w, None, 1.0, w_is_kn=True), None, None, None
+        gy = gy.contiguous()
+        if ctx.skinny:                                   # gx[m, k] = sum_n gy[m, n] w[n, k]: w in its own [N, K] layout is the stream
+            g3 = gy if gy.ndim == 3 else gy.unsqueeze(0)
+            w3 = w if w.ndim == 3 else w.unsqueeze(0)
+            gx = K.linear_skinny(g3, w3, None, 1.0)
+            gx = gx if gy.ndim == 3 else gx[0]
+        else:
+            gx = K.linear(gy, w, None, 1.0, w_is_kn=True)
+        return gx, None, None, None, None
 
 
 class StyledConvFn(Function):

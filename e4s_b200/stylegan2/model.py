@@ -111,8 +111,8 @@ class EqualLinear(nn.Module):
         key = (self.weight.data_ptr(), self.weight._version, None if self.bias is None else (self.bias.data_ptr(), self.bias._version))
         if getattr(self, "_prep_key", None) != key:
             with torch.no_grad():
-                self._prep = ((self.weight * self.scale).float().contiguous(),
-                              None if self.bias is None else (self.bias * self.lr_mul).float().contiguous())
+                w = (self.weight * self.scale).float().contiguous()
+                self._prep = (w, None if self.bias is None else (self.bias * self.lr_mul).float().contiguous(), w.t().contiguous())
             self._prep_key = key
         return self._prep
 
@@ -121,9 +121,9 @@ class EqualLinear(nn.Module):
         if (input.is_cuda and not self.activation and not trainable and input.dtype == torch.float32
                 and self.weight.shape[0] % 4 == 0 and self.weight.shape[1] % 4 == 0):
             # the style modulations of the synthesis path (model.py:276): own small-GEMM kernel, no library GEMM
-            w, b = self._frozen()
+            w, b, w_kn = self._frozen()
             lead = input.shape[:-1]
-            y = MC.LinearFn.apply(input.reshape(-1, input.shape[-1]).contiguous(), w, b, 1.0)
+            y = MC.LinearFn.apply(input.reshape(-1, input.shape[-1]).contiguous(), w, b, 1.0, w_kn)
             return y.reshape(*lead, w.shape[0])
         w = self.weight * self.scale
         if self.activation:

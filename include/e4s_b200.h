@@ -109,6 +109,8 @@ int e4s_region_mean_f32(const float* feats, const uint8_t* label, float* out, in
  * s: [rows, cin], wsq: [cout, cin], demod: [rows, cout]. */
 int e4s_demod_f32(const float* s, const float* wsq, float* demod, int rows, int cin, int cout, float eps,
                   void* stream);
+/* The same on the tiled small-GEMM kernel (csrc/linear.cu; cin % 4 == 0, cout % 4 == 0): what the generator uses. */
+int e4s_demod_gemm_f32(const float* s, const float* wsq, float* demod, int rows, int cin, int cout, float eps, void* stream);
 
 /* Region-selected modulated 3x3 convolution with fused noise + bias + leaky-ReLU epilogue:
  * one call = one StyledConv.forward (model.py:382-406) for every region at once.
@@ -148,6 +150,12 @@ int e4s_modconv3x3_up_tch_fwd(const float* x, const void* v_hilo_bf16, const flo
                               const uint8_t* label, const float* noise, const float* noise_w, const float* bias,
                               float* y, float fx0, float fx1, float fx2, float fx3, int batch, int h, int w, int cin,
                               int cout, int ncls, int noise_b, int act, void* stream);
+/* Bit reproducibility of the tensor-core convolutions (forward kernels).  0 (default): three warps issue the three
+ * split-precision products concurrently, accumulation order - hence the last bits - varies between runs (~2e-6 relative).
+ * 1: one warp issues them in a fixed order; identical bits in every run, lower MMA issue rate.  The initial value comes from
+ * the environment variable E4S_B200_DETERMINISTIC.  e4s_get_deterministic returns the current setting (0 / 1). */
+int e4s_set_deterministic(int on);
+int e4s_get_deterministic(void);
 /* Diagnostic (no reference counterpart): per-role stall attribution of CTA 0 of every following gen-4 launch.
  * device_counters: [5 roles][4] int64 in device memory (role time, cycles in its barrier waits); NULL = off. */
 int e4s_tcr_set_profile(long long* device_counters);
@@ -222,6 +230,13 @@ int e4s_torgb_bwd_f32(const float* g, const float* x, const float* wrgb, const f
 int e4s_linear_f32(const float* x, const float* w, const float* bias, float* y, int groups, int m, int n, int k,
                    long long x_gstride, long long w_gstride, long long bias_gstride, long long y_gstride, int w_is_kn,
                    float act_slope, void* stream);
+
+/* The same product for at most 16 rows, organised as a weight stream (the LocalMLPs: 163 MB of weights for a handful of rows):
+ * y[g, m, j] = act( sum_i x[g, m, i] * w_ij[g, i, j] + bias[g, j] ), w_ij: [G, I, J] with J contiguous, j % 4 == 0, m <= 16.
+ * For I >= 2048 the reduction is cut into slabs of 512 rows whose partial sums meet by red.global.add (y is zeroed by a memset
+ * on `stream`; the last bits of y may differ between runs); bias must then be NULL and act_slope 1. */
+int e4s_linear_skinny_f32(const float* x, const float* w_ij, const float* bias, float* y, int groups, int m, int i, int j,
+                          float act_slope, void* stream);
 
 /* ---- loss networks of the inversion loop (scripts/optimization.py:88-122) -------------------------------------------
  * Average-pooling pyramid: y2 = 2x2 block means, y4 = 4x4 block means of planar x [planes, H, W] (H % 4 == 0, W % 8 == 0):

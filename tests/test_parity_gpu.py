@@ -364,6 +364,23 @@ def test_linear_kernel(g, m, n, k, shared_x, shared_w):
     assert_close(gx, torch.matmul(gy.double(), w.double()).float(), 1e-5, "linear NN (input gradient)")
 
 
+@pytest.mark.parametrize("g,m,i,j", [(12, 16, 1280, 512), (12, 1, 512, 6656), (12, 3, 6656, 512), (1, 12, 512, 64), (2, 5, 100, 36)])
+def test_linear_skinny_kernel(g, m, i, j):
+    """Weight-streaming form for at most 16 rows (csrc/linear.cu): single slab with bias + activation, and the multi-slab
+    reduction (I >= 2048: partial sums by red.global.add)."""
+    from e4s_b200 import kernels as K
+    gen = torch.Generator().manual_seed(g + m + i + j)
+    x = torch.randn(g, m, i, generator=gen)
+    w = torch.randn(g, i, j, generator=gen) / i ** 0.5
+    multi = i >= 2048
+    bias = None if multi else torch.randn(g, j, generator=gen)
+    ref = torch.matmul(x.double(), w.double())
+    if bias is not None:
+        ref = torch.nn.functional.leaky_relu(ref + bias.double()[:, None, :], 0.01)
+    out = K.linear_skinny(cu(x), cu(w), None if bias is None else cu(bias), 1.0 if multi else 0.01)
+    assert_close(out, ref.float(), 1e-5, f"skinny linear G={g} M={m} I={i} J={j}")
+
+
 def test_local_mlps_match_oracle_and_autograd():
     """Net3.cal_style_codes (12 LocalMLPs, networks.py:135-158) on the own GEMM kernel: values and the gradient wrt the texture
     vectors (what the inversion loop optimises) against the oracle's autograd."""
@@ -552,6 +569,53 @@ def test_tch_kernel_asymmetric_fir_and_no_epilogue_inputs():
     assert_close(out, ref, 1e-4, "tch, asymmetric FIR, bare conv")
 
 
+@pytest.fixture
+def deterministic():
+    import e4s_b200
+    e4s_b200.set_deterministic(True)
+    assert e4s_b200.is_deterministic()
+    yield
+    e4s_b200.set_deterministic(False)
+
+
+@pytest.mark.parametrize("b,cin,cout,hw,up,ncls,kind", [
+    (2, 64, 64, 40, False, 1, "blobs"),       # small K, resident weights, several items per CTA
+    (1, 128, 256, 28, False, 12, "iid"),      # row-class staging on every tile
+    (2, 64, 64, 24, True, 2, "iid"),          # four parities along N, two-region tiles (both accumulator buffers)
+    (2, 512, 256, 24, True, 12, "blobs"),     # parity work items
+    (1, 256, 128, 40, True, 5, "blobs"),      # H-form kernel (auto choice for this shape): one- and two-region passes
+])
+def test_deterministic_mode_is_bit_reproducible(deterministic, b, cin, cout, hw, up, ncls, kind):
+    """e4s_b200.set_deterministic(True): one warp issues the three split-precision products in a fixed order, so two runs give
+    identical bits (the default, three concurrently issuing warps, is reproducible to fp32 rounding only); same values as
+    the default mode and the fp32 SIMT kernel within the usual tolerance."""
+    import e4s_b200
+    from e4s_b200.stylegan2.modconv import up_form
+    K, prep, x, args = _tc_case(b, cin, cout, hw, up, ncls, kind, seed=cin + cout + hw)
+    s, dm, label, noise, nw, bias, up_, act = args
+
+    def run():
+        if up and up_form(prep) == "h":
+            return K.modconv3x3_up_tch_fwd(x, prep.v_hilo, prep.fx, s, dm, label, noise, nw, bias, act)
+        return K.modconv3x3_tcr_fwd(x, prep.w_hilo, *args)
+
+    outs = [run() for _ in range(3)]
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2]), "deterministic mode is not bit-reproducible"
+    assert_close(outs[0], K.modconv3x3_fwd(x, prep.wt, *args), 1e-4, "deterministic mode vs simt")
+    e4s_b200.set_deterministic(False)
+    assert_close(run(), outs[0], 2e-5, "default mode vs deterministic mode")
+
+
+def test_deterministic_generator_is_bit_reproducible(deterministic):
+    G, _ = _generator(64, 5)
+    codes, mask, _, noise = O.synthetic_inputs(2, 5, 64, 32, seed=69)
+    with torch.no_grad():
+        a, _, _ = G([cu(codes)], None, cu(mask), input_is_latent=True, noise=[cu(n) for n in noise])
+        b, _, _ = G([cu(codes)], None, cu(mask), input_is_latent=True, noise=[cu(n) for n in noise])
+    assert torch.equal(a, b)
+
+
 @pytest.mark.parametrize("b,cin,cout,hw,up,ncls,kind", PRODUCTION_CASES)
 def test_tcr_kernel_production_shapes(b, cin, cout, hw, up, ncls, kind):
     K, prep, x, args = _tc_case(b, cin, cout, hw, up, ncls, kind, seed=cin + cout + hw)
@@ -620,3 +684,62 @@ def test_generator_1024_tensor_core_path_matches_exact_fp32_path(monkeypatch):
     # accumulation order of the three MMA-issuing warps is not fixed), so the check sits at 3e-4 - a third of the path's bar
     e = assert_close(outs["auto"], outs["simt"], 3e-4, "1024x1024 generator, tensor-core vs exact path")
     print(f"1024 generator tc-vs-exact rel err {e:.2e}")
+
+
+def test_generator_1024_matches_cpu_oracle_alone_and_inside_a_batch():
+    """The benched configuration against the ORACLE (not against another kernel of this library): one 1024x1024 face, 12 regions
+    of a blob mask, K = 13, default kernels, vs O.generator_forward on the host (~7 s); then the same face as sample 9 of a
+    16-face batch with other codes and masks around it - batching must not change a face.  REL_TOL, both norms."""
+    g, st = _generator(1024, 13)
+    codes, mask, _, noise = O.synthetic_inputs(1, 12, 1024, 512, seed=21)
+    with torch.no_grad():
+        ref, _ = O.generator_forward(st, codes, mask, noise, 1024, 13)
+        img, _, _ = g([cu(codes)], None, cu(mask), input_is_latent=True, noise=[cu(n) for n in noise])
+    e = assert_close(img, ref, REL_TOL, "1024x1024 generator (default kernels) vs CPU oracle")
+    print(f"1024 generator vs oracle: max-rel {e:.2e}")
+    bc, bm, _, _ = O.synthetic_inputs(16, 12, 1024, 512, seed=33)
+    bc[9], bm[9] = codes[0], mask[0]
+    with torch.no_grad():
+        batch, _, _ = g([cu(bc)], None, cu(bm), input_is_latent=True, noise=[cu(n) for n in noise])
+    assert_close(batch[9:10], ref, REL_TOL, "face 9 of a 16-face batch vs CPU oracle")
+    assert_close(batch[9:10], img, 5e-5, "face 9 of a 16-face batch vs the same face alone")
+
+
+def test_dcodes_gradient_default_kernels_256():
+    """d loss / d codes through the 256x256 generator on the DEFAULT (tensor-core) forward and backward kernels against the
+    oracle's autograd.  Stated tolerance: rel-L2 <= 1e-2 and cosine >= 0.9999 over the whole gradient (observed 5.8e-3 /
+    0.999983).  The gradient of a 15-layer leaky-ReLU network is not a smooth function of its rounding: the few pixels whose
+    pre-activation sits within 1e-5 of zero take the other branch (slope 1 vs 0.2) under the split-bf16 forward, and each flip
+    moves the gradient by O(1e-3) of its norm; on the exact-fp32 kernels the same quantity holds 1e-3 in the max norm
+    (tests/test_backward_gpu.py)."""
+    g, st = _generator(256, 13)
+    codes, mask, _, noise = O.synthetic_inputs(1, 12, 256, 256, seed=5)
+    w = torch.randn(1, 3, 256, 256, generator=torch.Generator().manual_seed(4))
+    c_ref = codes.clone().requires_grad_(True)
+    ref, _ = O.generator_forward(st, c_ref, mask, noise, 256, 13)
+    (ref * w).sum().backward()
+    c = cu(codes).requires_grad_(True)
+    img, _, _ = g([c], None, cu(mask), input_is_latent=True, noise=[cu(n) for n in noise])
+    (img * cu(w)).sum().backward()
+    a, b = c.grad.double().cpu().flatten(), c_ref.grad.double().flatten()
+    rel_l2 = float((a - b).norm() / b.norm())
+    cos = float(torch.dot(a, b) / (a.norm() * b.norm()))
+    print(f"dcodes @256, default kernels: rel-L2 {rel_l2:.2e}, cosine {cos:.7f}")
+    assert rel_l2 < 1e-2 and cos > 0.9999, (rel_l2, cos)
+
+
+def test_demod_gemm_form_equals_reference_formula():
+    """e4s_demod_gemm_f32 (tiled small-GEMM kernel, x squared on load, rsqrt epilogue) == rsqrt(s^2 @ wsq^T + 1e-8) in fp64
+    (model.py:279-281 in the shared-weight form) == the warp-per-output kernel e4s_demod_f32."""
+    from e4s_b200 import kernels as K, _lib
+    g = torch.Generator().manual_seed(31)
+    for rows, cin, cout in ((192, 512, 512), (1, 32, 32), (37, 64, 36)):
+        s = 1.0 + 0.3 * torch.randn(rows, cin, generator=g)
+        wsq = torch.rand(cout, cin, generator=g) / cin
+        ref = torch.rsqrt(s.double().pow(2) @ wsq.double().t() + 1e-8).float()
+        sd, wd = cu(s), cu(wsq)
+        out = K.demod(sd, wd)
+        assert_close(out, ref, 1e-5, f"demod gemm form {rows}x{cin}x{cout}")
+        old = torch.empty(rows, cout, device=DEV)
+        _lib.check(_lib.load().e4s_demod_f32(_lib.ptr(sd), _lib.ptr(wd), _lib.ptr(old), rows, cin, cout, 1e-8, _lib.stream_ptr()), "e4s_demod_f32")
+        assert_close(old, ref, 1e-5, "demod warp form")

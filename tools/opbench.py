@@ -43,7 +43,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "opbench.json"))
-    ap.add_argument("--conv", default="tcr", help="comma list of simt,tcr,tch")
+    ap.add_argument("--conv", default="tcr", help="comma list of auto,simt,tcr,tch")
     ap.add_argument("--layers", default="all")
     ap.add_argument("--prof", action="store_true", help="gen-4 kernel: per-role stall attribution of CTA 0 (e4s_tcr_set_profile)")
     ap.add_argument("--only-conv", action="store_true", help="skip the HBM-bound kernels")
@@ -135,7 +135,15 @@ def conv_rows(args, B, fir, flush, row, res):
         dm = K.demod(s, prep.wsq)
         flops = 2.0 * 9 * cin * cout * B * r * r
         for mode in args.conv.split(","):
-            if mode == "tcr":
+            if mode == "auto":                      # the kernel the generator uses for this layer (modconv.up_form)
+                from e4s_b200.stylegan2.modconv import up_form
+                if prep.w_hilo is None:
+                    continue
+                if up and up_form(prep) == "h":
+                    fn = lambda: K.modconv3x3_up_tch_fwd(xpm, prep.v_hilo, prep.fx, s, dm, label, noise, nw, bias, True)
+                else:
+                    fn = lambda: K.modconv3x3_tcr_fwd(xpm, prep.w_hilo, s, dm, label, noise, nw, bias, bool(up), True)
+            elif mode == "tcr":
                 if prep.w_hilo is None:
                     continue
                 fn = lambda: K.modconv3x3_tcr_fwd(xpm, prep.w_hilo, s, dm, label, noise, nw, bias, bool(up), True)
