@@ -34,7 +34,7 @@ SIGNATURES = {
     "e4s_box_morph_f32": [P, P, c_int, c_int, c_int, c_int, c_int, c_float, P],
     "e4s_region_mean_f32": [P, P, P, P, c_int, c_int, c_int, c_int, c_int, P],
     "e4s_demod_f32": [P, P, P, c_int, c_int, c_int, c_float, P],
-    "e4s_demod_gemm_f32": [P, P, P, c_int, c_int, c_int, c_float, P],
+    "e4s_demod_gemm_f32": [P, P, P, c_int, c_int, c_int, c_float, P, P],
     "e4s_modconv3x3_fwd_f32": [P] * 9 + [c_int] * 9 + [P],
     "e4s_modconv3x3_tcr_fwd": [P] * 9 + [c_int] * 9 + [P],
     "e4s_modconv3x3_up_tch_fwd": [P] * 9 + [c_float] * 4 + [c_int] * 8 + [P],
@@ -50,14 +50,13 @@ SIGNATURES = {
     "e4s_class_reduce_f32": [P] * 7 + [c_int] * 7 + [P],
     "e4s_torgb_bwd_f32": [P] * 7 + [c_int] * 5 + [P],
     "e4s_torgb_fwd_f32": [P] * 8 + [c_int] * 5 + [P],
-    "e4s_linear_f32": [P, P, P, P, c_int, c_int, c_int, c_int, c_int64, c_int64, c_int64, c_int64, c_int, c_float, P],
-    "e4s_linear_skinny_f32": [P, P, P, P, c_int, c_int, c_int, c_int, c_float, P],
+    "e4s_linear_f32": [P, P, P, P, c_int, c_int, c_int, c_int, c_int64, c_int64, c_int64, c_int64, c_int, c_float, P, P],
     "e4s_avgpool_pyramid_f32": [P, P, P, c_int64, c_int, c_int, P],
     "e4s_avgpool_pyramid_bwd_f32": [P, P, P, P, c_int64, c_int, c_int, P],
     "e4s_planar_to_pixel_f32": [P, P, c_int, c_int, c_int, c_int, P],
     "e4s_pixel_to_planar_f32": [P, P, c_int, c_int, c_int, c_int, P],
 }
-PLAIN = {"e4s_get_deterministic": ([], c_int), "e4s_version": ([], c_int), "e4s_build_arch": ([], c_char_p), "e4s_device_ok": ([], c_int)}
+PLAIN = {"e4s_linear_workspace_floats": ([c_int, c_int, c_int, c_int], c_int64), "e4s_get_deterministic": ([], c_int), "e4s_version": ([], c_int), "e4s_build_arch": ([], c_char_p), "e4s_device_ok": ([], c_int)}
 
 _lib = None
 

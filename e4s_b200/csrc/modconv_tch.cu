@@ -193,9 +193,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) modconv3x3_up_tch_kernel(const
         uint32_t ph = 0;
         Walk wk;
         wk.init(p, blockIdx.x, gridDim.x);
-        for (int it = blockIdx.x; it < p.items; it += gridDim.x, wk.advance(p)) {
+        Walk wk2 = wk;                                     // two items ahead: pulls the (streaming) noise rows into L2 for the epilogue
+        wk2.advance(p), wk2.advance(p);
+        for (int it = blockIdx.x; it < p.items; it += gridDim.x, wk.advance(p), wk2.advance(p)) {
             const Item item = wk.cur;
             const int npass = (__popc(tile_classes(p, item, lane)) + 1) >> 1;
+            if (p.noise && it + 2 * (int)gridDim.x < p.items && lane < 2 * TH) {
+                const Item f = wk2.cur;
+                const int oy = 2 * f.ty * TH + lane;
+                if (oy < 2 * p.h)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p.noise + ((int64_t)(p.noise_b == 1 ? 0 : f.b) * 2 * p.h + oy) * 2 * p.w + 2 * f.tx * TW));
+            }
             if (elect_one()) {
                 for (int ps = 0; ps < npass; ++ps)
                     for (int kc = 0; kc < nchunks; ++kc)

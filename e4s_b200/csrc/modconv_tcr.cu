@@ -269,12 +269,26 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
             };
             Walk wk;
             wk.init(p, blockIdx.x, gridDim.x);
+            // The noise map is a streaming tensor: the epilogue fetches its value one work item ahead, which on the HBM-bound
+            // top layers is less than a DRAM round trip under load (the epilogue warps stalled on it: ncu source view of round
+            // 2).  This otherwise idle thread pulls the noise rows of the tile TWO items ahead into L2.
+            Walk wk2 = wk;
+            wk2.advance(p), wk2.advance(p);
+            constexpr int OM = (NPH == 4 || UP2) ? 2 : 1;
             if (XS && blockIdx.x < p.items) issue_x(wk.cur, 0);
             for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
                 const bool load_w = !(p.resident && loaded_resident);
                 if (!XS && !load_w) break;
                 const Item item = wk.cur;
                 wk.advance(p);
+                if (p.noise && it + 2 * (int)gridDim.x < p.items) {
+                    const Item f = wk2.cur;
+                    const int oh2 = p.h * OM, ow2 = p.w * OM;
+                    const float* nrow = p.noise + ((int64_t)(p.noise_b == 1 ? 0 : f.b) * oh2 + f.ty * TH * OM) * ow2 + f.tx * TW * OM;
+                    for (int r = 0; r < TH * OM && f.ty * TH * OM + r < oh2; ++r)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(nrow + (int64_t)r * ow2));
+                }
+                wk2.advance(p);
                 for (int kc = 0; kc < nchunks; ++kc) {
                     if (XS) {
                         if (kc + 1 < nchunks) issue_x(item, kc + 1);

@@ -278,10 +278,19 @@ def demod(s: Tensor, wsq: Tensor, eps: float = 1e-8) -> Tensor:
     rows, cin = s2.shape
     cout = wsq.shape[0]
     out = torch.empty((rows, cout), device=s.device, dtype=torch.float32)
-    entry = "e4s_demod_gemm_f32" if (cin % 4 == 0 and cout % 4 == 0) else "e4s_demod_f32"      # tiled GEMM form / warp-per-output form
     with torch.cuda.device(s.device):
-        _call(entry, getattr(_lib.load(), entry), ptr(s2), ptr(wsq), ptr(out), rows, cin, cout, eps, stream_ptr())
+        if cin % 4 == 0 and cout % 4 == 0:             # tiled GEMM form (csrc/linear.cu)
+            ws = _workspace(1, rows, cout, cin, s.device)
+            _call("e4s_demod_gemm_f32", _lib.load().e4s_demod_gemm_f32, ptr(s2), ptr(wsq), ptr(out), rows, cin, cout, eps, ptr(ws), stream_ptr())
+        else:                                           # warp-per-output form
+            _call("e4s_demod_f32", _lib.load().e4s_demod_f32, ptr(s2), ptr(wsq), ptr(out), rows, cin, cout, eps, stream_ptr())
     return out.reshape(*s.shape[:-1], cout)
+
+
+def _workspace(groups: int, m: int, n: int, k: int, device) -> Optional[Tensor]:
+    """K-split scratch of the small-GEMM kernels (None when the shape needs none)."""
+    need = int(_lib.load().e4s_linear_workspace_floats(groups, m, n, k))
+    return torch.empty(need, device=device, dtype=torch.float32) if need else None
 
 
 def modconv3x3_fwd(x_pm: Tensor, wt: Tensor, s: Tensor, dm: Optional[Tensor], label: Optional[Tensor],
@@ -493,23 +502,8 @@ def linear(x: Tensor, w: Tensor, bias: Optional[Tensor] = None, act_slope: float
     grouped = x.ndim == 3 or w.ndim == 3
     y = torch.empty((groups, m, n) if grouped else (m, n), device=x.device, dtype=torch.float32)
     with torch.cuda.device(x.device):
+        ws = _workspace(groups, m, n, k, x.device)
         _call("e4s_linear_f32", _lib.load().e4s_linear_f32, ptr(x), ptr(w), ptr(bias), ptr(y), groups, m, n, k,
               m * k if x.ndim == 3 else 0, n * k if w.ndim == 3 else 0, (n if (bias is not None and bias.ndim == 2) else 0), m * n,
-              int(w_is_kn), float(act_slope), stream_ptr(), work=2.0 * groups * m * n * k)
-    return y
-
-
-def linear_skinny(x: Tensor, w_ij: Tensor, bias: Optional[Tensor] = None, act_slope: float = 1.0) -> Tensor:
-    """x [G, M, I] (M <= 16), w_ij [G, I, J] (J contiguous), bias [G, J] -> [G, M, J]: weight-streaming form (csrc/linear.cu)."""
-    x, w_ij = _f32c(x, "input"), _f32c(w_ij, "weight")
-    _lib.ensure_device(x)
-    g, m, i = x.shape
-    j = w_ij.shape[2]
-    assert tuple(w_ij.shape[:2]) == (g, i) and m <= 16
-    if bias is not None:
-        bias = _f32c(bias, "bias")
-    y = torch.empty((g, m, j), device=x.device, dtype=torch.float32)
-    with torch.cuda.device(x.device):
-        _call("e4s_linear_skinny_f32", _lib.load().e4s_linear_skinny_f32, ptr(x), ptr(w_ij), ptr(bias), ptr(y), g, m, i, j, float(act_slope),
-              stream_ptr(), work=4.0 * w_ij.numel())
+              int(w_is_kn), float(act_slope), ptr(ws), stream_ptr(), work=2.0 * groups * m * n * k)
     return y

@@ -68,8 +68,7 @@ class Net3(nn.Module):
                 b0 = torch.stack([l.bias * l.lr_mul for l in l0]).float().contiguous()     # [ncls, 512]
                 w2 = torch.stack([l.weight * l.scale for l in l2]).float().contiguous()    # [ncls, K*512, 512]
                 b2 = torch.stack([l.bias * l.lr_mul for l in l2]).float().contiguous()
-                w0t, w2t = w0.transpose(1, 2).contiguous(), w2.transpose(1, 2).contiguous()      # [ncls, K, N]: the forward's weight stream
-            self._mlp_cache = (key, w0, b0, w2, b2, w0t, w2t)
+            self._mlp_cache = (key, w0, b0, w2, b2)
         return self._mlp_cache[1:]
 
     def _region_codes(self, style_vectors):
@@ -79,13 +78,13 @@ class Net3(nn.Module):
         trainable = torch.is_grad_enabled() and any(p.requires_grad for p in self.MLPs.parameters())
         if trainable:   # keep the parameter graph (training is outside the hot path)
             return torch.stack([self.MLPs[i](style_vectors[:, i, :]) for i in range(ncls)], dim=1)
-        w0, b0, w2, b2, w0t, w2t = self._stacked_mlps()
+        w0, b0, w2, b2 = self._stacked_mlps()
         if not style_vectors.is_cuda:
             raise RuntimeError("input must be a CUDA tensor")
         from .stylegan2.modconv import LinearFn
         x = style_vectors.float().transpose(0, 1).contiguous()              # [ncls, B, 1280]
-        h = LinearFn.apply(x, w0, b0, 0.01, w0t)                            # [ncls, B, 512]   EqualLinear + LeakyReLU(0.01)
-        o = LinearFn.apply(h, w2, b2, 1.0, w2t)                             # [ncls, B, K*512]
+        h = LinearFn.apply(x, w0, b0, 0.01)                           # [ncls, B, 512]   EqualLinear + LeakyReLU(0.01)
+        o = LinearFn.apply(h, w2, b2, 1.0)                            # [ncls, B, K*512]
         return o.transpose(0, 1).reshape(bs, ncls, -1, 512)
 
     def _add_latent_avg(self, codes):

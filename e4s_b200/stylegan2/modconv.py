@@ -11,10 +11,12 @@ from __future__ import annotations
 import math
 import os
 import warnings
+import weakref
 from typing import Dict, Optional, Tuple
 
 import torch
 from torch.autograd import Function
+from torch.autograd.function import once_differentiable
 
 from .. import kernels as K
 
@@ -29,7 +31,9 @@ class LabelPyramid:
     every level is resampled from the ORIGINAL mask, like the reference does, never from another level.
     """
 
-    _validated: Dict[Tuple, bool] = {}
+    # one-hot validation is remembered per mask TENSOR OBJECT (weak reference) and version: an address-keyed cache could be hit
+    # by a different, freshly allocated mask that recycles a freed tensor's address (round-1 review)
+    _validated = weakref.WeakKeyDictionary()
 
     def __init__(self, label: Tensor, ncls: int):
         assert label.dtype == torch.uint8 and label.ndim == 3
@@ -46,15 +50,12 @@ class LabelPyramid:
         if not mask.is_cuda:
             raise RuntimeError("mask must be a CUDA tensor")
         label, flag = K.onehot_to_label(mask)
-        key = (mask.data_ptr(), mask._version, tuple(mask.shape), str(mask.device))
-        if os.environ.get("E4S_B200_CHECK_MASK", "1") != "0" and key not in cls._validated:
-            if int(flag.item()) != 0:   # one host sync per distinct mask tensor
+        if os.environ.get("E4S_B200_CHECK_MASK", "1") != "0" and cls._validated.get(mask) != mask._version:
+            if int(flag.item()) != 0:   # one host sync per distinct mask tensor (and version)
                 raise RuntimeError(
                     "e4s_b200: the region mask is not one-hot (exactly one 1.0 per pixel). The region-selected "
                     "kernels implement the reference's mask-sum (model.py:395-398) for one-hot masks only.")
-            if len(cls._validated) > 64:
-                cls._validated.clear()
-            cls._validated[key] = True
+            cls._validated[mask] = mask._version
         return cls(label, mask.shape[1])
 
     def at(self, h: int, w: int) -> Tensor:
@@ -136,6 +137,12 @@ class PreparedConv:
         self.v_hilo = None  # up-sampling layers: bf16 [2, 6, 3, Cout, Cin] H-form operand planes (vertical blur half folded in)
         self.fx = None      # ... and the flipped horizontal FIR taps for its epilogue
 
+    def invalidate(self) -> None:
+        """Forget the prepared tensors.  The cache key is (address, autograd version): in-place writes through ``.data``
+        (``param.data.copy_()``, EMA ``accumulate`` loops) bump no version - call this (or ``e4s_b200.invalidate_prepared(model)``)
+        after them.  ``load_state_dict`` and ordinary in-place ops are picked up automatically."""
+        self.key = None
+
     def get(self, weight: Tensor, upsample: bool, blur: Optional[Tensor]):
         key = (weight.data_ptr(), weight._version, str(weight.device),
                None if blur is None else (blur.data_ptr(), blur._version))
@@ -176,9 +183,13 @@ class PreparedConv:
 _warned_weight_grad = False
 
 
-def warn_frozen(weight: Tensor):
+def warn_frozen(*params: Optional[Tensor]):
+    """The fused kernels produce gradients for the activations, styles and noise maps only.  Any PARAMETER of the layer that
+    requires grad under grad mode (conv weight, NoiseInjection.weight, FusedLeakyReLU bias, ToRGB bias) gets none: say so once."""
     global _warned_weight_grad
-    if weight.requires_grad and torch.is_grad_enabled() and not _warned_weight_grad:
+    if _warned_weight_grad or not torch.is_grad_enabled():
+        return
+    if any(p is not None and p.requires_grad for p in params):
         warnings.warn("e4s_b200: synthesis-network weights are treated as frozen (as Net3 does for inference and "
                       "inversion, networks.py:69-71); no gradient is produced for them.")
         _warned_weight_grad = True
@@ -211,23 +222,13 @@ def up_form(prep: "PreparedConv") -> str:
 
 # ================================================================================== autograd
 class LinearFn(Function):
-    """y = leaky_relu(x @ w^T + bias, slope) on the library's small-GEMM kernels (csrc/linear.cu); w, bias are frozen prepared
-    tensors (scale / lr_mul folded in), grouped [G, N, K] or shared [N, K].  With at most 16 rows and the transposed copy
-    w_kn ([G,] K, N) at hand, forward and input gradient run in the weight-streaming form (the LocalMLPs stream 163 MB of
-    weights for a handful of rows).  Differentiable wrt x."""
+    """y = leaky_relu(x @ w^T + bias, slope) on the library's small-GEMM kernel (csrc/linear.cu); w, bias are frozen prepared
+    tensors (scale / lr_mul folded in), grouped [G, N, K] or shared [N, K] (kernels.linear).  Differentiable wrt x."""
 
     @staticmethod
-    def forward(ctx, x, w, bias, slope, w_kn=None):
-        skinny = w_kn is not None and x.shape[-2] <= 16
-        if skinny:
-            x3 = x if x.ndim == 3 else x.unsqueeze(0)
-            wk = w_kn if w_kn.ndim == 3 else w_kn.unsqueeze(0)
-            b2 = None if bias is None else (bias if bias.ndim == 2 else bias.unsqueeze(0))
-            y = K.linear_skinny(x3, wk, b2, slope)
-            y = y if x.ndim == 3 else y[0]
-        else:
-            y = K.linear(x, w, bias, slope)
-        ctx.slope, ctx.skinny = float(slope), skinny
+    def forward(ctx, x, w, bias, slope):
+        y = K.linear(x, w, bias, slope)
+        ctx.slope = float(slope)
         ctx.save_for_backward(w, y if slope != 1.0 else None)
         return y
 
@@ -236,15 +237,7 @@ class LinearFn(Function):
         w, y = ctx.saved_tensors
         if ctx.slope != 1.0:
             gy = gy * torch.where(y > 0, 1.0, ctx.slope)
-        gy = gy.contiguous()
-        if ctx.skinny:                                   # gx[m, k] = sum_n gy[m, n] w[n, k]: w in its own [N, K] layout is the stream
-            g3 = gy if gy.ndim == 3 else gy.unsqueeze(0)
-            w3 = w if w.ndim == 3 else w.unsqueeze(0)
-            gx = K.linear_skinny(g3, w3, None, 1.0)
-            gx = gx if gy.ndim == 3 else gx[0]
-        else:
-            gx = K.linear(gy, w, None, 1.0, w_is_kn=True)
-        return gx, None, None, None, None
+        return K.linear(gy.contiguous(), w, None, 1.0, w_is_kn=True), None, None, None
 
 
 class StyledConvFn(Function):
@@ -267,6 +260,7 @@ class StyledConvFn(Function):
         return y
 
     @staticmethod
+    @once_differentiable            # first-order only: a double backward (R1 / path-length regularisation) raises instead of being wrong
     def backward(ctx, gy):
         from . import modconv_bwd
         return modconv_bwd.styled_backward(ctx, gy)
@@ -285,6 +279,7 @@ class ToRGBFn(Function):
         return out
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, g):
         from . import modconv_bwd
         return modconv_bwd.torgb_backward(ctx, g)

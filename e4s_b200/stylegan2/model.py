@@ -10,8 +10,10 @@ unchanged.  What differs is the execution:
 * activations travel between layers in pixel-major storage (NCHW tensors with channels_last strides);
 * region masks travel as a uint8 label pyramid built once per forward.
 
-Outputs equal the reference's for one-hot masks (tests/test_parity_gpu.py).  The discriminator half of the
-reference file (model.py:670-799) is training-only and out of scope.
+Outputs equal the reference's for one-hot masks (tests/test_parity_gpu.py).  The discriminator half of the reference
+file (model.py:670-799: ConvLayer, ResBlock, Discriminator) is mirrored at the end of this file on this package's
+upfirdn2d / fused-act ops (the module, forward and autograd; the training loop of
+src/training/coach.py stays out of scope).
 """
 from __future__ import annotations
 
@@ -111,8 +113,8 @@ class EqualLinear(nn.Module):
         key = (self.weight.data_ptr(), self.weight._version, None if self.bias is None else (self.bias.data_ptr(), self.bias._version))
         if getattr(self, "_prep_key", None) != key:
             with torch.no_grad():
-                w = (self.weight * self.scale).float().contiguous()
-                self._prep = (w, None if self.bias is None else (self.bias * self.lr_mul).float().contiguous(), w.t().contiguous())
+                self._prep = ((self.weight * self.scale).float().contiguous(),
+                              None if self.bias is None else (self.bias * self.lr_mul).float().contiguous())
             self._prep_key = key
         return self._prep
 
@@ -121,9 +123,9 @@ class EqualLinear(nn.Module):
         if (input.is_cuda and not self.activation and not trainable and input.dtype == torch.float32
                 and self.weight.shape[0] % 4 == 0 and self.weight.shape[1] % 4 == 0):
             # the style modulations of the synthesis path (model.py:276): own small-GEMM kernel, no library GEMM
-            w, b, w_kn = self._frozen()
+            w, b = self._frozen()
             lead = input.shape[:-1]
-            y = MC.LinearFn.apply(input.reshape(-1, input.shape[-1]).contiguous(), w, b, 1.0, w_kn)
+            y = MC.LinearFn.apply(input.reshape(-1, input.shape[-1]).contiguous(), w, b, 1.0)
             return y.reshape(*lead, w.shape[0])
         w = self.weight * self.scale
         if self.activation:
@@ -189,6 +191,7 @@ class ModulatedConv2d(nn.Module):
 
     def forward_regions(self, x_pm, styles, label, noise=None, noise_w=None, bias=None, act=False):
         """x_pm [B,H,W,Cin] pixel-major; styles [B, R, style_dim]; label [B,Ho,Wo] uint8 or None (R == 1)."""
+        MC.warn_frozen(noise_w, bias)
         s = self.modulation(styles)                                    # [B, R, Cin]   (model.py:276)
         return MC.StyledConvFn.apply(x_pm, s, noise, noise_w, bias, label, self.prepared(), self.upsample,
                                      self.demodulate, act)
@@ -279,6 +282,7 @@ class ToRGB(nn.Module):
             styles = style
         else:
             label, styles = None, style.unsqueeze(1)
+        MC.warn_frozen(self.bias)
         s = self.conv.modulation(styles)
         prep = self.conv.prepared()
         fuse_skip = (skip is not None and tuple(skip.shape[2:]) == (h // 2, w // 2) and h % 2 == 0 and w % 2 == 0
@@ -413,3 +417,74 @@ class Generator(nn.Module):
 
         image = skip
         return image, (latent if return_latents else None), intermediate_feats
+
+
+# ================================================================================ discriminator half (model.py:670-799)
+class ConvLayer(nn.Sequential):
+    """Blur (when down-sampling) -> EqualConv2d -> FusedLeakyReLU / ScaledLeakyReLU, reference model.py:670-716.  The blur and
+    the activation run on this package's kernels (upfirdn2d, fused bias + leaky ReLU, both with first- and second-order
+    autograd, which R1 regularisation needs); the convolution is the plain library convolution the reference uses."""
+
+    def __init__(self, in_channel, out_channel, kernel_size, downsample=False, blur_kernel=[1, 3, 3, 1], bias=True, activate=True):
+        layers = []
+        if downsample:
+            factor = 2
+            p = (len(blur_kernel) - factor) + (kernel_size - 1)
+            layers.append(Blur(blur_kernel, pad=((p + 1) // 2, p // 2)))
+            stride = 2
+            self.padding = 0
+        else:
+            stride = 1
+            self.padding = kernel_size // 2
+        layers.append(EqualConv2d(in_channel, out_channel, kernel_size, padding=self.padding, stride=stride,
+                                  bias=bias and not activate))
+        if activate:
+            layers.append(FusedLeakyReLU(out_channel) if bias else ScaledLeakyReLU(0.2))
+        super().__init__(*layers)
+
+
+class ResBlock(nn.Module):
+    def __init__(self, in_channel, out_channel, blur_kernel=[1, 3, 3, 1]):
+        super().__init__()
+        self.conv1 = ConvLayer(in_channel, in_channel, 3)
+        self.conv2 = ConvLayer(in_channel, out_channel, 3, downsample=True)
+        self.skip = ConvLayer(in_channel, out_channel, 1, downsample=True, activate=False, bias=False)
+
+    def forward(self, input):
+        out = self.conv2(self.conv1(input))
+        return (out + self.skip(input)) / math.sqrt(2)
+
+
+class Discriminator(nn.Module):
+    """StyleGAN2 discriminator with minibatch standard deviation, reference model.py:740-799 (same module tree and state-dict
+    keys: ``convs.N.*``, ``final_conv.*``, ``final_linear.{0,1}.*``)."""
+
+    def __init__(self, size, channel_multiplier=2, blur_kernel=[1, 3, 3, 1]):
+        super().__init__()
+        cm = channel_multiplier
+        channels = {4: 512, 8: 512, 16: 512, 32: 512, 64: 256 * cm, 128: 128 * cm, 256: 64 * cm, 512: 32 * cm, 1024: 16 * cm}
+        convs = [ConvLayer(3, channels[size], 1)]
+        log_size = int(math.log(size, 2))
+        in_channel = channels[size]
+        for i in range(log_size, 2, -1):
+            out_channel = channels[2 ** (i - 1)]
+            convs.append(ResBlock(in_channel, out_channel, blur_kernel))
+            in_channel = out_channel
+        self.convs = nn.Sequential(*convs)
+        self.stddev_group = 4
+        self.stddev_feat = 1
+        self.final_conv = ConvLayer(in_channel + 1, channels[4], 3)
+        self.final_linear = nn.Sequential(EqualLinear(channels[4] * 4 * 4, channels[4], activation="fused_lrelu"),
+                                          EqualLinear(channels[4], 1))
+
+    def forward(self, input):
+        out = self.convs(input)
+        batch, channel, height, width = out.shape
+        group = min(batch, self.stddev_group)
+        stddev = out.reshape(group, -1, self.stddev_feat, channel // self.stddev_feat, height, width)
+        stddev = torch.sqrt(stddev.var(0, unbiased=False) + 1e-8)
+        stddev = stddev.mean([2, 3, 4], keepdims=True).squeeze(2)
+        stddev = stddev.repeat(group, 1, height, width)
+        out = torch.cat([out, stddev], 1)
+        out = self.final_conv(out)
+        return self.final_linear(out.reshape(batch, -1))

@@ -110,7 +110,8 @@ int e4s_region_mean_f32(const float* feats, const uint8_t* label, float* out, in
 int e4s_demod_f32(const float* s, const float* wsq, float* demod, int rows, int cin, int cout, float eps,
                   void* stream);
 /* The same on the tiled small-GEMM kernel (csrc/linear.cu; cin % 4 == 0, cout % 4 == 0): what the generator uses. */
-int e4s_demod_gemm_f32(const float* s, const float* wsq, float* demod, int rows, int cin, int cout, float eps, void* stream);
+int e4s_demod_gemm_f32(const float* s, const float* wsq, float* demod, int rows, int cin, int cout, float eps, float* workspace,
+                       void* stream);
 
 /* Region-selected modulated 3x3 convolution with fused noise + bias + leaky-ReLU epilogue:
  * one call = one StyledConv.forward (model.py:382-406) for every region at once.
@@ -226,17 +227,14 @@ int e4s_torgb_bwd_f32(const float* g, const float* x, const float* wrgb, const f
  *                folded EqualLinear's scale / lr_mul into w and bias)
  * w_is_kn != 0:  y[g, m, n] = sum_k x[g, m, k] * w[g, k, n]                        (input gradient of the above; bias must be NULL)
  * act = leaky ReLU with slope act_slope (1 = none).  *_gstride: element strides between groups (0 = shared operand).
- * n % 4 == 0, k % 4 == 0, 16-byte aligned pointers. */
+ * n % 4 == 0, k % 4 == 0, 16-byte aligned pointers.  workspace: e4s_linear_workspace_floats(groups, m, n, k) floats (may be
+ * NULL when that is 0); with a workspace y must be densely packed (y_gstride == m * n). */
 int e4s_linear_f32(const float* x, const float* w, const float* bias, float* y, int groups, int m, int n, int k,
                    long long x_gstride, long long w_gstride, long long bias_gstride, long long y_gstride, int w_is_kn,
-                   float act_slope, void* stream);
-
-/* The same product for at most 16 rows, organised as a weight stream (the LocalMLPs: 163 MB of weights for a handful of rows):
- * y[g, m, j] = act( sum_i x[g, m, i] * w_ij[g, i, j] + bias[g, j] ), w_ij: [G, I, J] with J contiguous, j % 4 == 0, m <= 16.
- * For I >= 2048 the reduction is cut into slabs of 512 rows whose partial sums meet by red.global.add (y is zeroed by a memset
- * on `stream`; the last bits of y may differ between runs); bias must then be NULL and act_slope 1. */
-int e4s_linear_skinny_f32(const float* x, const float* w_ij, const float* bias, float* y, int groups, int m, int i, int j,
-                          float act_slope, void* stream);
+                   float act_slope, float* workspace, void* stream);
+/* Host-only: floats of workspace the two entry points need for a shape (0 = none).  When the output tiles alone cannot fill
+ * the GPU, K is cut into slices handled by different CTAs and summed in a fixed order by a second kernel (deterministic). */
+long long e4s_linear_workspace_floats(int groups, int m, int n, int k);
 
 /* ---- loss networks of the inversion loop (scripts/optimization.py:88-122) -------------------------------------------
  * Average-pooling pyramid: y2 = 2x2 block means, y4 = 4x4 block means of planar x [planes, H, W] (H % 4 == 0, W % 8 == 0):

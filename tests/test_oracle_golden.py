@@ -94,3 +94,19 @@ def test_gpu_baseline_structure_equals_oracle():
         b, fb = GB.generator_forward(st, codes, mask, noise, size, K)
     assert float((a - b).abs().max() / a.abs().max()) < 1e-5
     assert float((fa - fb).abs().max() / fa.abs().max()) < 1e-5
+
+
+def test_discriminator_oracle_matches_reference_vectors():
+    """oracle/disc_oracle.py against the reference Discriminator's logits (oracle/make_golden_disc.py)."""
+    import os
+    from conftest import ROOT
+    from oracle import disc_oracle as DO
+    from e4s_b200.stylegan2.model import Discriminator
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "disc_vectors.npz"))
+    for size, batch in ((32, 4), (64, 8)):
+        D = Discriminator(size).eval()                       # the mirror supplies the key layout and the registered FIR buffers
+        D.load_state_dict(O.synthetic_state({k: tuple(v.shape) for k, v in D.named_parameters()}, salt=size + 1), strict=False)
+        st = {k: v.detach() for k, v in D.state_dict().items()}
+        with torch.no_grad():
+            out = DO.discriminator_forward(st, DO.synthetic_inputs(batch, size, seed=size), size)
+        assert_close(out, gold[f"d{size}/logits"], 2e-5, f"discriminator oracle {size}")
