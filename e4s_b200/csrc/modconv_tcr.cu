@@ -166,11 +166,17 @@ __device__ __forceinline__ void xform_barrier() { asm volatile("bar.sync 1, 256;
 // its row-class operand 9 times per chunk for MMAs of N = 256 instead of 36 times for MMAs of N = 64 - the masked
 // low-resolution up-sampling layers (>= 3 regions in most tiles at <= 64x64) were transform- and issue-bound at 27-33 %
 // tensor pipe (profiles/r1_ncu_tcr_17_layers.md).  Item::nt carries (N tile) * 4 + parity.
-template <int NTC, int KC, int NPH, bool XS, bool UP2>
+template <int NTC, int KC, int NPH, bool XS, bool UP2, bool STK>
 __global__ void __launch_bounds__(XS ? NUM_THREADS_XS : NUM_THREADS, 1)
 modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap xmap, Params p) {
     static_assert(!XS || KC == 32, "XS mode stages 32-channel chunks");
-    static_assert(!UP2 || (NPH == 1 && !XS), "parity work items are plain-convolution items");
+    static_assert(!UP2 || NPH == 1, "parity work items are plain-convolution items");
+    // STK (small N tiles of plain layers): the w_hi and w_lo slots of a tap are contiguous in shared memory, so ONE MMA with
+    // N = 2 NTC multiplies x_hi by both (columns [0, NTC): x_hi w_hi, [NTC, 2 NTC): x_hi w_lo) and a second one adds x_lo w_hi to
+    // the first half: two MMAs and two operand fetches per (tap, K step) instead of three.  At N <= 64 an MMA costs its A-operand
+    // fetch from shared memory (~80 cycles for 16 of arithmetic at N = 32), not its arithmetic: the 32->32 layer at 1024x1024
+    // spent 54 such MMAs per tile.  The epilogue adds the two halves.
+    static_assert(!STK || (NPH == 1 && !UP2 && 2 * NTC <= 256), "stacked hi/lo weights: plain layers, N tile <= 128");
     constexpr int N = NTC * NPH;
     constexpr int ROWB = KC * 2;
     constexpr int A_PLANE = A_ROWS * ROWB;
@@ -190,6 +196,8 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
     constexpr uint32_t IDESC_BASE = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 4) << 24);
     constexpr uint32_t IDESC_N = IDESC_BASE | ((uint32_t)(N >> 3) << 17);         // all parities in one MMA
     constexpr uint32_t IDESC_Q = IDESC_BASE | ((uint32_t)(NTC >> 3) << 17);       // one parity
+    constexpr uint32_t IDESC_2N = IDESC_BASE | ((uint32_t)((2 * N) >> 3) << 17);  // STK: w_hi and w_lo stacked along N
+    constexpr int NMMA = STK ? 2 : NUM_MMA_WARPS;                                 // issuing warps in use
     constexpr uint32_t DESC_HI = (uint32_t)((KC == 64 ? 1024u : 512u) >> 4) | (1u << 14) | ((KC == 64 ? 2u : 4u) << 29);
     constexpr int KSTEPS = KC / 16;
     constexpr int MUL = (NPH == 4 || UP2) ? 2 : 1;
@@ -222,7 +230,7 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
         // every MMA warp commits to the barriers of what it read: both operand planes are read by two of them
         // (x_hi: warps 0 and 2, w_hi: warps 0 and 1) - A stages, accumulators and (hi, lo) weight slot PAIRS (the ring unit:
         // one TMA box, the barriers of the even slot) are released by all three
-        const uint32_t nmma = p.det ? 1u : (uint32_t)NUM_MMA_WARPS;      // issuing warps that commit to each barrier
+        const uint32_t nmma = p.det ? 1u : (uint32_t)NMMA;               // issuing warps that commit to each barrier
         for (int i = 0; i < NSTAGE_A; ++i) mbar_init(smem_u32(&bars[A_FULL + i]), NUM_XFORM), mbar_init(smem_u32(&bars[A_EMPTY + i]), nmma);
         for (int i = 0; i < NACC; ++i) mbar_init(smem_u32(&bars[ACC_FULL + i]), nmma), mbar_init(smem_u32(&bars[ACC_EMPTY + i]), NUM_EPI);
         for (int i = 0; i < p.nslot_b; ++i) mbar_init(smem_u32(&bars[B_FULL + i]), 1), mbar_init(smem_u32(&bars[B_EMPTY + i]), nmma);
@@ -312,7 +320,7 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
         }
         __syncwarp();
     } else if (warp <= NUM_MMA_WARPS) {
-      if (!p.det || warp == 1) {
+      if ((!p.det || warp == 1) && warp - 1 < NMMA) {
         // ===================================================================== MMA issuers (one split-precision product each)
         // product 0: x_hi * w_hi, 1: x_lo * w_hi, 2: x_hi * w_lo.  Each warp walks the loops with warp-uniform state (barrier
         // waits included) and one lane, chosen by elect.sync, issues.  Deterministic mode (p.det): warp 1 alone issues the
@@ -321,6 +329,11 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
         const int role = warp - 1;
         constexpr uint32_t A_LO = (uint32_t)A_PLANE >> 4, W_LO = (uint32_t)B_SLOT >> 4;      // descriptor offsets of the x_lo plane / w_lo slot
         const uint32_t a_role = role == 1 ? A_LO : 0u, w_role = role == 2 ? W_LO : 0u;     // this warp's product (default mode)
+        // STK: product 0 = x_hi [w_hi | w_lo] (N doubled), product 1 = x_lo w_hi; deterministic mode walks r = 0 .. NPROD-1
+        constexpr int NPROD = STK ? 2 : 3;
+        const uint32_t idn_role = (STK && role == 0) ? IDESC_2N : IDESC_N, idq_role = (STK && role == 0) ? IDESC_2N : IDESC_Q;
+        auto idn_of = [&](int r) -> uint32_t { return (STK && r == 0) ? IDESC_2N : IDESC_N; };
+        auto idq_of = [&](int r) -> uint32_t { return (STK && r == 0) ? IDESC_2N : IDESC_Q; };
         int sa = 0, slot = 0, acc = 0;
         uint32_t pa = 0, pb = 0, pacc0 = 0, pacc1 = 0;
         bool b_ready = false;                            // resident weights: waited for once
@@ -363,17 +376,17 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                         if (elect_one()) {
                             if (!p.det) {
 #pragma unroll
-                                for (int k = 0; k < KSTEPS; ++k) umma_bf16(d_tmem, desc(apA + a_role + roff + 2 * k), desc(bp + w_role + 2 * k), IDESC_N, 1u);
+                                for (int k = 0; k < KSTEPS; ++k) umma_bf16(d_tmem, desc(apA + a_role + roff + 2 * k), desc(bp + w_role + 2 * k), idn_role, 1u);
 #pragma unroll
-                                for (int k = 0; k < KSTEPS; ++k) umma_bf16(d_other, desc(apB + a_role + roff + 2 * k), desc(bp + w_role + 2 * k), IDESC_N, 1u);
+                                for (int k = 0; k < KSTEPS; ++k) umma_bf16(d_other, desc(apB + a_role + roff + 2 * k), desc(bp + w_role + 2 * k), idn_role, 1u);
                             } else {
 #pragma unroll 1
-                                for (int r = 0; r < 3; ++r) {
+                                for (int r = 0; r < NPROD; ++r) {
                                     const uint32_t ao = r == 1 ? A_LO : 0u, wo2 = r == 2 ? W_LO : 0u;
 #pragma unroll
-                                    for (int k = 0; k < KSTEPS; ++k) umma_bf16(d_tmem, desc(apA + ao + roff + 2 * k), desc(bp + wo2 + 2 * k), IDESC_N, 1u);
+                                    for (int k = 0; k < KSTEPS; ++k) umma_bf16(d_tmem, desc(apA + ao + roff + 2 * k), desc(bp + wo2 + 2 * k), idn_of(r), 1u);
 #pragma unroll
-                                    for (int k = 0; k < KSTEPS; ++k) umma_bf16(d_other, desc(apB + ao + roff + 2 * k), desc(bp + wo2 + 2 * k), IDESC_N, 1u);
+                                    for (int k = 0; k < KSTEPS; ++k) umma_bf16(d_other, desc(apB + ao + roff + 2 * k), desc(bp + wo2 + 2 * k), idn_of(r), 1u);
                                 }
                             }
                             if (!p.resident) umma_commit(bars0 + 8 * (B_EMPTY + slot));
@@ -396,7 +409,7 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                 // instructions per tap: the three issuing warps were 85 % busy on the 32->32 layer while the tensor pipe idled,
                 // profiles/r2_stall_attribution_tcr_elect.log.)  State (stage / slot rings) is advanced by every lane afterwards.
                 if (elect_one()) {
-                    const uint32_t a_mine = a0 + (role == 1 ? A_PLANE : 0), b_mine = b0 + (role == 2 ? B_SLOT : 0);
+                    const uint32_t a_mine = a0 + (role == 1 ? A_PLANE : 0), b_mine = b0 + ((!STK && role == 2) ? B_SLOT : 0);
                     int sa2 = sa, slot2 = slot;
                     uint32_t pa2 = pa, pb2 = pb;
 #pragma unroll 1
@@ -413,7 +426,7 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                             }
                             const uint32_t bp = lo_of(b_mine + slot2 * B_SLOT);
 #pragma unroll
-                            for (int k = 0; k < KSTEPS; ++k) umma_bf16(d_tmem, desc(ap + roff + 2 * k), desc(bp + 2 * k), IDESC_N, 1u);
+                            for (int k = 0; k < KSTEPS; ++k) umma_bf16(d_tmem, desc(ap + roff + 2 * k), desc(bp + 2 * k), idn_role, 1u);
                             if (!p.resident) umma_commit(bars0 + 8 * (B_EMPTY + slot2));
                             slot2 += 2;
                             if (slot2 >= p.nslot_b) slot2 = 0, pb2 ^= 1;
@@ -449,13 +462,13 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                         if (elect_one()) {
                             if (!p.det) {
 #pragma unroll
-                                for (int k = 0; k < KSTEPS; ++k) umma_bf16(d_tmem, desc(ap + a_role + roff + 2 * k), desc(bp + w_role + 2 * k), IDESC_N, 1u);
+                                for (int k = 0; k < KSTEPS; ++k) umma_bf16(d_tmem, desc(ap + a_role + roff + 2 * k), desc(bp + w_role + 2 * k), idn_role, 1u);
                             } else {
 #pragma unroll 1
-                                for (int r = 0; r < 3; ++r) {
+                                for (int r = 0; r < NPROD; ++r) {
                                     const uint32_t ao = r == 1 ? A_LO : 0u, wo2 = r == 2 ? W_LO : 0u;
 #pragma unroll
-                                    for (int k = 0; k < KSTEPS; ++k) umma_bf16(d_tmem, desc(ap + ao + roff + 2 * k), desc(bp + wo2 + 2 * k), IDESC_N, 1u);
+                                    for (int k = 0; k < KSTEPS; ++k) umma_bf16(d_tmem, desc(ap + ao + roff + 2 * k), desc(bp + wo2 + 2 * k), idn_of(r), 1u);
                                 }
                             }
                             if (!p.resident) umma_commit(bars0 + 8 * (B_EMPTY + slot));
@@ -485,13 +498,13 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                             if (elect_one()) {
                                 if (!p.det) {
 #pragma unroll
-                                    for (int k = 0; k < KSTEPS; ++k) umma_bf16(dq, desc(ap + a_role + 2 * k), desc(bp + w_role + boff + 2 * k), IDESC_Q, 1u);
+                                    for (int k = 0; k < KSTEPS; ++k) umma_bf16(dq, desc(ap + a_role + 2 * k), desc(bp + w_role + boff + 2 * k), idq_role, 1u);
                                 } else {
 #pragma unroll 1
-                                    for (int r = 0; r < 3; ++r) {
+                                    for (int r = 0; r < NPROD; ++r) {
                                         const uint32_t ao = r == 1 ? A_LO : 0u, wo2 = r == 2 ? W_LO : 0u;
 #pragma unroll
-                                        for (int k = 0; k < KSTEPS; ++k) umma_bf16(dq, desc(ap + ao + 2 * k), desc(bp + wo2 + boff + 2 * k), IDESC_Q, 1u);
+                                        for (int k = 0; k < KSTEPS; ++k) umma_bf16(dq, desc(ap + ao + 2 * k), desc(bp + wo2 + boff + 2 * k), idq_of(r), 1u);
                                     }
                                 }
                                 umma_commit(bars0 + 8 * (A_EMPTY + sa));
@@ -776,6 +789,13 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                         tmem_zero32(lanes + cbase);      // the next tile's MMAs only accumulate
                         PROF_END(2);
                     }
+                    if (STK) {                           // second half of the stacked accumulator: x_hi w_lo
+                        uint32_t rl[32];
+                        tmem_ld32(lanes + cbase + (uint32_t)N, rl);
+                        tmem_zero32(lanes + cbase + (uint32_t)N);
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) + __uint_as_float(rl[e]));
+                    }
                     if (two) {
                         uint32_t r2[32];
                         tmem_ld32(lanes + cother, r2);
@@ -901,7 +921,7 @@ static int num_sms() { return e4s_num_sms(); }
 
 static long long* g_prof = nullptr;
 
-template <int NTC, int KC, int NPH, bool XS = false, bool UP2 = false>
+template <int NTC, int KC, int NPH, bool XS = false, bool UP2 = false, bool STK = false>
 static int launch(const void* w_hilo, Params p, cudaStream_t st) {
     p.prof = g_prof;
     p.det = e4s_get_deterministic();
@@ -962,9 +982,9 @@ static int launch(const void* w_hilo, Params p, cudaStream_t st) {
     p.nslot_b = p.resident ? planes : (max_slots > 16 ? 16 : (max_slots & ~1));
     const size_t smem = 1024 + A_BYTES + (size_t)p.nslot_b * B_SLOT + tab_bytes + (size_t)(2 * NSTAGE_A + 4 + 2 * p.nslot_b + 2 * NXS) * 8 + 64;
     static E4sSmemOptIn optin;
-    if (const int rc = e4s_smem_optin(optin, modconv3x3_tcr_kernel<NTC, KC, NPH, XS, UP2>, smem)) return rc;
+    if (const int rc = e4s_smem_optin(optin, modconv3x3_tcr_kernel<NTC, KC, NPH, XS, UP2, STK>, smem)) return rc;
     const int grid = p.items < num_sms() ? p.items : num_sms();
-    modconv3x3_tcr_kernel<NTC, KC, NPH, XS, UP2><<<grid, XS ? NUM_THREADS_XS : NUM_THREADS, smem, st>>>(map, xmap, p);
+    modconv3x3_tcr_kernel<NTC, KC, NPH, XS, UP2, STK><<<grid, XS ? NUM_THREADS_XS : NUM_THREADS, smem, st>>>(map, xmap, p);
     return e4s_launch_status();
 }
 
@@ -989,8 +1009,11 @@ int dispatch(const void* w_hilo_bf16, Params p, int up, cudaStream_t st) {
     if (cin <= 64) {                 // small K: HBM-bound layers -> TMA-staged activations, 32-channel chunks
         if (!up) {
             if (cout % 128 == 0) return launch<128, 32, 1, true>(w_hilo_bf16, p, st);
-            if (cout % 64 == 0) return launch<64, 32, 1, true>(w_hilo_bf16, p, st);
-            return launch<32, 32, 1, true>(w_hilo_bf16, p, st);
+            // N <= 64: w_hi and w_lo stacked along N (STK) - two MMAs per (tap, K step); E4S_B200_STK=0 switches it off
+            const char* fstk = getenv("E4S_B200_STK");
+            const bool stk = !(fstk && atoi(fstk) == 0);
+            if (cout % 64 == 0) return stk ? launch<64, 32, 1, true, false, true>(w_hilo_bf16, p, st) : launch<64, 32, 1, true>(w_hilo_bf16, p, st);
+            return stk ? launch<32, 32, 1, true, false, true>(w_hilo_bf16, p, st) : launch<32, 32, 1, true>(w_hilo_bf16, p, st);
         }
         if (cout % 64 == 0) return launch<64, 32, 4, true>(w_hilo_bf16, p, st);
         return launch<32, 32, 4, true>(w_hilo_bf16, p, st);
@@ -999,6 +1022,15 @@ int dispatch(const void* w_hilo_bf16, Params p, int up, cudaStream_t st) {
     // low-resolution 512-channel layers have a handful of pixel tiles, and wide N tiles left most SMs without work.
     const bool k64 = (cin % 64) == 0;
     const int64_t pixel_tiles = e4s_ceil_div(p.w, TW) * e4s_ceil_div(p.h, TH) * p.batch;
+    // Experimental (E4S_B200_XS=1): TMA-staged raw activation tiles + 32-channel chunks for the wide masked layers too.  With
+    // 225 KB of shared memory the L1 keeps ~30 KB: the 40-KB halo tile of a 64-channel chunk does not fit, so the nine
+    // row-class stagings of a mixed tile re-fetch it from L2; from shared memory they would not.
+    if (const char* f = getenv("E4S_B200_XS")) {
+        if (atoi(f) != 0 && p.label && cout % 128 == 0 && pixel_tiles * (cout / 128) >= num_sms() / 2) {
+            if (!up) return cout % 256 == 0 ? launch<256, 32, 1, true>(w_hilo_bf16, p, st) : launch<128, 32, 1, true>(w_hilo_bf16, p, st);
+            if (cin >= 128 && cout >= 256) return launch<256, 32, 1, true, true>(w_hilo_bf16, p, st);
+        }
+    }
     if (!up) {
         if (k64) {
             int nt = pick_ntile(cout, 256, pixel_tiles);

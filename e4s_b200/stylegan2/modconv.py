@@ -33,7 +33,7 @@ class LabelPyramid:
 
     # one-hot validation is remembered per mask TENSOR OBJECT (weak reference) and version: an address-keyed cache could be hit
     # by a different, freshly allocated mask that recycles a freed tensor's address (round-1 review)
-    _validated = weakref.WeakKeyDictionary()
+    _validated: Dict[int, Tuple] = {}                 # id(mask) -> (weakref to the mask, its version when validated)
 
     def __init__(self, label: Tensor, ncls: int):
         assert label.dtype == torch.uint8 and label.ndim == 3
@@ -50,12 +50,15 @@ class LabelPyramid:
         if not mask.is_cuda:
             raise RuntimeError("mask must be a CUDA tensor")
         label, flag = K.onehot_to_label(mask)
-        if os.environ.get("E4S_B200_CHECK_MASK", "1") != "0" and cls._validated.get(mask) != mask._version:
-            if int(flag.item()) != 0:   # one host sync per distinct mask tensor (and version)
-                raise RuntimeError(
-                    "e4s_b200: the region mask is not one-hot (exactly one 1.0 per pixel). The region-selected "
-                    "kernels implement the reference's mask-sum (model.py:395-398) for one-hot masks only.")
-            cls._validated[mask] = mask._version
+        if os.environ.get("E4S_B200_CHECK_MASK", "1") != "0":
+            hit = cls._validated.get(id(mask))
+            if hit is None or hit[0]() is not mask or hit[1] != mask._version:
+                if int(flag.item()) != 0:   # one host sync per distinct mask tensor (and version)
+                    raise RuntimeError(
+                        "e4s_b200: the region mask is not one-hot (exactly one 1.0 per pixel). The region-selected "
+                        "kernels implement the reference's mask-sum (model.py:395-398) for one-hot masks only.")
+                key = id(mask)
+                cls._validated[key] = (weakref.ref(mask, lambda _r, k=key: cls._validated.pop(k, None)), mask._version)
         return cls(label, mask.shape[1])
 
     def at(self, h: int, w: int) -> Tensor:

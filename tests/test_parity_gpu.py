@@ -599,6 +599,40 @@ def test_deterministic_generator_is_bit_reproducible(deterministic):
     assert torch.equal(a, b)
 
 
+@pytest.mark.parametrize("stk", ["0", "1"])
+@pytest.mark.parametrize("b,cin,cout,hw,up,ncls,kind", [
+    (2, 32, 32, 40, False, 1, "blobs"),       # c15's channels: resident weights, several items per CTA
+    (1, 64, 64, 36, False, 1, "blobs"),       # c13's channels: two K chunks
+    (1, 32, 64, 18, False, 4, "iid"),         # masked: row-class path with the stacked product
+    (2, 64, 32, 24, False, 3, "blobs"),
+])
+def test_tcr_kernel_stacked_hilo_weights(monkeypatch, stk, b, cin, cout, hw, up, ncls, kind):
+    """Small-N plain layers with w_hi / w_lo stacked along N (csrc/modconv_tcr.cu STK: two MMAs per (tap, K step) instead of
+    three, the two accumulator halves added in the epilogue) and without, against the fp32 SIMT kernel."""
+    monkeypatch.setenv("E4S_B200_STK", stk)
+    K, prep, x, args = _tc_case(b, cin, cout, hw, up, ncls, kind, seed=cin + cout + hw)
+    ref = K.modconv3x3_fwd(x, prep.wt, *args)
+    out = K.modconv3x3_tcr_fwd(x, prep.w_hilo, *args)
+    torch.cuda.synchronize()
+    assert_close(out, ref, 1e-4, f"tcr (STK={stk}) vs simt {b},{cin},{cout},{hw},{ncls},{kind}")
+
+
+@pytest.mark.parametrize("b,cin,cout,hw,up,ncls,kind", [
+    (2, 512, 512, 24, False, 12, "blobs"),    # wide masked plain layer on TMA-staged 32-channel chunks
+    (2, 256, 128, 28, False, 5, "iid"),
+    (2, 512, 256, 20, True, 12, "blobs"),     # parity work items on TMA-staged chunks
+])
+def test_tcr_kernel_xs_mode_for_wide_masked_layers(monkeypatch, b, cin, cout, hw, up, ncls, kind):
+    """E4S_B200_XS=1 (experimental): raw activation tiles by TMA + 32-channel chunks for Cin > 64 masked layers."""
+    monkeypatch.setenv("E4S_B200_XS", "1")
+    monkeypatch.setenv("E4S_B200_UPFORM", "poly")
+    K, prep, x, args = _tc_case(b, cin, cout, hw, up, ncls, kind, seed=cin + cout + hw)
+    ref = K.modconv3x3_fwd(x, prep.wt, *args)
+    out = K.modconv3x3_tcr_fwd(x, prep.w_hilo, *args)
+    torch.cuda.synchronize()
+    assert_close(out, ref, 1e-4, f"tcr (XS=1) vs simt {b},{cin},{cout},{hw},{up},{ncls},{kind}")
+
+
 @pytest.mark.parametrize("b,cin,cout,hw,up,ncls,kind", PRODUCTION_CASES)
 def test_tcr_kernel_production_shapes(b, cin, cout, hw, up, ncls, kind):
     K, prep, x, args = _tc_case(b, cin, cout, hw, up, ncls, kind, seed=cin + cout + hw)
