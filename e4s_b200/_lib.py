@@ -51,12 +51,21 @@ SIGNATURES = {
     "e4s_torgb_bwd_f32": [P] * 7 + [c_int] * 5 + [P],
     "e4s_torgb_fwd_f32": [P] * 8 + [c_int] * 5 + [P],
     "e4s_linear_f32": [P, P, P, P, c_int, c_int, c_int, c_int, c_int64, c_int64, c_int64, c_int64, c_int, c_float, P, P],
+    "e4s_linear_multi_f32": [P, c_int, P],
     "e4s_avgpool_pyramid_f32": [P, P, P, c_int64, c_int, c_int, P],
     "e4s_avgpool_pyramid_bwd_f32": [P, P, P, P, c_int64, c_int, c_int, P],
     "e4s_planar_to_pixel_f32": [P, P, c_int, c_int, c_int, c_int, P],
     "e4s_pixel_to_planar_f32": [P, P, c_int, c_int, c_int, c_int, P],
 }
 PLAIN = {"e4s_linear_workspace_floats": ([c_int, c_int, c_int, c_int], c_int64), "e4s_get_deterministic": ([], c_int), "e4s_version": ([], c_int), "e4s_build_arch": ([], c_char_p), "e4s_device_ok": ([], c_int)}
+
+
+
+class LinearProblem(ctypes.Structure):
+    """E4sLinearProblem of include/e4s_b200.h."""
+    _fields_ = [("x", c_void_p), ("w", c_void_p), ("bias", c_void_p), ("y", c_void_p), ("m", c_int), ("n", c_int), ("k", c_int),
+                ("ldx", c_int), ("rsqrt_eps", c_float), ("reserved", c_int)]
+
 
 _lib = None
 

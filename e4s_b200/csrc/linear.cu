@@ -146,6 +146,81 @@ __global__ void __launch_bounds__(256) linear_reduce_kernel(LinParams p) {
     }
 }
 
+// ---- many small products in one launch ------------------------------------------------------------------------------------
+// One synthesis forward needs 26 style modulations ([B * regions, 512] x [512, Cin], different Cin, different latent) and 17
+// demodulation products; launched one by one they are ~85 launches of 6-8 us each (latency, not work).  Here the problems of
+// one kind travel BY VALUE in the kernel parameters (<= E4S_LINEAR_MULTI_MAX per launch) and a CTA finds its (problem, tile)
+// from a prefix of tile counts: all modulations are one launch, all demodulations a second one.  Together the tiles fill the
+// GPU, so K is not split (deterministic, no workspace).  x rows may be strided (ldx): a latent slice is read in place.
+struct MultiParams {
+    E4sLinearProblem prob[E4S_LINEAR_MULTI_MAX];
+    int tile0[E4S_LINEAR_MULTI_MAX + 1];
+    int nprob;
+};
+
+__global__ void __launch_bounds__(NT) linear_multi_kernel(const __grid_constant__ MultiParams mp) {
+    __shared__ __align__(16) float xs[BK][BM + 4];
+    __shared__ __align__(16) float ws[BK][BN + 4];
+    int pi = 0;
+    while (pi + 1 < mp.nprob && (int)blockIdx.x >= mp.tile0[pi + 1]) ++pi;
+    const E4sLinearProblem& p = mp.prob[pi];
+    const int tile = blockIdx.x - mp.tile0[pi], tiles_n = (p.n + BN - 1) / BN;
+    const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+    const float* __restrict__ x = p.x;
+    const float* __restrict__ w = p.w;
+    const int M = p.m, N = p.n, Kd = p.k, ldx = p.ldx;
+    const bool demod = p.rsqrt_eps >= 0.f;
+    const int t = threadIdx.x, ty = t >> 3, tx = t & 7;
+    const int xr = t >> 3, xk = (t & 7) * 4;
+    float acc[2][4] = {};
+    float4 xv[2], wv[2];
+    auto load = [&](int k0) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int r = xr + 16 * i;
+            xv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m0 + r < M && k0 + xk < Kd) xv[i] = __ldg(reinterpret_cast<const float4*>(x + (int64_t)(m0 + r) * ldx + k0 + xk));
+            wv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int e = t + NT * i, nr = e >> 3, kq = (e & 7) * 4;
+            if (n0 + nr < N && k0 + kq < Kd) wv[i] = __ldg(reinterpret_cast<const float4*>(w + (int64_t)(n0 + nr) * Kd + k0 + kq));
+        }
+    };
+    load(0);
+    for (int k0 = 0; k0 < Kd; k0 += BK) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int r = xr + 16 * i;
+            float4 v = xv[i];
+            if (demod) v.x *= v.x, v.y *= v.y, v.z *= v.z, v.w *= v.w;
+            xs[xk][r] = v.x, xs[xk + 1][r] = v.y, xs[xk + 2][r] = v.z, xs[xk + 3][r] = v.w;
+            const int e = t + NT * i, nr = e >> 3, kq = (e & 7) * 4;
+            ws[kq][nr] = wv[i].x, ws[kq + 1][nr] = wv[i].y, ws[kq + 2][nr] = wv[i].z, ws[kq + 3][nr] = wv[i].w;
+        }
+        __syncthreads();
+        if (k0 + BK < Kd) load(k0 + BK);
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            const float a0 = xs[kk][ty], a1 = xs[kk][ty + 16];
+            const float4 b = *reinterpret_cast<const float4*>(&ws[kk][tx * 4]);
+            acc[0][0] = fmaf(a0, b.x, acc[0][0]), acc[0][1] = fmaf(a0, b.y, acc[0][1]), acc[0][2] = fmaf(a0, b.z, acc[0][2]), acc[0][3] = fmaf(a0, b.w, acc[0][3]);
+            acc[1][0] = fmaf(a1, b.x, acc[1][0]), acc[1][1] = fmaf(a1, b.y, acc[1][1]), acc[1][2] = fmaf(a1, b.z, acc[1][2]), acc[1][3] = fmaf(a1, b.w, acc[1][3]);
+        }
+        __syncthreads();
+    }
+    const int n = n0 + tx * 4;
+    if (n >= N) return;
+    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.bias) bv = *reinterpret_cast<const float4*>(p.bias + n);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int m = m0 + ty + 16 * i;
+        if (m >= M) continue;
+        float4 o = make_float4(acc[i][0] + bv.x, acc[i][1] + bv.y, acc[i][2] + bv.z, acc[i][3] + bv.w);
+        if (demod) o.x = rsqrtf(o.x + p.rsqrt_eps), o.y = rsqrtf(o.y + p.rsqrt_eps), o.z = rsqrtf(o.z + p.rsqrt_eps), o.w = rsqrtf(o.w + p.rsqrt_eps);
+        *reinterpret_cast<float4*>(p.y + (int64_t)m * N + n) = o;
+    }
+}
+
 // These GEMMs are bound by the serial chain of K chunks in one CTA, not by FLOPs: when the output tiles alone cannot fill the
 // GPU, K is cut into slices handled by different CTAs (deterministic: fixed slices, summed in a fixed order by a second
 // tiny kernel).  Returns the slice count; 1 = no split, no workspace.
@@ -213,4 +288,33 @@ extern "C" int e4s_demod_gemm_f32(const float* s, const float* wsq, float* demod
     const int kper = (int)(e4s_ceil_div(e4s_ceil_div(cin, ks), BK) * BK);
     LinParams p{s, wsq, nullptr, demod, rows, cout, cin, 0, 0, 0, (long long)rows * cout, 1.f, eps, ks, kper, workspace, 1};
     return launch_linear<false>(p, 1, (cudaStream_t)stream);
+}
+
+// Many independent small products in ONE launch per <= E4S_LINEAR_MULTI_MAX problems: y_i = x_i w_i^T + bias_i, or with
+// rsqrt_eps >= 0 the demodulation form y_i = rsqrt((x_i * x_i) w_i^T + rsqrt_eps).  `problems` is a HOST array (copied into the
+// kernel parameters; nothing is read from it after the call returns); the pointers inside are device pointers.
+extern "C" int e4s_linear_multi_f32(const E4sLinearProblem* problems, int nproblems, void* stream) {
+    E4S_REQUIRE(problems && nproblems > 0, E4S_ERR_ARG);
+    for (int i = 0; i < nproblems; ++i) {
+        const E4sLinearProblem& q = problems[i];
+        E4S_REQUIRE(q.x && q.w && q.y && q.m > 0 && q.n > 0 && q.k > 0 && q.ldx >= q.k, E4S_ERR_ARG);
+        E4S_REQUIRE((q.n % 4) == 0 && (q.k % 4) == 0 && (q.ldx % 4) == 0, E4S_ERR_SHAPE);
+        E4S_REQUIRE(e4s_aligned16(q.x) && e4s_aligned16(q.w) && e4s_aligned16(q.y) && (!q.bias || e4s_aligned16(q.bias)), E4S_ERR_ALIGN);
+    }
+    for (int first = 0; first < nproblems; first += E4S_LINEAR_MULTI_MAX) {
+        MultiParams mp;
+        mp.nprob = nproblems - first < E4S_LINEAR_MULTI_MAX ? nproblems - first : E4S_LINEAR_MULTI_MAX;
+        int64_t tiles = 0;
+        for (int i = 0; i < mp.nprob; ++i) {
+            mp.prob[i] = problems[first + i];
+            mp.tile0[i] = (int)tiles;
+            tiles += e4s_ceil_div(mp.prob[i].m, BM) * e4s_ceil_div(mp.prob[i].n, BN);
+            E4S_REQUIRE(tiles < (1ll << 30), E4S_ERR_SHAPE);
+        }
+        mp.tile0[mp.nprob] = (int)tiles;
+        linear_multi_kernel<<<(unsigned)tiles, NT, 0, (cudaStream_t)stream>>>(mp);
+        const int rc = e4s_launch_status();
+        if (rc) return rc;
+    }
+    return 0;
 }

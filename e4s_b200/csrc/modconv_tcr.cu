@@ -1009,11 +1009,13 @@ int dispatch(const void* w_hilo_bf16, Params p, int up, cudaStream_t st) {
     if (cin <= 64) {                 // small K: HBM-bound layers -> TMA-staged activations, 32-channel chunks
         if (!up) {
             if (cout % 128 == 0) return launch<128, 32, 1, true>(w_hilo_bf16, p, st);
-            // N <= 64: w_hi and w_lo stacked along N (STK) - two MMAs per (tap, K step); E4S_B200_STK=0 switches it off
+            // N = 32: w_hi and w_lo stacked along N (STK) - two MMAs per (tap, K step) instead of three: c15 2.25 -> 1.95 ms
+            // (the layer is bound by operand fetches from shared memory).  At N = 64 it is a wash (c13: 1.13 vs 1.15 ms:
+            // that layer is bound by re-streaming 147 KB of weights per tile), so only E4S_B200_STK=1 stacks there; =0: never.
             const char* fstk = getenv("E4S_B200_STK");
-            const bool stk = !(fstk && atoi(fstk) == 0);
-            if (cout % 64 == 0) return stk ? launch<64, 32, 1, true, false, true>(w_hilo_bf16, p, st) : launch<64, 32, 1, true>(w_hilo_bf16, p, st);
-            return stk ? launch<32, 32, 1, true, false, true>(w_hilo_bf16, p, st) : launch<32, 32, 1, true>(w_hilo_bf16, p, st);
+            const int stk = fstk ? atoi(fstk) : -1;
+            if (cout % 64 == 0) return stk == 1 ? launch<64, 32, 1, true, false, true>(w_hilo_bf16, p, st) : launch<64, 32, 1, true>(w_hilo_bf16, p, st);
+            return stk != 0 ? launch<32, 32, 1, true, false, true>(w_hilo_bf16, p, st) : launch<32, 32, 1, true>(w_hilo_bf16, p, st);
         }
         if (cout % 64 == 0) return launch<64, 32, 4, true>(w_hilo_bf16, p, st);
         return launch<32, 32, 4, true>(w_hilo_bf16, p, st);
@@ -1022,15 +1024,6 @@ int dispatch(const void* w_hilo_bf16, Params p, int up, cudaStream_t st) {
     // low-resolution 512-channel layers have a handful of pixel tiles, and wide N tiles left most SMs without work.
     const bool k64 = (cin % 64) == 0;
     const int64_t pixel_tiles = e4s_ceil_div(p.w, TW) * e4s_ceil_div(p.h, TH) * p.batch;
-    // Experimental (E4S_B200_XS=1): TMA-staged raw activation tiles + 32-channel chunks for the wide masked layers too.  With
-    // 225 KB of shared memory the L1 keeps ~30 KB: the 40-KB halo tile of a 64-channel chunk does not fit, so the nine
-    // row-class stagings of a mixed tile re-fetch it from L2; from shared memory they would not.
-    if (const char* f = getenv("E4S_B200_XS")) {
-        if (atoi(f) != 0 && p.label && cout % 128 == 0 && pixel_tiles * (cout / 128) >= num_sms() / 2) {
-            if (!up) return cout % 256 == 0 ? launch<256, 32, 1, true>(w_hilo_bf16, p, st) : launch<128, 32, 1, true>(w_hilo_bf16, p, st);
-            if (cin >= 128 && cout >= 256) return launch<256, 32, 1, true, true>(w_hilo_bf16, p, st);
-        }
-    }
     if (!up) {
         if (k64) {
             int nt = pick_ntile(cout, 256, pixel_tiles);

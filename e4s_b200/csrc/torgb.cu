@@ -95,7 +95,9 @@ __global__ void __launch_bounds__(256) torgb_kernel(TorgbParams p) {
     }
 }
 
-// Thread-per-pixel variant for the high-resolution layers (Cin <= 64): no cross-lane reduction, weights already
+// Thread-per-pixel variant for every layer whose styled weights fit 40 KB of shared memory (Cin <= 256 at 12 regions; the
+// warp-per-pixel kernel above ran the 256x256 / Cin = 128 layer at 0.51 ms for 0.54 GB - one pixel per warp and iteration
+// exposes the whole load -> shuffle tree -> store chain): no cross-lane reduction, weights already
 // multiplied by the region's style sit in shared memory as [cls][3][cin] (broadcast reads), planar stores are
 // coalesced because consecutive threads own consecutive pixels.
 __global__ void __launch_bounds__(256) torgb_pixel_kernel(TorgbParams p) {
@@ -185,7 +187,7 @@ extern "C" int e4s_torgb_fwd_f32(const float* x, const float* wrgb, const float*
     E4S_REQUIRE((size_t)(3 + ncls) * cin * sizeof(float) <= 200 * 1024, E4S_ERR_SHAPE);
     TorgbParams p{x, wrgb, s, label, bias, skip, fir4x4, out, batch, h, w, cin, ncls};
     cudaStream_t st = (cudaStream_t)stream;
-    if (cin <= 64 && (cin % 8) == 0 && (reinterpret_cast<uintptr_t>(x) & 31) == 0 &&
+    if (cin <= 256 && (cin % 8) == 0 && (reinterpret_cast<uintptr_t>(x) & 31) == 0 &&
         (size_t)ncls * 3 * cin * sizeof(float) <= 40 * 1024) {
         const int64_t hw = (int64_t)h * w;
         int64_t want = e4s_ceil_div(hw, 256), cap = e4s_ceil_div((int64_t)E4S_NUM_SMS * 16, batch);

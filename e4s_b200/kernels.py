@@ -8,6 +8,8 @@ from __future__ import annotations
 
 from typing import Optional
 
+import ctypes
+
 import torch
 
 from . import _lib
@@ -507,3 +509,20 @@ def linear(x: Tensor, w: Tensor, bias: Optional[Tensor] = None, act_slope: float
               m * k if x.ndim == 3 else 0, n * k if w.ndim == 3 else 0, (n if (bias is not None and bias.ndim == 2) else 0), m * n,
               int(w_is_kn), float(act_slope), ptr(ws), stream_ptr(), work=2.0 * groups * m * n * k)
     return y
+
+
+def linear_multi(problems) -> None:
+    """Many small products in one launch per 48 (e4s_linear_multi_f32): problems = [(x_ptr, ldx, w, bias | None, y, m, rsqrt_eps)]
+    with x_ptr an int device address of [m, k] fp32 rows ldx floats apart, w [n, k], y [m, n] contiguous fp32 tensors;
+    rsqrt_eps < 0: y = x w^T + bias, >= 0: y = rsqrt((x * x) w^T + eps)."""
+    arr = (_lib.LinearProblem * len(problems))()
+    work = 0.0
+    for q, (x_ptr, ldx, w, bias, y, m, eps) in zip(arr, problems):
+        n, k = w.shape
+        assert w.is_contiguous() and y.is_contiguous() and y.numel() == m * n and w.dtype == y.dtype == torch.float32
+        q.x, q.w, q.bias, q.y = x_ptr, w.data_ptr(), (0 if bias is None else bias.data_ptr()), y.data_ptr()
+        q.m, q.n, q.k, q.ldx, q.rsqrt_eps = m, n, k, ldx, eps
+        work += 2.0 * m * n * k
+    dev = problems[0][4].device
+    with torch.cuda.device(dev):
+        _call("e4s_linear_multi_f32", _lib.load().e4s_linear_multi_f32, ctypes.cast(arr, ctypes.c_void_p), len(problems), stream_ptr(), work=work)

@@ -224,6 +224,16 @@ def up_form(prep: "PreparedConv") -> str:
 
 
 # ================================================================================== autograd
+class PrecomputedStyle:
+    """Modulation output s = EqualLinear(style) [B, R, Cin] (and, for demodulated convs, demod [B, R, Cout]) computed ahead of
+    the layer: ``Generator.forward`` runs the modulations of ALL its layers as one launch and the demodulations as a second
+    (``kernels.linear_multi``) when no gradient is wanted, and hands each StyledConv / ToRGB one of these instead of a style."""
+    __slots__ = ("s", "dm")
+
+    def __init__(self, s: Tensor, dm: Optional[Tensor] = None):
+        self.s, self.dm = s, dm
+
+
 class LinearFn(Function):
     """y = leaky_relu(x @ w^T + bias, slope) on the library's small-GEMM kernel (csrc/linear.cu); w, bias are frozen prepared
     tensors (scale / lr_mul folded in), grouped [G, N, K] or shared [N, K] (kernels.linear).  Differentiable wrt x."""
@@ -247,8 +257,8 @@ class StyledConvFn(Function):
     """y = act(demod * conv(x*s) + noise_w*noise + bias) on pixel-major tensors; differentiable wrt x, s, noise."""
 
     @staticmethod
-    def forward(ctx, x_pm, s, noise, noise_w, bias, label, prep, up, demodulate, act):
-        dm = K.demod(s, prep.wsq) if demodulate else None
+    def forward(ctx, x_pm, s, noise, noise_w, bias, label, prep, up, demodulate, act, dm_pre=None):
+        dm = (dm_pre if dm_pre is not None else K.demod(s, prep.wsq)) if demodulate else None
         path = conv_path(prep, x_pm)
         if path == "tcr" and up and up_form(prep) == "h":
             y = K.modconv3x3_up_tch_fwd(x_pm, prep.v_hilo, prep.fx, s.contiguous(), dm, label, noise, noise_w, bias, act)

@@ -50,9 +50,9 @@ def save_for_styled_backward(ctx, x_pm, s, dm, noise, noise_w, bias, label, prep
 def styled_backward(ctx, gy):
     x_pm, s, dm, noise, noise_w, bias, label, y = ctx.saved_tensors
     prep, up, demodulate, act = ctx.cfg
-    none10 = [None] * 10
+    none11 = [None] * 11
     if gy is None:
-        return tuple(none10)
+        return tuple(none11)
     need_gx, need_gs, need_gn = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
     gy = gy.contiguous().float()
     s = s.contiguous()
@@ -74,8 +74,8 @@ def styled_backward(ctx, gy):
         gn = (gv.sum(-1) * noise_w).unsqueeze(1)
         if noise.shape[0] == 1 and gn.shape[0] != 1:
             gn = gn.sum(0, keepdim=True)
-    none10[0], none10[1], none10[2] = gx, gs, gn
-    return tuple(none10)
+    none11[0], none11[1], none11[2] = gx, gs, gn
+    return tuple(none11)
 
 
 def save_for_torgb_backward(ctx, x_pm, s, skip, label, prep, fir):

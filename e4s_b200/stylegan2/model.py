@@ -18,6 +18,7 @@ src/training/coach.py stays out of scope).
 from __future__ import annotations
 
 import math
+import os
 import random
 
 import torch
@@ -192,6 +193,9 @@ class ModulatedConv2d(nn.Module):
     def forward_regions(self, x_pm, styles, label, noise=None, noise_w=None, bias=None, act=False):
         """x_pm [B,H,W,Cin] pixel-major; styles [B, R, style_dim]; label [B,Ho,Wo] uint8 or None (R == 1)."""
         MC.warn_frozen(noise_w, bias)
+        if isinstance(styles, MC.PrecomputedStyle):                    # modulations of the whole network ran as one launch
+            return MC.StyledConvFn.apply(x_pm, styles.s, noise, noise_w, bias, label, self.prepared(), self.upsample,
+                                         self.demodulate, act, styles.dm)
         s = self.modulation(styles)                                    # [B, R, Cin]   (model.py:276)
         return MC.StyledConvFn.apply(x_pm, s, noise, noise_w, bias, label, self.prepared(), self.upsample,
                                      self.demodulate, act)
@@ -248,11 +252,12 @@ class StyledConv(nn.Module):
         x_pm = K.to_pixel_major(input)
         b, h, w, _ = x_pm.shape
         ho, wo = (2 * h, 2 * w) if self.conv.upsample else (h, w)
+        pre = isinstance(style, MC.PrecomputedStyle)
         if self.mask_op:
             label = MC.LabelPyramid.from_mask(mask).at(ho, wo)
             styles = style
         else:
-            label, styles = None, style.unsqueeze(1)
+            label, styles = None, (style if pre else style.unsqueeze(1))
         if noise is None:
             noise = x_pm.new_empty(b, 1, ho, wo).normal_()
         standard_act = (self.activate.negative_slope == 0.2 and abs(self.activate.scale - 2 ** 0.5) < 1e-12)
@@ -277,13 +282,14 @@ class ToRGB(nn.Module):
     def forward(self, input, style, mask, skip=None):
         x_pm = K.to_pixel_major(input)
         b, h, w, _ = x_pm.shape
+        pre = isinstance(style, MC.PrecomputedStyle)
         if self.mask_op:
             label = MC.LabelPyramid.from_mask(mask).at(h, w)
             styles = style
         else:
-            label, styles = None, style.unsqueeze(1)
+            label, styles = None, (style if pre else style.unsqueeze(1))
         MC.warn_frozen(self.bias)
-        s = self.conv.modulation(styles)
+        s = styles.s if pre else self.conv.modulation(styles)
         prep = self.conv.prepared()
         fuse_skip = (skip is not None and tuple(skip.shape[2:]) == (h // 2, w // 2) and h % 2 == 0 and w % 2 == 0
                      and tuple(self.upsample.kernel.shape) == (4, 4) and self.upsample.pad == (2, 1))
@@ -370,6 +376,60 @@ class Generator(nn.Module):
         second = styles[1].unsqueeze(1).repeat(1, self.n_latent - inject_index, 1)
         return torch.cat([first, second], 1)
 
+    def _schedule(self):
+        """[(module, latent index, per-region style?)] in execution order: which latent each layer of ``forward`` consumes
+        (reference model.py:639-657).  Per-region layers take latent[:, :, i] ([B, ncls, 512]), the others latent[:, 0, i]."""
+        K_ = self.remaining_layer_idx
+        sched = [(self.conv1, 0, True), (self.to_rgb1, 1, True)]
+        i = 1
+        for r, to_rgb in enumerate(self.to_rgbs):
+            up_conv, conv = self.convs[2 * r], self.convs[2 * r + 1]
+            if i < K_:
+                sched += [(up_conv, i, up_conv.mask_op), (conv, i + 1, conv.mask_op),
+                          (to_rgb, i + 2, to_rgb.mask_op if (K_ == 17 or i + 2 != K_) else False)]
+            else:
+                sched += [(up_conv, i, False), (conv, i + 1, False), (to_rgb, i + 2, False)]
+            i += 2
+        return sched
+
+    def _layer_styles(self, latent, sched):
+        """What each scheduled layer receives as its style.  Under grad mode with a latent that requires grad (inversion), or
+        with trainable modulations: the latent slices themselves (each layer runs its own differentiable EqualLinear).
+        Otherwise: every layer's modulation s = EqualLinear(style) in ONE launch and every demodulation rsqrt(s^2 Wsq^T + eps)
+        in a second (kernels.linear_multi reads the latent slices in place) instead of ~85 launches of 6-8 us."""
+        slices = [latent[:, :, idx] if per_region else latent[:, 0, idx] for _, idx, per_region in sched]
+        mods = [m.conv.modulation for m, _, _ in sched]
+        wants_grad = torch.is_grad_enabled() and (latent.requires_grad or any(p.requires_grad for m in mods for p in m.parameters()))
+        if (wants_grad or not latent.is_cuda or latent.dtype != torch.float32 or not latent.is_contiguous()
+                or os.environ.get("E4S_B200_STYLE_BATCH", "1") == "0"
+                or any(m.conv.in_channel % 4 or m.conv.out_channel % 4 for m, _, _ in sched if m.conv.kernel_size == 3)
+                or any(m.conv.in_channel % 4 for m, _, _ in sched)):
+            return slices
+        bsz, ncls, nlat, dim = latent.shape
+        rows = [bsz * ncls if per_region else bsz for _, _, per_region in sched]
+        cins = [m.conv.in_channel for m, _, _ in sched]
+        demods = [m.conv.out_channel if (m.conv.demodulate and m.conv.kernel_size == 3) else 0 for m, _, _ in sched]
+        s_all = latent.new_empty(sum(r * c for r, c in zip(rows, cins)))
+        d_all = latent.new_empty(sum(r * c for r, c in zip(rows, demods)))
+        base, esz = latent.data_ptr(), latent.element_size()
+        lin, dem, styles, so, do = [], [], [], 0, 0
+        for (m, idx, per_region), r, cin, cout in zip(sched, rows, cins, demods):
+            w, b = m.conv.modulation._frozen()
+            s = s_all[so:so + r * cin].view(bsz, r // bsz, cin)
+            so += r * cin
+            ldx = nlat * dim if per_region else ncls * nlat * dim
+            lin.append((base + idx * dim * esz, ldx, w, b, s, r, -1.0))
+            dm = None
+            if cout:
+                dm = d_all[do:do + r * cout].view(bsz, r // bsz, cout)
+                do += r * cout
+                dem.append((s.data_ptr(), cin, m.conv.prepared().wsq, None, dm, r, m.conv.eps))
+            styles.append(MC.PrecomputedStyle(s, dm))
+        K.linear_multi(lin)
+        if dem:
+            K.linear_multi(dem)
+        return styles
+
     def forward(self, styles, structure_feats, mask, return_latents=False, inject_index=None, truncation=1,
                 truncation_latent=None, input_is_latent=False, noise=None, randomize_noise=True,
                 use_structure_code=False):
@@ -388,31 +448,24 @@ class Generator(nn.Module):
 
         K_ = self.remaining_layer_idx
         regions = MC.LabelPyramid.from_mask(mask)            # one argmax + validation per forward
+        sched = self._schedule()
+        st = iter(self._layer_styles(latent, sched))
         out = self.input(latent)
-        out = self.conv1(out, latent[:, :, 0], regions, noise=noise[0])
-        skip = self.to_rgb1(out, latent[:, :, 1], regions)
+        out = self.conv1(out, next(st), regions, noise=noise[0])
+        skip = self.to_rgb1(out, next(st), regions)
         intermediate_feats = None
 
         i = 1
         for r, to_rgb in enumerate(self.to_rgbs):
             up_conv, conv = self.convs[2 * r], self.convs[2 * r + 1]
             n_up, n_conv = noise[1 + 2 * r], noise[2 + 2 * r]
-            if i < K_:
-                out = up_conv(out, latent[:, :, i] if up_conv.mask_op else latent[:, 0, i], regions, noise=n_up)
-                if i + 2 == self.split_layer_idx:
-                    if use_structure_code:
-                        out = structure_feats
-                    intermediate_feats = out
-                out = conv(out, latent[:, :, i + 1] if conv.mask_op else latent[:, 0, i + 1], regions, noise=n_conv)
-                if K_ == 17 or i + 2 != K_:
-                    rgb_style = latent[:, :, i + 2] if to_rgb.mask_op else latent[:, 0, i + 2]
-                else:
-                    rgb_style = latent[:, 0, i + 2]
-                skip = to_rgb(out, rgb_style, regions, skip)
-            else:
-                out = up_conv(out, latent[:, 0, i], regions, noise=n_up)
-                out = conv(out, latent[:, 0, i + 1], regions, noise=n_conv)
-                skip = to_rgb(out, latent[:, 0, i + 2], regions, skip)
+            out = up_conv(out, next(st), regions, noise=n_up)
+            if i < K_ and i + 2 == self.split_layer_idx:
+                if use_structure_code:
+                    out = structure_feats
+                intermediate_feats = out
+            out = conv(out, next(st), regions, noise=n_conv)
+            skip = to_rgb(out, next(st), regions, skip)
             i += 2
 
         image = skip

@@ -113,6 +113,24 @@ int e4s_demod_f32(const float* s, const float* wsq, float* demod, int rows, int 
 int e4s_demod_gemm_f32(const float* s, const float* wsq, float* demod, int rows, int cin, int cout, float eps, float* workspace,
                        void* stream);
 
+/* Many independent small fp32 products in ONE launch (csrc/linear.cu): the 26 EqualLinear style modulations of a synthesis
+ * forward (model.py:276, one per ModulatedConv2d) as one call, the 17 demodulation products (model.py:279-281) as a second.
+ *   rsqrt_eps <  0:  y = x w^T + bias            x: [m, k] rows ldx floats apart (a latent slice is read in place),
+ *   rsqrt_eps >= 0:  y = rsqrt((x*x) w^T + eps)  w: [n, k] (nn.Linear layout), bias: [n] | NULL, y: [m, n] contiguous.
+ * n, k, ldx multiples of 4; pointers 16-byte aligned.  `problems` is a HOST array of device pointers (copied into kernel
+ * parameters, E4S_LINEAR_MULTI_MAX per launch); K is never split, so the result is deterministic and needs no workspace. */
+typedef struct E4sLinearProblem {
+    const float* x;
+    const float* w;
+    const float* bias;
+    float* y;
+    int m, n, k, ldx;
+    float rsqrt_eps;
+    int reserved;
+} E4sLinearProblem;
+#define E4S_LINEAR_MULTI_MAX 48
+int e4s_linear_multi_f32(const E4sLinearProblem* problems, int nproblems, void* stream);
+
 /* Region-selected modulated 3x3 convolution with fused noise + bias + leaky-ReLU epilogue:
  * one call = one StyledConv.forward (model.py:382-406) for every region at once.
  *

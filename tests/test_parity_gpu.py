@@ -209,7 +209,7 @@ def test_styled_conv_and_torgb_vs_oracle(kind):
         with torch.no_grad():
             y = m.to(DEV)(cu(x), cu(codes[:, :, 0]), cu(mask), noise=cu(nz))
         assert_close(y, O.styled_conv(x, codes[:, :, 0], mask, nz, st, "", up, True), 1e-5, f"{kind}/{tag}")
-    for cin in (24, 48, 136):
+    for cin in (24, 48, 128, 136, 256, 512):      # thread-per-pixel kernel up to 256 channels, warp-per-pixel beyond
         m = ToRGB(cin, 512, upsample=True, mask_op=True)
         st = _load(m, 11)
         x = torch.randn(2, cin, 16, 16, generator=g)
@@ -617,22 +617,6 @@ def test_tcr_kernel_stacked_hilo_weights(monkeypatch, stk, b, cin, cout, hw, up,
     assert_close(out, ref, 1e-4, f"tcr (STK={stk}) vs simt {b},{cin},{cout},{hw},{ncls},{kind}")
 
 
-@pytest.mark.parametrize("b,cin,cout,hw,up,ncls,kind", [
-    (2, 512, 512, 24, False, 12, "blobs"),    # wide masked plain layer on TMA-staged 32-channel chunks
-    (2, 256, 128, 28, False, 5, "iid"),
-    (2, 512, 256, 20, True, 12, "blobs"),     # parity work items on TMA-staged chunks
-])
-def test_tcr_kernel_xs_mode_for_wide_masked_layers(monkeypatch, b, cin, cout, hw, up, ncls, kind):
-    """E4S_B200_XS=1 (experimental): raw activation tiles by TMA + 32-channel chunks for Cin > 64 masked layers."""
-    monkeypatch.setenv("E4S_B200_XS", "1")
-    monkeypatch.setenv("E4S_B200_UPFORM", "poly")
-    K, prep, x, args = _tc_case(b, cin, cout, hw, up, ncls, kind, seed=cin + cout + hw)
-    ref = K.modconv3x3_fwd(x, prep.wt, *args)
-    out = K.modconv3x3_tcr_fwd(x, prep.w_hilo, *args)
-    torch.cuda.synchronize()
-    assert_close(out, ref, 1e-4, f"tcr (XS=1) vs simt {b},{cin},{cout},{hw},{up},{ncls},{kind}")
-
-
 @pytest.mark.parametrize("b,cin,cout,hw,up,ncls,kind", PRODUCTION_CASES)
 def test_tcr_kernel_production_shapes(b, cin, cout, hw, up, ncls, kind):
     K, prep, x, args = _tc_case(b, cin, cout, hw, up, ncls, kind, seed=cin + cout + hw)
@@ -743,6 +727,102 @@ def test_dcodes_gradient_default_kernels_256():
     cos = float(torch.dot(a, b) / (a.norm() * b.norm()))
     print(f"dcodes @256, default kernels: rel-L2 {rel_l2:.2e}, cosine {cos:.7f}")
     assert rel_l2 < 1e-2 and cos > 0.9999, (rel_l2, cos)
+
+
+def test_linear_multi_strided_rows_and_demod_form():
+    """e4s_linear_multi_f32: problems of different shapes in one launch, x rows read in place from a strided latent slice, plain
+    and demodulation forms, against fp64."""
+    from e4s_b200 import kernels as K
+    g = torch.Generator().manual_seed(5)
+    latent = cu(torch.randn(3, 4, 6, 64, generator=g))                           # [B, ncls, n_latent, dim]
+    shapes = [(1, True, 96), (4, True, 32), (2, False, 64), (5, False, 36)]      # (latent index, per-region rows?, N)
+    probs, refs = [], []
+    for idx, per_region, n in shapes:
+        w = cu(torch.randn(n, 64, generator=g) / 8)
+        b = cu(torch.randn(n, generator=g))
+        rows = 12 if per_region else 3
+        y = torch.empty(rows, n, device=DEV)
+        x = latent[:, :, idx] if per_region else latent[:, 0, idx]
+        probs.append((latent.data_ptr() + idx * 64 * 4, 6 * 64 if per_region else 4 * 6 * 64, w, b, y, rows, -1.0))
+        refs.append((x.reshape(rows, 64).double() @ w.double().t() + b.double()).float())
+    K.linear_multi(probs)
+    dem = []
+    for (_, _, _, _, y, rows, _), n in zip(probs, [s[2] for s in shapes]):
+        wsq = cu(torch.rand(40, n, generator=g) / n)
+        d = torch.empty(rows, 40, device=DEV)
+        dem.append((y.data_ptr(), n, wsq, None, d, rows, 1e-8))
+    K.linear_multi(dem)
+    torch.cuda.synchronize()
+    for (q, ref, dq) in zip(probs, refs, dem):
+        assert_close(q[4], ref, 1e-5, "linear_multi plain")
+        assert_close(dq[4], torch.rsqrt(ref.double().pow(2) @ dq[2].double().t() + 1e-8).float(), 1e-5, "linear_multi demod form")
+    many = [(latent.data_ptr(), 64, probs[0][2], None, torch.empty(72, 96, device=DEV), 72, -1.0) for _ in range(101)]   # > 48: several launches
+    K.linear_multi(many)
+    ref = (latent.reshape(72, 64).double() @ probs[0][2].double().t()).float()
+    for q in (many[0], many[47], many[48], many[100]):
+        assert_close(q[4], ref, 1e-5, "linear_multi > 48 problems")
+
+
+def test_generator_batched_modulations_equal_per_layer_modulations(monkeypatch):
+    """Generator.forward without gradients computes all style modulations in one launch and all demodulations in a second
+    (model.py:_layer_styles); E4S_B200_STYLE_BATCH=0 keeps one EqualLinear + one demod launch per layer.  Same image."""
+    G, _ = _generator(64, 13)
+    codes, mask, _, noise = O.synthetic_inputs(3, 12, 64, 128, seed=8, kind="blobs")
+    args = ([cu(codes)], None, cu(mask))
+    kw = dict(input_is_latent=True, noise=[cu(n) for n in noise])
+    from e4s_b200 import kernels as K
+    with torch.no_grad():
+        K.LaunchStats.reset()
+        a, _, fa = G(*args, **kw)
+        batched = K.LaunchStats.launches
+        monkeypatch.setenv("E4S_B200_STYLE_BATCH", "0")
+        K.LaunchStats.reset()
+        b, _, fb = G(*args, **kw)
+        per_layer = K.LaunchStats.launches
+    assert batched < per_layer - 20, (batched, per_layer)
+    assert_close(a, b, 1e-5, "batched vs per-layer modulations: image")
+    assert_close(fa, fb, 1e-5, "batched vs per-layer modulations: feats")
+    monkeypatch.delenv("E4S_B200_STYLE_BATCH")
+    c = cu(codes).requires_grad_(True)                  # gradients wanted: the differentiable per-layer path
+    img, _, _ = G([c], None, cu(mask), **kw)
+    img.square().mean().backward()
+    assert c.grad is not None and torch.isfinite(c.grad).all() and float(c.grad.abs().max()) > 0
+
+
+def test_graphed_synthesis_equals_eager_and_draws_fresh_noise():
+    """e4s_b200.pipeline.GraphedSynthesis: the forward of one batch shape as a CUDA graph.  With fixed noise buffers a replay
+    equals the eager forward, for the inputs of the CALL (not of the capture); with randomize_noise every replay
+    draws new noise maps."""
+    from types import SimpleNamespace
+    from e4s_b200.networks import Net3
+    from e4s_b200.pipeline import GraphedSynthesis, SynthesisPipeline
+    from e4s_b200.stylegan2.modconv import LabelPyramid
+    from e4s_b200.synthetic import load_synthetic
+    opts = SimpleNamespace(num_seg_cls=6, remaining_layer_idx=13, out_size=64, train_G=False, start_from_latent_avg=False,
+                           learn_in_w=False, fsencoder_type="psp")
+    net = Net3(opts).eval()
+    load_synthetic(net.G, salt=3)
+    net = net.to(DEV)
+    g = torch.Generator().manual_seed(12)
+    synth = GraphedSynthesis(net, 6, (2, 6, 18, 512), (2, 1, 128, 128), randomize_noise=False)
+    for trial in range(2):
+        codes = cu(torch.randn(2, 6, 18, 512, generator=g))
+        labels = cu(torch.randint(0, 6, (2, 1, 128, 128), generator=g).to(torch.uint8))
+        with torch.no_grad():
+            ref = net.gen_img(None, codes, LabelPyramid(labels[:, 0], 6), randomize_noise=False)[0]
+        out = synth(codes, labels)
+        assert_close(out, ref, 1e-5, f"replay {trial} vs the eager forward")     # (MMA warps race: equal to fp32 rounding)
+    fresh = GraphedSynthesis(net, 6, (2, 6, 18, 512), (2, 1, 128, 128))
+    a = fresh(codes, labels).clone()
+    b = fresh(codes, labels).clone()
+    assert not torch.equal(a, b), "randomize_noise: two replays must not share their noise maps"
+    assert torch.isfinite(a).all() and torch.isfinite(b).all()
+    with pytest.raises(RuntimeError):
+        fresh(codes[:1], labels[:1])
+    pipe = SynthesisPipeline(net, 6, depth=2, cuda_graph=True)
+    t = pipe.submit(codes.cpu().pin_memory(), labels.cpu().pin_memory())
+    img = pipe.result(t)
+    assert tuple(img.shape) == (2, 3, 64, 64) and torch.isfinite(img).all()
 
 
 def test_demod_gemm_form_equals_reference_formula():
