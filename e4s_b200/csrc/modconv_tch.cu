@@ -343,26 +343,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) modconv3x3_up_tch_kernel(const
                         const float4 s0 = __ldg(reinterpret_cast<const float4*>(sc + ch));
                         const float4 s1 = __ldg(reinterpret_cast<const float4*>(sc + ch + 4));
                         TCH_WAIT(smem_u32(&bars[A_EMPTY + sa]), pa ^ 1, 1);
-                        uint8_t* hi_plane = a_buf + sa * A_STAGE;
-                        uint8_t* lo_plane = hi_plane + A_PLANE;
+                        const uint32_t hi_plane = smem_u32(a_buf) + (uint32_t)sa * A_STAGE, lo_plane = hi_plane + A_PLANE;
 #pragma unroll
                         for (int i = 0; i < NSW; ++i) {
                             const int hp = pix0 + PPS * i;
                             if (hp >= 160) continue;
                             const int row = hp + 1;
-                            const float f[8] = {v0[i].x * s0.x, v0[i].y * s0.y, v0[i].z * s0.z, v0[i].w * s0.w,
-                                                v1[i].x * s1.x, v1[i].y * s1.y, v1[i].z * s1.z, v1[i].w * s1.w};
-                            uint32_t hi[4], lo[4];
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const float h0 = bf16_round(f[2 * j]), h1 = bf16_round(f[2 * j + 1]);
-                                hi[j] = pack_bf16x2(h0, h1);
-                                lo[j] = pack_bf16x2(f[2 * j] - h0, f[2 * j + 1] - h1);
-                            }
                             const uint32_t sx = KC == 64 ? (uint32_t)(row & 7) : (uint32_t)((row >> 1) & 3);
                             const uint32_t off = (uint32_t)row * ROWB + (((uint32_t)c8 ^ sx) << 4);
-                            *reinterpret_cast<uint4*>(hi_plane + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                            *reinterpret_cast<uint4*>(lo_plane + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                            scale_split_store8(v0[i], v1[i], s0, s1, s0, s1, false, hi_plane + off, lo_plane + off);
                         }
                         fence_proxy_async();
                         mbar_arrive(smem_u32(&bars[A_FULL + sa]));

@@ -586,30 +586,16 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                     const float4 t0 = sh ? __ldg(reinterpret_cast<const float4*>(sh + ch)) : zero4;
                     const float4 t1 = sh ? __ldg(reinterpret_cast<const float4*>(sh + ch + 4)) : zero4;
                     MBAR_WAIT_P(smem_u32(&bars[A_EMPTY + sa]), pa ^ 1, 2);
-                    uint8_t* hi_plane = a_buf + sa * A_STAGE;
-                    uint8_t* lo_plane = hi_plane + A_PLANE;
+                    const uint32_t hi_plane = smem_u32(a_buf) + (uint32_t)sa * A_STAGE, lo_plane = hi_plane + A_PLANE;
 #pragma unroll
                     for (int i = 0; i < NSW_SHIFT; ++i) {
                         const int hp = pix0 + PPS * i;
                         if (hp >= 160) continue;
                         const int row = hp + 1;
-                        float f[8] = {v0[i].x * s0.x, v0[i].y * s0.y, v0[i].z * s0.z, v0[i].w * s0.w,
-                                      v1[i].x * s1.x, v1[i].y * s1.y, v1[i].z * s1.z, v1[i].w * s1.w};
-                        if (sh && inb[i]) {      // zero padding applies to the NORMALISED tensor: shift in-image pixels only
-                            f[0] += t0.x, f[1] += t0.y, f[2] += t0.z, f[3] += t0.w;
-                            f[4] += t1.x, f[5] += t1.y, f[6] += t1.z, f[7] += t1.w;
-                        }
-                        uint32_t hi[4], lo[4];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float h0 = bf16_round(f[2 * j]), h1 = bf16_round(f[2 * j + 1]);
-                            hi[j] = pack_bf16x2(h0, h1);
-                            lo[j] = pack_bf16x2(f[2 * j] - h0, f[2 * j + 1] - h1);
-                        }
+                        // zero padding applies to the NORMALISED tensor: shift in-image pixels only
                         const uint32_t sx = KC == 64 ? (uint32_t)(row & 7) : (uint32_t)((row >> 1) & 3);
                         const uint32_t off = (uint32_t)row * ROWB + (((uint32_t)c8 ^ sx) << 4);
-                        *reinterpret_cast<uint4*>(hi_plane + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                        *reinterpret_cast<uint4*>(lo_plane + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                        scale_split_store8(v0[i], v1[i], s0, s1, t0, t1, sh && inb[i], hi_plane + off, lo_plane + off);
                     }
                     fence_proxy_async();
                     mbar_arrive(smem_u32(&bars[A_FULL + sa]));
@@ -652,6 +638,7 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                             __ldg(reinterpret_cast<const float4*>(sbase + (int64_t)c * p.cin + kc * KC + 4 * j));
                     }
                     xform_barrier();
+                    const uint32_t tab_s = smem_u32(tab);
                     const int ch = kc * KC + 8 * c8;
                     if (XS) MBAR_WAIT_P(smem_u32(&bars[XS_FULL + xstage]), px, 1);
                     const uint32_t xs = smem_u32(xs_buf + xstage * XS_STAGE);
@@ -677,27 +664,15 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
 #pragma unroll
                         for (int q = 0; q < NPH; ++q) {
                             MBAR_WAIT_P(smem_u32(&bars[A_EMPTY + sa]), pa ^ 1, 2);
-                            uint8_t* hi_plane = a_buf + sa * A_STAGE;
-                            uint8_t* lo_plane = hi_plane + A_PLANE;
+                            const uint32_t hi_plane = smem_u32(a_buf) + (uint32_t)sa * A_STAGE, lo_plane = hi_plane + A_PLANE;
 #pragma unroll
                             for (int i = 0; i < NSW_ROWS; ++i) {
                                 const int r = pix0 + PPS * i;
-                                const int cl = (int)((rcls[i] >> (8 * q)) & 0xffu);
-                                const float4 s0 = *reinterpret_cast<const float4*>(tab + cl * KC + 8 * c8);
-                                const float4 s1 = *reinterpret_cast<const float4*>(tab + cl * KC + 8 * c8 + 4);
-                                float f[8] = {v0[i].x * s0.x, v0[i].y * s0.y, v0[i].z * s0.z, v0[i].w * s0.w,
-                                              v1[i].x * s1.x, v1[i].y * s1.y, v1[i].z * s1.z, v1[i].w * s1.w};
-                                uint32_t hi[4], lo[4];
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    const float h0 = bf16_round(f[2 * j]), h1 = bf16_round(f[2 * j + 1]);
-                                    hi[j] = pack_bf16x2(h0, h1);
-                                    lo[j] = pack_bf16x2(f[2 * j] - h0, f[2 * j + 1] - h1);
-                                }
+                                const uint32_t cl = (rcls[i] >> (8 * q)) & 0xffu;
+                                const float4 s0 = lds_f4(tab_s + (cl * KC + 8 * c8) * 4), s1 = lds_f4(tab_s + (cl * KC + 8 * c8) * 4 + 16);
                                 const uint32_t sx = KC == 64 ? (uint32_t)(r & 7) : (uint32_t)((r >> 1) & 3);
                                 const uint32_t off = (uint32_t)r * ROWB + (((uint32_t)c8 ^ sx) << 4);
-                                *reinterpret_cast<uint4*>(hi_plane + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                                *reinterpret_cast<uint4*>(lo_plane + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                                scale_split_store8(v0[i], v1[i], s0, s1, s0, s1, false, hi_plane + off, lo_plane + off);
                             }
                             fence_proxy_async();
                             mbar_arrive(smem_u32(&bars[A_FULL + sa]));

@@ -14,6 +14,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_n(uint32_t bar, uint32_t count) {      // one thread arrives for `count` threads
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
@@ -161,4 +164,33 @@ __device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
     return d;
 }
 
+__device__ __forceinline__ void sts_u4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// Two fp32 values (packed) -> their bf16 roundings (hi, element 0 in the low half) and the bf16 roundings of the residuals
+// (lo): the split-precision operand pair, six instructions per pair (F2FP, SHL, LOP, FFMA2, F2FP + the producer's FMUL2)
+// instead of ten with scalar converts (F2F, IMAD.U32, FADD per element).  Bit-identical to bf16_round / f - h.
+__device__ __forceinline__ void split_pair(uint64_t f, uint32_t& hi, uint32_t& lo) {
+    float a, b;
+    upk2(f, a, b);
+    hi = pack_bf16x2(a, b);
+    const uint64_t r = fma2(pk2u(hi << 16, hi & 0xffff0000u), pk2(-1.f, -1.f), f);      // f - h, exact
+    upk2(r, a, b);
+    lo = pack_bf16x2(a, b);
+}
+// Eight channels of one operand row: v * s (+ t) -> hi / lo planes (one 16-byte shared-memory store each).
+__device__ __forceinline__ void scale_split_store8(const float4& v0, const float4& v1, const float4& s0, const float4& s1,
+                                                   const float4& t0, const float4& t1, bool shift, uint32_t hi_addr, uint32_t lo_addr) {
+    uint64_t f[4] = {mul2(pk2(v0.x, v0.y), pk2(s0.x, s0.y)), mul2(pk2(v0.z, v0.w), pk2(s0.z, s0.w)),
+                     mul2(pk2(v1.x, v1.y), pk2(s1.x, s1.y)), mul2(pk2(v1.z, v1.w), pk2(s1.z, s1.w))};
+    if (shift) {
+        f[0] = add2(f[0], pk2(t0.x, t0.y)), f[1] = add2(f[1], pk2(t0.z, t0.w));
+        f[2] = add2(f[2], pk2(t1.x, t1.y)), f[3] = add2(f[3], pk2(t1.z, t1.w));
+    }
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) split_pair(f[j], hi[j], lo[j]);
+    sts_u4(hi_addr, hi[0], hi[1], hi[2], hi[3]);
+    sts_u4(lo_addr, lo[0], lo[1], lo[2], lo[3]);
+}
 }  // namespace tcx
