@@ -627,6 +627,24 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                                       ((uint32_t)min((int)lp[wo + 1], p.ncls - 1) << 24);
                     }
                 }
+                // my rows' halo origin (element offset inside the image; h * w * cin < 2^31 is checked on the host) and which of
+                // the nine taps stay inside the image: computed once per tile - recomputing the 64-bit index and the bounds per
+                // (tap, row) was ~110 of the 262 instructions a tap costs a thread, and the transform bounds mixed tiles
+                int roff[NSW_ROWS];
+                uint32_t vmask[NSW_ROWS];
+#pragma unroll
+                for (int i = 0; i < NSW_ROWS; ++i) {
+                    const int r = pix0 + PPS * i;
+                    const int gy0 = y0 - 1 + (r >> 4), gx0 = x0 - 1 + (r & 15);
+                    roff[i] = (gy0 * p.w + gx0) * p.cin + 8 * c8;
+                    uint32_t m = 0;
+#pragma unroll
+                    for (int tp = 0; tp < 9; ++tp) {
+                        const int gy = gy0 + tp / 3, gx = gx0 + tp % 3;
+                        m |= (gy >= 0 && gy < p.h && gx >= 0 && gx < p.w) ? (1u << tp) : 0u;
+                    }
+                    vmask[i] = m;
+                }
                 const float* sbase = p.s + (int64_t)item.b * p.ncls * p.cin;
                 for (int kc = 0; kc < nchunks; ++kc) {
                     // styles of every region for this chunk -> shared table (double-buffered across chunks)
@@ -642,25 +660,26 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                     const int ch = kc * KC + 8 * c8;
                     if (XS) MBAR_WAIT_P(smem_u32(&bars[XS_FULL + xstage]), px, 1);
                     const uint32_t xs = smem_u32(xs_buf + xstage * XS_STAGE);
+                    const float* xc = xb + kc * KC;
+                    int toff = 0, thp = 0;               // (dy * w + dx) * cin and dy * 16 + dx of the running tap
 #pragma unroll 1
-                    for (int tap = 0; tap < 9; ++tap) {
-                        const int dy = tap / 3, dx = tap - 3 * dy;
+                    for (int tap = 0, dx = 0; tap < 9; ++tap) {
                         float4 v0[NSW_ROWS], v1[NSW_ROWS];
 #pragma unroll
                         for (int i = 0; i < NSW_ROWS; ++i) {
-                            const int r = pix0 + PPS * i;
-                            const int gy = y0 - 1 + (r >> 4) + dy, gx = x0 - 1 + (r & 15) + dx;
                             v0[i] = make_float4(0.f, 0.f, 0.f, 0.f), v1[i] = v0[i];
                             if (XS) {
-                                const int hp = min(((r >> 4) + dy) * 16 + (r & 15) + dx, 159);
+                                const int hp = min(pix0 + PPS * i + thp, 159);
                                 v0[i] = lds_f4(xs + (uint32_t)(hp * 128 + 32 * c8));
                                 v1[i] = lds_f4(xs + (uint32_t)(hp * 128 + 32 * c8 + 16));
-                            } else if (gy >= 0 && gy < p.h && gx >= 0 && gx < p.w) {
-                                const float* src = xb + ((int64_t)gy * p.w + gx) * p.cin + ch;
+                            } else if ((vmask[i] >> tap) & 1u) {
+                                const float* src = xc + (roff[i] + toff);
                                 v0[i] = __ldg(reinterpret_cast<const float4*>(src));
                                 v1[i] = __ldg(reinterpret_cast<const float4*>(src + 4));
                             }
                         }
+                        if (++dx == 3) dx = 0, toff += (p.w - 2) * p.cin, thp += 14;
+                        else toff += p.cin, thp += 1;
 #pragma unroll
                         for (int q = 0; q < NPH; ++q) {
                             MBAR_WAIT_P(smem_u32(&bars[A_EMPTY + sa]), pa ^ 1, 2);
@@ -1050,6 +1069,7 @@ extern "C" int e4s_modconv3x3_tcr_fwd(const float* x, const void* w_hilo_bf16, c
     E4S_REQUIRE(x && w_hilo_bf16 && s && y, E4S_ERR_ARG);
     E4S_REQUIRE(batch > 0 && h > 0 && w > 0 && cin > 0 && cout > 0 && ncls > 0 && ncls <= 32, E4S_ERR_ARG);
     E4S_REQUIRE((cin % 32) == 0 && (cout % 32) == 0, E4S_ERR_SHAPE);
+    E4S_REQUIRE((int64_t)h * w * cin < (1ll << 31), E4S_ERR_SHAPE);      // per-image element offsets are 32-bit in the transform
     E4S_REQUIRE(label || ncls == 1, E4S_ERR_ARG);
     E4S_REQUIRE(!noise || (noise_w && (noise_b == 1 || noise_b == batch)), E4S_ERR_ARG);
     E4S_REQUIRE(e4s_aligned16(x) && e4s_aligned16(w_hilo_bf16) && e4s_aligned16(s) && e4s_aligned16(y) &&
