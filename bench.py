@@ -629,11 +629,24 @@ def run_ours(args):
                         crit.set_target(target)
                     r1.record()
                     barrier()
+                # the loss networks with cuDNN's TF32 convolutions: what torch (and so the reference's script) runs by default
+                tf32_ms = None
+                try:
+                    crit.exact = False
+                    invert(net, target, onehot1, style_vectors=sv, steps=6, criterion=crit, cuda_graph=True)
+                    barrier()
+                    tstats = {}
+                    invert(net, target, onehot1, style_vectors=sv, steps=40, criterion=crit, cuda_graph=True, stats=tstats)
+                    barrier()
+                    tf32_ms = tstats.get("replay_ms_per_step")
+                finally:
+                    crit.exact = True
                 full_loss = {"lambdas": {"id": 0.1, "l2": 1.0, "lpips": 0.8, "face_parsing": 0.1}, "ms_per_step_eager": lms,
+                             "ms_per_replayed_step_tf32_loss_networks": tf32_ms,
                              "ms_per_replayed_step": qstats.get("replay_ms_per_step"), "ms_total_100_steps": qtot,
                              "faces_per_sec_100_steps": world / (qtot * 1e-3), "loss_first": float(qhist[0]), "loss_last": float(qhist[-1]),
                              "target_feature_pass_ms": r0.elapsed_time(r1) / 5,
-                             "note": "loss networks = library convolutions (cuDNN, fp32); target-image features cached once per face - the "
+                             "note": "loss networks = library convolutions (cuDNN; exact fp32 = InversionLoss's default, TF32 = torch's); target-image features cached once per face - the "
                                      "reference recomputes them every step (target_feature_pass_ms each); seeded stand-in weights"}
                 del crit
             except Exception as exc:                                  # reported, never hidden

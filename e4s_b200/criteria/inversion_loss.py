@@ -101,6 +101,11 @@ class InversionLoss(nn.Module):
             p.requires_grad = False
         self._target = None
 
+    def conv_precision(self):
+        """Context for code that differentiates through this loss (``loss.backward()``): the backward convolutions of the three
+        networks must run at the same precision as their forward ones (e4s_b200.optimization.invert enters it)."""
+        return conv_precision(self.exact)
+
     # -------------------------------------------------------------------------------------------------- features
     def _views(self, img: torch.Tensor):
         """The inputs the three networks start from: the LPIPS pyramid and, where a level already is the 512 / 256 pooling the

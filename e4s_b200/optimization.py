@@ -14,6 +14,7 @@ of being recomputed every step).  Without a criterion the loop uses the l2 term 
 from __future__ import annotations
 
 from functools import partial
+import contextlib
 from typing import Callable, List, Optional, Sequence, Tuple
 
 import torch
@@ -69,12 +70,21 @@ def invert(net, target: torch.Tensor, onehot: torch.Tensor, style_vectors: Optio
         codes = net.cal_style_codes(latent)
         recon, _, _ = net.gen_img(None, codes, onehot, noise=noise) if noise is not None else net.gen_img(None, codes, onehot)
         loss = _loss(recon, target, l2_lambda, extra_losses, criterion)
-        loss.backward()
+        with _precision(criterion):
+            loss.backward()
         opt.step()
         history.append(loss.detach())
         if callback is not None:
             callback(step, loss, recon, latent)
     return latent.detach(), recon.detach(), history
+
+
+def _precision(criterion):
+    """The cuDNN precision context of the criterion's networks (InversionLoss.exact) - their BACKWARD convolutions run inside
+    loss.backward(), outside the criterion's own forward, and must see the same setting."""
+    if criterion is not None and hasattr(criterion, "conv_precision"):
+        return criterion.conv_precision()
+    return contextlib.nullcontext()
 
 
 def _loss(recon, target, l2_lambda, extra_losses, criterion):
@@ -102,7 +112,8 @@ def _invert_graphed(net, target, onehot, style_vectors, steps, lr, l2_lambda, ex
         codes = net.cal_style_codes(latent)
         recon, _, _ = net.gen_img(None, codes, onehot, noise=noise) if noise is not None else net.gen_img(None, codes, onehot)
         loss = _loss(recon, target, l2_lambda, extra_losses, criterion)
-        loss.backward()
+        with _precision(criterion):
+            loss.backward()
         opt.step()
         static_loss.copy_(loss.detach())
         static_recon.copy_(recon.detach())

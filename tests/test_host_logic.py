@@ -211,3 +211,30 @@ def test_fold_upsample_vertical_equals_convT_blur():
         ref = O.upfirdn2d(u, fir, pad=(1, 1))[0]
         assert float((out - ref.double()).abs().max() / ref.abs().max()) < 1e-5
     assert fold_upsample_vertical(w, torch.randn(4, 4, generator=g)) is None      # not separable -> polyphase form
+
+
+@pytest.mark.parametrize("size,K", [(64, 5), (256, 13), (1024, 13), (256, 17)])
+def test_generator_style_schedule_follows_the_reference_latent_indexing(size, K):
+    """Generator._schedule (what the batched modulation launch is built from) = the latent index and the per-region / global
+    choice the reference's forward makes layer by layer (model.py:639-657): conv1 <- 0, to_rgb1 <- 1, then per resolution
+    (up conv, conv, to_rgb) <- (i, i + 1, i + 2) with i = 1, 3, 5, ...; per-region styles while i < K on masked layers."""
+    from e4s_b200.stylegan2.model import Generator
+    G = Generator(size, 512, 8, split_layer_idx=5, remaining_layer_idx=K)
+    sched = G._schedule()
+    assert len(sched) == 2 + 3 * len(G.to_rgbs) and [s[1] for s in sched[:2]] == [0, 1] and all(s[2] for s in sched[:2])
+    assert sched[0][0] is G.conv1 and sched[1][0] is G.to_rgb1
+    i = 1
+    for r, to_rgb in enumerate(G.to_rgbs):
+        up, conv, rgb = sched[2 + 3 * r: 5 + 3 * r]
+        assert (up[0], conv[0], rgb[0]) == (G.convs[2 * r], G.convs[2 * r + 1], to_rgb)
+        assert (up[1], conv[1], rgb[1]) == (i, i + 1, i + 2)
+        if i < K:
+            assert up[2] == G.convs[2 * r].mask_op and conv[2] == G.convs[2 * r + 1].mask_op
+            assert rgb[2] == (to_rgb.mask_op if (K == 17 or i + 2 != K) else False)
+        else:
+            assert not (up[2] or conv[2] or rgb[2])
+        # a layer that receives per-region styles must be a masked layer (its kernel indexes the styles by label)
+        for mod, _, per_region in (up, conv, rgb):
+            assert mod.mask_op or not per_region
+        i += 2
+    assert i + 1 == G.n_latent
