@@ -368,7 +368,15 @@ def run_ours(args):
     # inputs resident in HBM are copied device-to-device into the graph's static buffers inside the timed region
     from e4s_b200.pipeline import SynthesisPipeline, GraphedSynthesis
     labels_dev = labels_host.to(dev)
-    synth = None if args.eager else GraphedSynthesis(net, ncls, codes_dev.shape, labels_dev.shape, dev)
+    synth, graph_error = None, None
+    if not args.eager:
+        try:
+            synth = GraphedSynthesis(net, ncls, codes_dev.shape, labels_dev.shape, dev)
+        except Exception as exc:                          # reported in the line (config.execution), never hidden: time eager launches
+            graph_error = repr(exc)[:300]
+            print(f"bench.py: CUDA-graph capture of the forward failed, timing eager launches instead: {graph_error}", file=sys.stderr)
+            args.eager = True
+            torch.cuda.synchronize()
 
     def step_graph():
         img = synth(codes_dev, labels_dev)
@@ -774,7 +782,7 @@ def run_ours(args):
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": f"{size}x{size} synthesis, batch {B} per GPU, {ncls} regions, K=13 (BASELINE configs[1])",
                            "global_batch": B * world, "mask": args.mask, "noise": "fresh N(0,1) per layer per step",
-                           "execution": "eager launches (Net3.gen_img)" if args.eager else
+                           "execution": ("eager launches (Net3.gen_img)" + (f"; graph capture failed: {graph_error}" if graph_error else "")) if args.eager else
                                         "one CUDA-graph replay per step (e4s_b200.pipeline.GraphedSynthesis; codes + label maps copied into its static buffers every step)",
                            "l2": "activations per layer (>= 0.5 GB at the top resolutions) exceed the 126 MB L2; no flush needed",
                            "parallelism": (f"dp{world}: faces sharded across ranks, weights replicated, no data-path collective"
