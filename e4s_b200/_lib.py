@@ -38,7 +38,7 @@ SIGNATURES = {
     "e4s_modconv3x3_fwd_f32": [P] * 9 + [c_int] * 9 + [P],
     "e4s_modconv3x3_tcr_fwd": [P] * 9 + [c_int] * 9 + [P],
     "e4s_modconv3x3_up_tch_fwd": [P] * 9 + [c_float] * 4 + [c_int] * 8 + [P],
-    "e4s_conv3x3_tcr_f32": [P] * 6 + [c_int] * 6 + [P],
+    "e4s_conv3x3_tcr_f32": [P] * 6 + [c_int] * 7 + [P],
     "e4s_set_deterministic": [c_int],
     "e4s_tcr_set_profile": [P],
     "e4s_tch_set_profile": [P],

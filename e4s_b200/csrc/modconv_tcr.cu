@@ -71,6 +71,8 @@ struct Params {
     int out_stride;
     int det;              // 1: ONE warp issues the three split-precision products in a fixed order (bit-reproducible accumulation)
     long long* prof;      // optional [5 roles][4] cycle counters of CTA 0 (e4s_tcr_set_profile); nullptr in production
+    int tap_mask;         // bit t set: tap t (row-major 3x3) is multiplied; 0 = all nine.  Taps whose weights are zero by construction
+                          // (a stride-2 convolution on a space-to-depth tensor uses 4 of 9) are neither loaded nor issued.
 };
 
 // Stall attribution (tools/opbench.py --prof): only in the diagnostic build (-DE4S_TCR_PROFILE, libe4s_b200_prof.so) -
@@ -220,6 +222,7 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ho = p.h * MUL, wo = p.w * MUL;
     const int nchunks = p.cin / KC;
+    const uint32_t tmask = p.tap_mask ? (uint32_t)p.tap_mask : 0x1FFu;
 #ifdef E4S_TCR_PROFILE
     const bool prof_on = p.prof != nullptr && blockIdx.x == 0;
     long long pw[4] = {0, 0, 0, 0};                      // [0] role time, [1..3] cycles in its barrier waits
@@ -305,6 +308,7 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                     if (load_w) {
                         // one 4-D box per tap: [hi | lo] x parities x NTC rows x KC channels = the (hi, lo) slot pair, contiguous
                         for (int tap = 0; tap < 9; ++tap) {
+                            if (!((tmask >> tap) & 1u)) continue;
                             if (!p.resident) MBAR_WAIT_P(smem_u32(&bars[B_EMPTY + slot]), ph ^ 1, 1);
                             const uint32_t full = smem_u32(&bars[B_FULL + slot]);
                             mbar_expect_tx(full, 2 * B_SLOT);
@@ -419,6 +423,7 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                         const uint32_t ap = lo_of(a_mine + sa2 * A_STAGE);
 #pragma unroll
                         for (int tap = 0; tap < 9; ++tap) {
+                            if (!((tmask >> tap) & 1u)) continue;
                             const uint32_t roff = (uint32_t)((1 + (tap / 3) * TWP + (tap % 3)) * ROWB) >> 4;   // halo pixel hp is operand row hp + 1
                             if (wait_b) {
                                 MBAR_WAIT_P(bars0 + 8 * (B_FULL + slot2), pb2, 3);
@@ -438,6 +443,7 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                 __syncwarp();
                 for (int kc = 0; kc < nchunks; ++kc) {               // the same ring arithmetic on every lane
                     for (int tap = 0; tap < 9; ++tap) {
+                        if (!((tmask >> tap) & 1u)) continue;
                         slot += 2;
                         if (slot >= p.nslot_b) slot = 0, pb ^= 1;
                     }
@@ -454,6 +460,10 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                     uint32_t roff = (uint32_t)ROWB >> 4;                   // tap (0,0): row shift 1
 #pragma unroll 1
                     for (int tap = 0; tap < 9; ++tap) {
+                        if (!((tmask >> tap) & 1u)) {
+                            roff += (uint32_t)(((tap % 3) == 2 ? (TWP - 2) : 1) * ROWB) >> 4;
+                            continue;
+                        }
                         if (wait_b) {
                             MBAR_WAIT_P(bars0 + 8 * (B_FULL + slot), pb, 3);
                             tc_fence_after();
@@ -714,6 +724,7 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
         uint32_t pacc[2] = {0, 0};
         const float nw = (p.noise && p.noise_w) ? __ldg(p.noise_w) : 0.f;
         const bool strided = (NPH == 1 && p.out_stride == 2);
+        const bool s2d = (NPH == 1 && p.out_stride == 4);        // store [B, H/2, W/2, (y & 1, x & 1, Cout)]: the next layer's stride 2 becomes 4 taps
         const int oh = strided ? (p.h >> 1) : ho, ow = strided ? (p.w >> 1) : wo;
         // Region and noise of my pixel do not depend on the accumulator, and the noise map is a streaming tensor (every
         // read is a DRAM miss): they are fetched one work item AHEAD, so that an epilogue-bound layer does not pay a DRAM
@@ -766,7 +777,8 @@ modconv3x3_tcr_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                 const int qq = UP2 ? (item.nt & 3) : q;
                 const int oy = strided ? (iy >> 1) : iy * MUL + (qq >> 1), ox = strided ? (ix >> 1) : ix * MUL + (qq & 1);
                 const float* dm = p.demod ? p.demod + ((int64_t)item.b * p.ncls + cls[q]) * p.cout + n0 : nullptr;
-                float* dst = p.y + (((int64_t)item.b * oh + oy) * ow + ox) * p.cout + n0;
+                float* dst = s2d ? p.y + (((((int64_t)item.b * (oh >> 1) + (oy >> 1)) * (ow >> 1) + (ox >> 1)) * 4 + ((oy & 1) * 2 + (ox & 1))) * p.cout + n0)
+                                 : p.y + (((int64_t)item.b * oh + oy) * ow + ox) * p.cout + n0;
 #pragma unroll 1
                 for (int j = 0; j < NTC / 32; ++j) {
                     // demodulation and bias are fetched two channel groups ahead of their use (inside a plain load -> use
@@ -1083,17 +1095,19 @@ extern "C" int e4s_modconv3x3_tcr_fwd(const float* x, const void* w_hilo_bf16, c
 
 extern "C" int e4s_conv3x3_tcr_f32(const float* x, const void* w_hilo_bf16, const float* scale, const float* shift,
                                    const float* prelu_slope, float* y, int batch, int h, int w, int cin, int cout,
-                                   int out_stride, void* stream) {
+                                   int out_stride, int tap_mask, void* stream) {
     E4S_REQUIRE(x && w_hilo_bf16 && y, E4S_ERR_ARG);
+    E4S_REQUIRE(tap_mask >= 0 && tap_mask <= 0x1FF, E4S_ERR_ARG);
     E4S_REQUIRE(batch > 0 && h > 0 && w > 0 && cin > 0 && cout > 0, E4S_ERR_ARG);
     E4S_REQUIRE((cin % 32) == 0 && (cout % 32) == 0, E4S_ERR_SHAPE);
-    E4S_REQUIRE(out_stride == 1 || (out_stride == 2 && (h % 2) == 0 && (w % 2) == 0), E4S_ERR_SHAPE);
+    E4S_REQUIRE(out_stride == 1 || ((out_stride == 2 || out_stride == 4) && (h % 2) == 0 && (w % 2) == 0), E4S_ERR_SHAPE);
     E4S_REQUIRE(e4s_aligned16(x) && e4s_aligned16(w_hilo_bf16) && e4s_aligned16(y) && (!scale || e4s_aligned16(scale)) &&
                     (!shift || e4s_aligned16(shift)) && (!prelu_slope || e4s_aligned16(prelu_slope)),
                 E4S_ERR_ALIGN);
     E4S_REQUIRE((reinterpret_cast<uintptr_t>(y) & 31) == 0, E4S_ERR_ALIGN);          // 256-bit stores
     tcr::Params p{x, scale, nullptr, nullptr, nullptr, nullptr, nullptr, y, batch, h, w, cin, cout, 1, 1, prelu_slope ? 2 : 0,
                   0, 0, 0, 0, 0, 0, shift, prelu_slope, out_stride};
+    p.tap_mask = tap_mask;
     return tcr::dispatch(w_hilo_bf16, p, 0, (cudaStream_t)stream);
 }
 

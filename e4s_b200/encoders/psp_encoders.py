@@ -5,7 +5,8 @@ reference's, so E4S checkpoints load.  ``forward`` does not run those torch modu
 on the e4s_b200 kernels -
 
 * every 3x3 convolution (and the 1x1 stride-2 shortcut convolutions, as centre-tap 3x3 kernels) on the persistent
-  tcgen05 kernel ``e4s_conv3x3_tcr_f32`` (split-bf16 x3, fp32 accumulate), stride 2 taken by keeping the even pixels;
+  tcgen05 kernel ``e4s_conv3x3_tcr_f32`` (split-bf16 x3, fp32 accumulate); a stride-2 convolution runs as four taps over the
+  space-to-depth output of the convolution before it, a 1x1 shortcut as the centre tap alone (tap mask);
 * InstanceNorm as per-(sample, channel) statistics (``e4s_instnorm_affine_f32``) folded onto the operand of the
   following convolution, PReLU in the convolution epilogue;
 * the unit tail ``0.5 * IN(conv2) + shortcut`` in one pass (``e4s_norm_residual_f32``); 0.5 is the SE gate - the
@@ -17,6 +18,8 @@ on the e4s_b200 kernels -
 Gradients through the encoder are training-only (scripts call it under ``torch.no_grad()``,
 scripts/optimization.py:178-180, scripts/face_swap.py:149) and are not provided.
 """
+import os
+
 import torch
 from torch import nn
 
@@ -38,6 +41,28 @@ def _conv_planes(weight: torch.Tensor, pad_cin_to: int = 0) -> torch.Tensor:
     return K.split_bf16(w.permute(2, 3, 0, 1).reshape(1, 9, cout, w.shape[1]))
 
 
+TAPS_S2D = 0x1B          # taps (dy, dx) in {-1, 0}^2 of a 3x3 kernel: bits 0, 1, 3, 4
+TAP_CENTRE = 0x10
+
+
+def _conv_planes_s2d(weight: torch.Tensor) -> torch.Tensor:
+    """Stride-2 3x3 convolution (padding 1) as a stride-1 kernel on the space-to-depth tensor x4[y, x, (py, px, c)] =
+    x[2y + py, 2x + px, c]: input row 2y + ky - 1 is (dy, py) = (-1, 1), (0, 0), (0, 1) for ky = 0, 1, 2 (same for columns), so
+    only the taps (dy, dx) in {-1, 0}^2 carry weights: W4[dy, dx][:, (py, px, c)] = W[:, c, ky, kx].  [Cout, Cin, 3, 3] ->
+    bf16 operand planes [2, 1, 9, Cout, 4 Cin]; the other five taps are zero and are skipped through the kernel's tap mask."""
+    w = weight.detach().float()
+    cout, cin, k, _ = w.shape
+    assert k == 3
+    w4 = w.new_zeros(9, cout, 4, cin)
+    tap_of = {0: (-1, 1), 1: (0, 0), 2: (0, 1)}           # k -> (d, parity)
+    for ky in range(3):
+        dy, py = tap_of[ky]
+        for kx in range(3):
+            dx, px = tap_of[kx]
+            w4[(dy + 1) * 3 + (dx + 1), :, py * 2 + px, :] = w[:, :, ky, kx]
+    return K.split_bf16(w4.reshape(1, 9, cout, 4 * cin))
+
+
 class FSEncoder_PSP(nn.Module):
     def __init__(self, mode="ir_se", opts=None):
         super().__init__()
@@ -49,11 +74,11 @@ class FSEncoder_PSP(nn.Module):
         self._planes = {}
 
     # ------------------------------------------------------------------------------------------ weights
-    def _prepared(self, name: str, weight: torch.Tensor, pad_cin_to: int = 0) -> torch.Tensor:
+    def _prepared(self, name: str, weight: torch.Tensor, pad_cin_to: int = 0, s2d: bool = False) -> torch.Tensor:
         key = (weight.data_ptr(), weight._version, str(weight.device))
         hit = self._planes.get(name)
         if hit is None or hit[0] != key:
-            hit = (key, _conv_planes(weight, pad_cin_to))
+            hit = (key, _conv_planes_s2d(weight) if s2d else _conv_planes(weight, pad_cin_to))
             self._planes[name] = hit
         return hit[1]
 
@@ -71,15 +96,21 @@ class FSEncoder_PSP(nn.Module):
         conv1, prelu, conv2 = unit.res_layer[1], unit.res_layer[2], unit.res_layer[3]
         stride = conv2.stride[0]
         sx, tx = K.instnorm_affine(x)                                                     # res_layer[0]
-        r = K.conv3x3_tc(x, self._prepared(f"{idx}.c1", conv1.weight), sx, tx, prelu.weight)   # conv + PReLU
-        r = K.conv3x3_tc(r, self._prepared(f"{idx}.c2", conv2.weight), out_stride=stride)
+        if stride == 2 and x.shape[1] % 2 == 0 and x.shape[2] % 2 == 0 and os.environ.get("E4S_B200_ENC_S2D", "1") != "0":
+            # true stride 2: conv1 stores its output space-to-depth, conv2 is then four taps over 4 C channels at the OUTPUT
+            # resolution (16 C Cout MACs per output instead of the 36 C Cout of "every pixel, keep the even ones")
+            r = K.conv3x3_tc(x, self._prepared(f"{idx}.c1", conv1.weight), sx, tx, prelu.weight, out_stride=4)
+            r = K.conv3x3_tc(r, self._prepared(f"{idx}.c2s", conv2.weight, s2d=True), tap_mask=TAPS_S2D)
+        else:
+            r = K.conv3x3_tc(x, self._prepared(f"{idx}.c1", conv1.weight), sx, tx, prelu.weight)   # conv + PReLU
+            r = K.conv3x3_tc(r, self._prepared(f"{idx}.c2", conv2.weight), out_stride=stride)
         s2, t2 = K.instnorm_affine(r)                                                     # res_layer[4]
         if isinstance(unit.shortcut_layer, nn.MaxPool2d):                                 # MaxPool2d(1, stride) == subsample
             return K.norm_residual(r, s2, t2, 0.5, shortcut=x, sc_stride=stride)
         # 1x1 stride-2 shortcut (helpers.py:125-131): sub-sample FIRST (a quarter of the pixels), then the centre-tap kernel at
-        # the output resolution - 4x fewer MMAs than convolving at full resolution and keeping the even pixels
+        # the output resolution (the other eight taps are masked: neither loaded nor multiplied)
         xs = x[:, ::stride, ::stride, :].contiguous() if stride > 1 else x
-        sc = K.conv3x3_tc(xs, self._prepared(f"{idx}.sc", unit.shortcut_layer[0].weight))
+        sc = K.conv3x3_tc(xs, self._prepared(f"{idx}.sc", unit.shortcut_layer[0].weight), tap_mask=TAP_CENTRE)
         ss, ts = K.instnorm_affine(sc)
         return K.norm_residual(r, s2, t2, 0.5, shortcut=sc, sc_scale=ss, sc_shift=ts, sc_stride=1)
 

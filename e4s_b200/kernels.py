@@ -426,14 +426,18 @@ def split_bf16(w: Tensor) -> Tensor:
 
 
 def conv3x3_tc(x_pm: Tensor, w_hilo: Tensor, scale: Optional[Tensor] = None, shift: Optional[Tensor] = None,
-               prelu: Optional[Tensor] = None, out_stride: int = 1) -> Tensor:
-    """x_pm [B,H,W,Cin]; w_hilo bf16 [2,1,9,Cout,Cin]; scale/shift [B,Cin]; prelu [Cout] -> [B,H/s,W/s,Cout]."""
+               prelu: Optional[Tensor] = None, out_stride: int = 1, tap_mask: int = 0) -> Tensor:
+    """x_pm [B,H,W,Cin]; w_hilo bf16 [2,1,9,Cout,Cin]; scale/shift [B,Cin]; prelu [Cout].  out_stride 1: [B,H,W,Cout]; 2: the even
+    pixels [B,H/2,W/2,Cout]; 4: space-to-depth store [B,H/2,W/2,4*Cout] (channel = (y & 1, x & 1, c)).  tap_mask: the 3x3 taps
+    (bit = row-major index) whose weights are not identically zero; 0 = all."""
     b, h, w, cin = x_pm.shape
     cout = w_hilo.shape[3]
-    y = torch.empty((b, h // out_stride, w // out_stride, cout), device=x_pm.device, dtype=torch.float32)
+    shape = (b, h, w, cout) if out_stride == 1 else (b, h // 2, w // 2, cout if out_stride == 2 else 4 * cout)
+    y = torch.empty(shape, device=x_pm.device, dtype=torch.float32)
+    ntaps = bin(tap_mask).count("1") if tap_mask else 9
     with torch.cuda.device(x_pm.device):
         _call("e4s_conv3x3_tcr_f32", _lib.load().e4s_conv3x3_tcr_f32, ptr(x_pm), ptr(w_hilo), ptr(scale), ptr(shift), ptr(prelu),
-              ptr(y), b, h, w, cin, cout, out_stride, stream_ptr(), work=2.0 * 9 * cin * cout * b * h * w)
+              ptr(y), b, h, w, cin, cout, out_stride, tap_mask, stream_ptr(), work=2.0 * ntaps * cin * cout * b * h * w)
     return y
 
 

@@ -182,13 +182,19 @@ int e4s_tcr_set_profile(long long* device_counters);
 int e4s_tch_set_profile(long long* device_counters);
 
 /* ---- RGI encoder conv stack (src/models/encoders/helpers.py:122-144, psp_encoders.py:285-309) ------------------
- * Plain 3x3 convolution, padding 1, stride 1 or 2 (out_stride), on the persistent tensor-core kernel.
+ * Plain 3x3 convolution, padding 1, on the persistent tensor-core kernel.
  * x: pixel-major [B, H, W, Cin]; w_hilo_bf16: [2][1][9][Cout][Cin]; scale/shift: optional per-(sample, channel)
  * affine [B, Cin] applied to in-image pixels while staging (InstanceNorm folded onto the operand; zero padding
- * stays zero); prelu_slope: optional [Cout] PReLU epilogue; y: [B, H/out_stride, W/out_stride, Cout]. */
+ * stays zero); prelu_slope: optional [Cout] PReLU epilogue.
+ * out_stride 1: y [B, H, W, Cout].  2: every pixel is computed, the even ones are stored, y [B, H/2, W/2, Cout].
+ * 4: space-to-depth store, y [B, H/2, W/2, 4 Cout] with channel (y & 1, x & 1, c) - what the NEXT layer wants when it is a
+ *    stride-2 convolution (helpers.py:138: conv2 of the first unit of a stage): on that tensor the stride-2 kernel is a
+ *    stride-1 kernel over 4 Cin channels of which only the taps (dy, dx) in {-1, 0}^2 are non-zero.
+ * tap_mask: bit t (row-major 3x3) set = tap t is multiplied, 0 = all nine; masked taps are neither loaded nor issued
+ *    (their weights must be zero for the result to be the full convolution).  0x1B = the four taps of the case above. */
 int e4s_conv3x3_tcr_f32(const float* x, const void* w_hilo_bf16, const float* scale, const float* shift,
                         const float* prelu_slope, float* y, int batch, int h, int w, int cin, int cout, int out_stride,
-                        void* stream);
+                        int tap_mask, void* stream);
 /* InstanceNorm2d statistics (biased variance, eps) of a pixel-major tensor as an affine: scale = rstd,
  * shift = -mean*rstd, both [B, C].  sums_ws: [B, C, 2] workspace. */
 int e4s_instnorm_affine_f32(const float* x, float* sums_ws, float* scale, float* shift, int batch, int h, int w, int c,

@@ -238,3 +238,21 @@ def test_generator_style_schedule_follows_the_reference_latent_indexing(size, K)
             assert mod.mask_op or not per_region
         i += 2
     assert i + 1 == G.n_latent
+
+
+def test_encoder_stride2_weights_on_space_to_depth_equal_the_strided_convolution():
+    """encoders/psp_encoders.py:_conv_planes_s2d: a stride-2 3x3 convolution = a stride-1 convolution of the space-to-depth
+    tensor with the re-indexed weights, of which exactly the taps 0, 1, 3, 4 are non-zero (host arithmetic only)."""
+    import torch.nn.functional as F
+    from e4s_b200.encoders.psp_encoders import _conv_planes_s2d, TAPS_S2D
+    g = torch.Generator().manual_seed(0)
+    w = torch.randn(8, 4, 3, 3, generator=g)
+    x = torch.randn(2, 4, 10, 12, generator=g)
+    planes = _conv_planes_s2d(w)
+    w4 = (planes[0].float() + planes[1].float())[0]                     # [9, Cout, 4 C]: bf16 hi + lo ~ fp32 to 2^-16
+    assert [bool(w4[t].abs().max() > 0) for t in range(9)] == [bool((TAPS_S2D >> t) & 1) for t in range(9)]
+    b, c, h, wd = x.shape
+    x4 = x.permute(0, 2, 3, 1).reshape(b, h // 2, 2, wd // 2, 2, c).permute(0, 1, 3, 2, 4, 5).reshape(b, h // 2, wd // 2, 4 * c)
+    out = F.conv2d(x4.permute(0, 3, 1, 2), w4.reshape(3, 3, 8, 4 * c).permute(2, 3, 0, 1), padding=1)
+    ref = F.conv2d(x, w, stride=2, padding=1)
+    assert float((out - ref).abs().max()) < 1e-4 * float(ref.abs().max())

@@ -667,6 +667,37 @@ def test_encoder_building_blocks():
     assert_close(out, ref, 1e-6, "unit tail")
 
 
+@pytest.mark.parametrize("b,cin,cout,h,w", [(2, 64, 64, 24, 20), (1, 128, 128, 34, 30), (2, 32, 96, 16, 16)])
+def test_encoder_stride2_as_four_taps_on_space_to_depth(b, cin, cout, h, w):
+    """helpers.py:138 (conv2 of the first unit of a stage, stride 2): conv1 stores its IN -> conv -> PReLU output space-to-depth
+    (out_stride 4), conv2 runs as the taps (dy, dx) in {-1, 0}^2 over 4 C channels at the output resolution (tap mask 0x1B) -
+    against torch's stride-2 convolution in fp64; and a 1x1 convolution as the centre tap alone (tap mask 0x10)."""
+    import torch.nn.functional as F
+    from e4s_b200 import kernels as K
+    from e4s_b200.encoders.psp_encoders import _conv_planes, _conv_planes_s2d, TAPS_S2D, TAP_CENTRE
+    g = torch.Generator().manual_seed(b + cin + h)
+    x = torch.randn(b, cin, h, w, generator=g) * 1.5 + 0.3
+    w1 = torch.randn(cin, cin, 3, 3, generator=g) / (3.0 * cin ** 0.5)
+    w2 = torch.randn(cout, cin, 3, 3, generator=g) / (3.0 * cin ** 0.5)
+    slope = 0.25 + 0.05 * torch.randn(cin, generator=g)
+    xpm = cu(x).permute(0, 2, 3, 1).contiguous()
+    sc, sh = K.instnorm_affine(xpm)
+    mid = K.conv3x3_tc(xpm, _conv_planes(cu(w1)), sc, sh, cu(slope), out_stride=4)
+    assert tuple(mid.shape) == (b, h // 2, w // 2, 4 * cin)
+    ref_mid = F.prelu(F.conv2d(F.instance_norm(x.double(), eps=1e-5), w1.double(), padding=1), slope.double())
+    s2d = ref_mid.permute(0, 2, 3, 1).reshape(b, h // 2, 2, w // 2, 2, cin).permute(0, 1, 3, 2, 4, 5).reshape(b, h // 2, w // 2, 4 * cin)
+    assert_close(mid, s2d.float(), 1e-4, "conv1 with the space-to-depth store")
+    y = K.conv3x3_tc(mid, _conv_planes_s2d(cu(w2)), tap_mask=TAPS_S2D)
+    ref = F.conv2d(ref_mid, w2.double(), stride=2, padding=1)
+    assert_close(y.permute(0, 3, 1, 2), ref.float(), 1e-4, "stride-2 conv as four taps")
+    old = K.conv3x3_tc(K.conv3x3_tc(xpm, _conv_planes(cu(w1)), sc, sh, cu(slope)), _conv_planes(cu(w2)), out_stride=2)
+    assert_close(y, old, 1e-4, "four-tap form vs every-pixel-keep-even form")
+    wsc = torch.randn(cout, cin, 1, 1, generator=g) / cin ** 0.5
+    xs = xpm[:, ::2, ::2, :].contiguous()
+    ysc = K.conv3x3_tc(xs, _conv_planes(cu(wsc)), tap_mask=TAP_CENTRE)
+    assert_close(ysc.permute(0, 3, 1, 2), F.conv2d(x.double()[:, :, ::2, ::2], wsc.double()).float(), 1e-4, "1x1 conv as the centre tap")
+
+
 def test_generator_1024_tensor_core_path_matches_exact_fp32_path(monkeypatch):
     """BASELINE's full size (1024x1024, K=13, 12 regions, one face): every layer on the tensor-core kernel against every
     layer on the exact-fp32 SIMT kernel (which the 32/64/256 goldens pin to the reference).  Size-independent property:
