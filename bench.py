@@ -278,20 +278,26 @@ def gpu_baseline_leg(net, size: int, ncls: int, batch: int, dev):
     return out
 
 
+_PROBE_BEST_S = {}
+
+
 def pick_cpu_threads(ncls: int, probe: int = 256) -> int:
     """torch's default (one thread per logical core) oversubscribes this path's convolutions on many-core hosts; give the CPU
-    arm its best setting: try a few thread counts on a 256x256 forward (convolutions of the size class that dominates the
-    timed 1024x1024 face: a 64x64 probe, as in round 1, favoured too few threads) and keep the fastest."""
+    arm its best setting: one 256x256 forward (convolutions of the size class that dominates the timed 1024x1024 face: a
+    64x64 probe, as in round 1, favoured too few threads) per candidate thread count, after a 64x64 warm-up of the thread
+    pool, and keep the fastest.  Candidates 16 / 32 / 64 (8 and all-cores lost every probe of this round's runs and all-cores
+    alone could take a minute): the probe has to leave the default bench run within minutes."""
     ncpu = os.cpu_count() or 1
-    cands = sorted({c for c in (8, 16, 32, 64, 96, ncpu) if c <= ncpu})
+    cands = sorted({c for c in (16, 32, 64) if c <= ncpu}) or [ncpu]
     best, best_t, state = cands[-1], float("inf"), None
     for c in cands:
         torch.set_num_threads(c)
-        _, state, _ = cpu_reference_face(probe, ncls, state)
+        cpu_reference_face(64, ncls)
         dt, state, _ = cpu_reference_face(probe, ncls, state, seed=3)
         if dt < best_t:
             best, best_t = c, dt
     torch.set_num_threads(best)
+    _PROBE_BEST_S[probe] = best_t
     return best
 
 
@@ -328,6 +334,7 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------------ our arm
 def run_ours(args):
+    t_run0 = time.perf_counter()
     import torch.distributed as dist
     from e4s_b200 import kernels as K
     from e4s_b200.dist import gather_images
@@ -432,6 +439,15 @@ def run_ours(args):
     eager = {"value": faces / (ms_eager * 1e-3), "ms_per_step": ms_eager / args.steps, "gpu_launches": launches_eager,
              "ms_per_step_with_per_launch_events": ms_inst / args.steps}
 
+    leg_s, _t_leg = {}, [t_run0]
+
+    def leg_done(name):                                   # wall-clock seconds per section of this run (host side; for the record)
+        torch.cuda.synchronize()
+        now = time.perf_counter()
+        leg_s[name] = round(now - _t_leg[0], 1)
+        _t_leg[0] = now
+
+    leg_done("setup+value+eager passes")
     e2e = None
     if not args.no_e2e:
         ms2, _, _, _ = timed(step_e2e, args.steps, max(args.warmup, 3), finish=pipe.drain)
@@ -441,6 +457,7 @@ def run_ours(args):
                "api": "e4s_b200.pipeline.SynthesisPipeline.submit (3 streams, depth 2" + (")" if args.eager else ", forward as one CUDA graph)")}
 
     # ---- the path's only collective: all-gather of the final images, alone and overlapped with the next step
+    leg_done("e2e")
     gather = None
     if world > 1:
         with torch.no_grad():
@@ -521,6 +538,7 @@ def run_ours(args):
                             "this fraction (ncu sm__pipe_tensor_cycles_active in profiles/)"}
 
     # ---- BASELINE configs[2]: regional latent optimisation of one face per GPU (forward + backward + Adam per step)
+    leg_done("gather+roofline")
     inversion = None
     if args.inversion_steps > 0:
         from e4s_b200.optimization import invert
@@ -665,6 +683,7 @@ def run_ours(args):
                      "config": f"one {size}x{size} face per GPU, {ncls} regions, Adam lr 1e-2, l2 loss, fresh noise per step"}
 
     # ---- BASELINE configs[3]: face swapping, steps 3-5 of scripts/face_swap.py on (driven, target) pairs, sharded like faces
+    leg_done("inversion")
     faceswap = None
     if args.faceswap_pairs > 0:
         try:
@@ -700,6 +719,7 @@ def run_ours(args):
             faceswap = {"error": repr(exc)[:300]}
 
     # ---- GPEN's generator on the same kernels (512x512 restoration, stage 2 of every swap)
+    leg_done("faceswap")
     gpen = None
     if args.gpen_batch > 0:
         try:
@@ -735,6 +755,7 @@ def run_ours(args):
         except Exception as exc:                                      # reported, never hidden
             gpen = {"error": repr(exc)[:300]}
 
+    leg_done("gpen")
     gpu_base = None
     if rank == 0 and world == 1 and not args.no_gpu_baseline:
         try:
@@ -746,6 +767,7 @@ def run_ours(args):
         except Exception as exc:                                      # reported, never hidden
             gpu_base = {"error": repr(exc)[:300]}
 
+    leg_done("gpu_baseline")
     cpu, parity = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         pick_cpu_threads(ncls)                                        # also warms the thread pool / allocator
@@ -769,13 +791,14 @@ def run_ours(args):
                   "in_batch_max_rel": float(db.abs().max()) / ref_max, "in_batch_rel_rms": float(db.pow(2).mean().sqrt()) / ref_rms,
                   "tolerance": 1e-3}
         del gpu_img, batch_img
-        dt256 = min(cpu_reference_face(256, ncls)[0] for _ in range(2)) if size != 256 else dt      # BASELINE configs[0]'s size
+        dt256 = _PROBE_BEST_S.get(256) or cpu_reference_face(256, ncls)[0]      # BASELINE configs[0]'s size: the probe's best run
         cpu = {"value": 1.0 / dt, "unit": "faces/s", "cores": torch.get_num_threads(), "kind": "port",
                "value_256x256": 1.0 / dt256,
                "host_logical_cpus": os.cpu_count(),
                "sample": f"one full {size}x{size} face (B=1, {ncls} regions, K=13) through the reference-structured CPU "
-                         f"oracle (fp32, torch CPU; thread count = fastest of 8/16/32/64/96/all on a 256x256 probe)"}
+                         f"oracle (fp32, torch CPU; thread count = fastest of 16/32/64 on a 256x256 probe)"}
 
+    leg_done("cpu_baseline+parity")
     if rank == 0:
         line = {"metric": METRIC.format(size=args.size, ncls=args.ncls), "value": value, "unit": "faces/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -789,7 +812,7 @@ def run_ours(args):
                                            + (" + NCCL all-gather of the final images" if args.gather else "")) if world > 1 else "single GPU"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "eager": eager, "roofline": roofline, "cpu_baseline": cpu,
                 f"parity_{size}": parity, "gpu_baseline": gpu_base, "gather": gather,
-                "kernels": kernels, "hbm_peak_gbs": hbm_gbs, "inversion": inversion, "faceswap": faceswap, "gpen": gpen}
+                "kernels": kernels, "leg_seconds": leg_s, "hbm_peak_gbs": hbm_gbs, "inversion": inversion, "faceswap": faceswap, "gpen": gpen}
         emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
